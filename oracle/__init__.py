@@ -1,0 +1,410 @@
+"""CPU oracle for phase_b200 -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end over oracle/phase_oracle.c (our flat-array restatement of the
+reference's hot path) and, when available, oracle/_ref (the reference's own
+``src/Math`` translation units compiled in place).  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import
+this package; the product (``phase_b200``) never does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+FIXED, NORMAL_GRADIENT, SYMMETRY = 0, 1, 2
+
+_lib = None
+_ref = None
+
+SOLVE_CB = C.CFUNCTYPE(C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                       C.POINTER(C.c_double), C.POINTER(C.c_double),
+                       C.POINTER(C.c_double), C.c_void_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = _build.ORACLE_SO
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(
+                os.path.join(_build.HERE, "phase_oracle.c")):
+            so = _build.build_oracle()
+        L = C.CDLL(so)
+        vp = C.c_void_p
+        L.or_mesh_create.restype = vp
+        L.or_mesh_create.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int,
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        for f in (L.or_mesh_rectilinear, L.or_mesh_triangulated):
+            f.restype = vp
+            f.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
+        L.or_mesh_destroy.argtypes = [vp]
+        L.or_mesh_add_patch_by_nodes.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+        L.or_mesh_patch_id.argtypes = [vp, C.c_char_p]
+        L.or_mesh_array.restype = C.c_long
+        L.or_mesh_array.argtypes = [vp, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+        L.or_mesh_partition_local.restype = vp
+        L.or_mesh_partition_local.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.c_int]
+        L.or_mesh_init_comm.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.or_crs_create.restype = vp
+        L.or_crs_create.argtypes = [C.c_int, C.c_int]
+        L.or_crs_clone.restype = vp
+        L.or_crs_clone.argtypes = [vp]
+        L.or_crs_destroy.argtypes = [vp]
+        L.or_crs_add_coeff.argtypes = [vp, C.c_int, C.c_int, C.c_double]
+        L.or_crs_set_coeff.argtypes = [vp, C.c_int, C.c_int, C.c_double]
+        L.or_crs_add_rhs.argtypes = [vp, C.c_int, C.c_double]
+        L.or_crs_scale_row.argtypes = [vp, C.c_int, C.c_double]
+        L.or_crs_add_eq.argtypes = [vp, vp]
+        L.or_crs_sub_eq.argtypes = [vp, vp]
+        L.or_crs_sub_vec.argtypes = [vp, C.POINTER(C.c_double)]
+        L.or_crs_add_vec.argtypes = [vp, C.POINTER(C.c_double)]
+        L.or_crs_scale.argtypes = [vp, C.c_double]
+        L.or_crs_rank.argtypes = [vp]
+        L.or_crs_nnz.argtypes = [vp]
+        L.or_crs_export.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.or_fs_create.restype = vp
+        L.or_fs_create.argtypes = [vp, C.c_double, C.c_double]
+        L.or_fs_destroy.argtypes = [vp]
+        L.or_fs_set_bc.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_double]
+        L.or_fs_initialize.argtypes = [vp]
+        L.or_fs_set_solver.argtypes = [vp, SOLVE_CB, vp]
+        L.or_fs_set_solver_params.argtypes = [vp, C.c_double, C.c_int, C.c_int]
+        L.or_fs_step.argtypes = [vp, C.c_double]
+        L.or_fs_assemble_u.argtypes = [vp, C.c_double]
+        L.or_fs_assemble_p.argtypes = [vp, C.c_double]
+        L.or_fs_ueqn.restype = vp
+        L.or_fs_ueqn.argtypes = [vp]
+        L.or_fs_peqn.restype = vp
+        L.or_fs_peqn.argtypes = [vp]
+        L.or_fs_array.restype = C.c_long
+        L.or_fs_array.argtypes = [vp, C.c_char_p, C.POINTER(C.POINTER(C.c_double))]
+        L.or_fs_max_divergence.restype = C.c_double
+        L.or_fs_max_divergence.argtypes = [vp]
+        L.or_fs_max_courant.restype = C.c_double
+        L.or_fs_max_courant.argtypes = [vp, C.c_double]
+        L.or_fs_last_iters.argtypes = [vp, C.c_int]
+        L.or_op_laplacian_field.restype = vp
+        L.or_op_laplacian_field.argtypes = [vp, C.POINTER(C.c_double)]
+        L.or_bicgstab.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int,
+                                  C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+def ref_lib():
+    """The reference's own CrsEquation algebra (oracle/_ref) or None."""
+    global _ref
+    if _ref is None:
+        so = _build.build_ref()
+        if so is None:
+            return None
+        R = C.CDLL(so)
+        vp = C.c_void_p
+        R.ref_crs_create.restype = vp
+        R.ref_crs_create.argtypes = [C.c_int, C.c_int]
+        R.ref_crs_clone.restype = vp
+        R.ref_crs_clone.argtypes = [vp]
+        R.ref_crs_destroy.argtypes = [vp]
+        R.ref_crs_add_coeff.argtypes = [vp, C.c_int, C.c_int, C.c_double]
+        R.ref_crs_set_coeff.argtypes = [vp, C.c_int, C.c_int, C.c_double]
+        R.ref_crs_add_rhs.argtypes = [vp, C.c_int, C.c_double]
+        R.ref_crs_scale_row.argtypes = [vp, C.c_int, C.c_double]
+        R.ref_crs_add_eq.argtypes = [vp, vp]
+        R.ref_crs_sub_eq.argtypes = [vp, vp]
+        R.ref_crs_sub_vec.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
+        R.ref_crs_scale.argtypes = [vp, C.c_double]
+        R.ref_crs_rank.argtypes = [vp]
+        R.ref_crs_nnz.argtypes = [vp]
+        R.ref_crs_export.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        R.ref_crs_solve_handoff.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                            C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _ref = R
+    return _ref
+
+
+class Mesh:
+    """Flat mesh in the reference's numbering (I1, I2, G1-G4)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def create(cls, xy, cptr, cind):
+        xy = np.ascontiguousarray(xy, dtype=np.float64)
+        cptr = np.ascontiguousarray(cptr, dtype=np.int32)
+        cind = np.ascontiguousarray(cind, dtype=np.int32)
+        return cls(lib().or_mesh_create(len(xy), _dp(xy), len(cptr) - 1, _ip(cptr), _ip(cind)))
+
+    @classmethod
+    def rectilinear(cls, nx, ny, width=1.0, height=1.0):
+        return cls(lib().or_mesh_rectilinear(nx, ny, width, height))
+
+    @classmethod
+    def triangulated(cls, nx, ny, width=1.0, height=1.0):
+        return cls(lib().or_mesh_triangulated(nx, ny, width, height))
+
+    def add_patch_by_nodes(self, name, pairs):
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1)
+        return lib().or_mesh_add_patch_by_nodes(self.h, name.encode(), len(pairs) // 2, _ip(pairs))
+
+    def patch_id(self, name):
+        return lib().or_mesh_patch_id(self.h, name.encode())
+
+    def array(self, name):
+        ptr = C.c_void_p()
+        isd = C.c_int()
+        n = lib().or_mesh_array(self.h, name.encode(), C.byref(ptr), C.byref(isd))
+        if n < 0:
+            raise KeyError(name)
+        if n == 0:
+            return np.zeros(0, dtype=np.float64 if isd.value else np.int32)
+        ct = C.c_double if isd.value else C.c_int
+        buf = C.cast(ptr, C.POINTER(ct * n)).contents
+        return np.frombuffer(buf, dtype=np.float64 if isd.value else np.int32).copy()
+
+    @property
+    def sizes(self):
+        s = self.array("sizes")
+        return dict(nNodes=int(s[0]), nCells=int(s[1]), nFaces=int(s[2]), nPatches=int(s[3]),
+                    rank=int(s[4]), nProcs=int(s[5]), nLocal=int(s[6]), rowOffset=int(s[7]))
+
+    def partition(self, part, nprocs):
+        """All local meshes + halo maps for a given cell-partition vector (I5)."""
+        part = np.ascontiguousarray(part, dtype=np.int32)
+        locs = [Mesh(lib().or_mesh_partition_local(self.h, _ip(part), r, nprocs))
+                for r in range(nprocs)]
+        arr = (C.c_void_p * nprocs)(*[m.h for m in locs])
+        lib().or_mesh_init_comm(arr, nprocs)
+        return locs
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().or_mesh_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class _CrsBase:
+    def export(self):
+        n, nnz = self.rank(), self.nnz()
+        rp = np.zeros(n + 1, np.int32)
+        ci = np.zeros(max(nnz, 1), np.int32)
+        va = np.zeros(max(nnz, 1), np.float64)
+        rhs = np.zeros(max(n, 1), np.float64)
+        self._export(rp, ci, va, rhs)
+        return rp, ci[:nnz], va[:nnz], rhs[:n]
+
+
+class Crs(_CrsBase):
+    """Our restatement of CrsEquation (M/CrsEquation.cpp)."""
+
+    def __init__(self, n=None, nnz=5, handle=None, own=True):
+        self.h = handle if handle is not None else lib().or_crs_create(n, nnz)
+        self.own = own
+
+    def clone(self):
+        return Crs(handle=lib().or_crs_clone(self.h))
+
+    def add_coeff(self, r, c, v): lib().or_crs_add_coeff(self.h, r, c, v)
+    def set_coeff(self, r, c, v): lib().or_crs_set_coeff(self.h, r, c, v)
+    def add_rhs(self, r, v): lib().or_crs_add_rhs(self.h, r, v)
+    def scale_row(self, r, v): lib().or_crs_scale_row(self.h, r, v)
+    def add_eq(self, o): lib().or_crs_add_eq(self.h, o.h)
+    def sub_eq(self, o): lib().or_crs_sub_eq(self.h, o.h)
+
+    def sub_vec(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        lib().or_crs_sub_vec(self.h, _dp(v))
+
+    def scale(self, s): lib().or_crs_scale(self.h, s)
+    def rank(self): return lib().or_crs_rank(self.h)
+    def nnz(self): return lib().or_crs_nnz(self.h)
+    def _export(self, rp, ci, va, rhs): lib().or_crs_export(self.h, _ip(rp), _ip(ci), _dp(va), _dp(rhs))
+
+    def __del__(self):
+        try:
+            if self.own and self.h:
+                lib().or_crs_destroy(self.h)
+        except Exception:
+            pass
+
+
+class RefCrs(_CrsBase):
+    """The reference's own CrsEquation (compiled in place, oracle/_ref)."""
+
+    def __init__(self, n=None, nnz=5, handle=None):
+        self.h = handle if handle is not None else ref_lib().ref_crs_create(n, nnz)
+
+    def clone(self):
+        return RefCrs(handle=ref_lib().ref_crs_clone(self.h))
+
+    def add_coeff(self, r, c, v): ref_lib().ref_crs_add_coeff(self.h, r, c, v)
+    def set_coeff(self, r, c, v): ref_lib().ref_crs_set_coeff(self.h, r, c, v)
+    def add_rhs(self, r, v): ref_lib().ref_crs_add_rhs(self.h, r, v)
+    def scale_row(self, r, v): ref_lib().ref_crs_scale_row(self.h, r, v)
+    def add_eq(self, o): ref_lib().ref_crs_add_eq(self.h, o.h)
+    def sub_eq(self, o): ref_lib().ref_crs_sub_eq(self.h, o.h)
+
+    def sub_vec(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        ref_lib().ref_crs_sub_vec(self.h, _dp(v), len(v))
+
+    def scale(self, s): ref_lib().ref_crs_scale(self.h, s)
+    def rank(self): return ref_lib().ref_crs_rank(self.h)
+    def nnz(self): return ref_lib().ref_crs_nnz(self.h)
+    def _export(self, rp, ci, va, rhs): ref_lib().ref_crs_export(self.h, _ip(rp), _ip(ci), _dp(va), _dp(rhs))
+
+    def solve_handoff(self):
+        n, nnz = self.rank(), self.nnz()
+        rp = np.zeros(n + 1, np.int32)
+        ci = np.zeros(max(nnz, 1), np.int32)
+        va = np.zeros(max(nnz, 1), np.float64)
+        b = np.zeros(max(n, 1), np.float64)
+        ref_lib().ref_crs_solve_handoff(self.h, _ip(rp), _ip(ci), _dp(va), _dp(b))
+        return rp, ci[:nnz], va[:nnz], b[:n]
+
+    def __del__(self):
+        try:
+            if self.h:
+                ref_lib().ref_crs_destroy(self.h)
+        except Exception:
+            pass
+
+
+def csr_to_scipy(rp, ci, va, n=None):
+    """CSR with -1 padding (what SparseMatrixSolver::set receives) -> scipy."""
+    import scipy.sparse as sp
+    n = len(rp) - 1 if n is None else n
+    rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+    keep = ci >= 0
+    return sp.csr_matrix((va[keep], (rows[keep], ci[keep])), shape=(len(rp) - 1, n))
+
+
+def direct_solve(rp, ci, va, b):
+    """Exact sparse LU (SuperLU): stand-in for the snapshot's Eigen SparseLU
+    (M/EigenSparseMatrixSolver.cpp:60-64).  Singular all-Neumann systems are
+    regularised by pinning the constant mode (hard part 3)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    A = csr_to_scipy(rp, ci, va).tocsc()
+    n = A.shape[0]
+    rs = np.abs(A @ np.ones(n)).max()
+    if rs < 1e-12 * np.abs(A.diagonal()).max():
+        # constant null space: bordered system  [A 1; 1^T 0]
+        one = sp.csc_matrix(np.ones((n, 1)))
+        K = sp.bmat([[A, one], [one.T, None]], format="csc")
+        x = spl.splu(K).solve(np.concatenate([b, [0.0]]))
+        return x[:n]
+    return spl.splu(A).solve(b)
+
+
+class FracStep:
+    """FractionalStep::solve restated (US/FractionalStep.cpp)."""
+
+    def __init__(self, mesh, rho=1.0, mu=1.0):
+        self.mesh = mesh
+        self.h = lib().or_fs_create(mesh.h, rho, mu)
+        self._cb = None
+
+    def set_bc(self, field, patch, type_, vx=0.0, vy=0.0):
+        rc = lib().or_fs_set_bc(self.h, field.encode(), patch.encode(), type_, vx, vy)
+        if rc:
+            raise ValueError("bad bc %s %s" % (field, patch))
+
+    def initialize(self):
+        lib().or_fs_initialize(self.h)
+
+    def use_direct_solver(self):
+        def cb(n, rp, ci, va, b, x, user):
+            rp_ = np.ctypeslib.as_array(rp, (n + 1,))
+            nnz = int(rp_[n])
+            ci_ = np.ctypeslib.as_array(ci, (nnz,))
+            va_ = np.ctypeslib.as_array(va, (nnz,))
+            b_ = np.ctypeslib.as_array(b, (n,))
+            x_ = np.ctypeslib.as_array(x, (n,))
+            x_[:] = direct_solve(rp_, ci_, va_, b_)
+            return 1
+        self._cb = SOLVE_CB(cb)
+        lib().or_fs_set_solver(self.h, self._cb, None)
+
+    def set_solver_params(self, tol=1e-10, max_iters=20000, precond=1):
+        lib().or_fs_set_solver_params(self.h, tol, max_iters, precond)
+
+    def step(self, dt):
+        return lib().or_fs_step(self.h, dt)
+
+    def assemble_u(self, dt):
+        lib().or_fs_assemble_u(self.h, dt)
+        return Crs(handle=lib().or_fs_ueqn(self.h), own=False)
+
+    def assemble_p(self, dt):
+        lib().or_fs_assemble_p(self.h, dt)
+        return Crs(handle=lib().or_fs_peqn(self.h), own=False)
+
+    def laplacian_field(self, gamma_face):
+        g = np.ascontiguousarray(gamma_face, dtype=np.float64)
+        return Crs(handle=lib().or_op_laplacian_field(self.h, _dp(g)))
+
+    def view(self, name):
+        """Writable numpy view of a field array (ux, uy, ufx, ufy, p, pf, gpx, ...)."""
+        ptr = C.POINTER(C.c_double)()
+        n = lib().or_fs_array(self.h, name.encode(), C.byref(ptr))
+        if n < 0:
+            raise KeyError(name)
+        return np.ctypeslib.as_array(ptr, (n,))
+
+    def max_divergence(self):
+        return lib().or_fs_max_divergence(self.h)
+
+    def max_courant(self, dt):
+        return lib().or_fs_max_courant(self.h, dt)
+
+    def last_iters(self, which):
+        return lib().or_fs_last_iters(self.h, which)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().or_fs_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def bicgstab(rp, ci, va, b, x0=None, tol=1e-8, max_iters=10000, precond=1):
+    rp = np.ascontiguousarray(rp, np.int32)
+    ci = np.ascontiguousarray(ci, np.int32)
+    va = np.ascontiguousarray(va, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    x = np.zeros_like(b) if x0 is None else np.array(x0, dtype=np.float64)
+    rr = C.c_double()
+    it = lib().or_bicgstab(len(b), _ip(rp), _ip(ci), _dp(va), _dp(b), _dp(x), tol, max_iters,
+                           precond, C.byref(rr))
+    return x, it, rr.value
+
+
+def cavity(mesh, rho=1.0, mu=0.1, lid=1.0):
+    """Lid-driven cavity BCs of Examples/LidDrivenCavity/case/boundaries.info."""
+    fs = FracStep(mesh, rho, mu)
+    for pt in ("x-", "x+", "y-"):
+        fs.set_bc("u", pt, FIXED, 0.0, 0.0)
+    fs.set_bc("u", "y+", FIXED, lid, 0.0)
+    for pt in ("x-", "x+", "y-", "y+"):
+        fs.set_bc("p", pt, NORMAL_GRADIENT, 0.0)
+    fs.initialize()
+    return fs
