@@ -1,0 +1,238 @@
+/*
+ * phase_b200.h -- C ABI of libphase_b200.so: the B200-native implementation of
+ * Phase's per-time-step linear-system path (fv:: operator assembly into a CSR
+ * FiniteVolumeEquation, then the BiCGStab solve), hand-written CUDA for sm_100a.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative phb_status on failure and
+ *     never throws; phb_last_error() gives the text (thread-local).
+ *   - every pointer argument is CALLER-OWNED HOST memory unless the name says
+ *     "device"; calls are synchronous from one host thread per context.
+ *   - Scalar = double, Index = int32 (reference: src/Types/Types.h:7-10).
+ *   - an equation is stored as  A x + rhs = 0  and the solver receives b = -rhs
+ *     (reference: UE/FiniteVolumeEquation.tpp:71-73, M/CrsEquation.cpp:169-175).
+ *
+ * Reference paths below are relative to /root/reference/src; UG = 2D/Unstructured/
+ * FiniteVolumeGrid2D, UF = 2D/Unstructured/FiniteVolume/Field, UD = .../Discretization,
+ * UE = .../Equation, US = 2D/Unstructured/Solvers, M = Math.
+ */
+#ifndef PHASE_B200_H
+#define PHASE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  PHB_OK = 0,
+  PHB_ERR_ARG = -1,        /* bad argument / unknown key / size mismatch */
+  PHB_ERR_CUDA = -2,       /* CUDA runtime error */
+  PHB_ERR_COMM = -3,       /* NCCL error */
+  PHB_ERR_BREAKDOWN = -4,  /* Krylov breakdown (rho or omega = 0, non-finite) */
+  PHB_ERR_NOT_CONVERGED = -5,
+  PHB_ERR_UNSUPPORTED = -6,
+  PHB_ERR_STATE = -7       /* call order (e.g. solve before set) */
+} phb_status;
+
+/* boundary types: UF/FiniteVolumeField.h:12 enum BoundaryType */
+enum { PHB_FIXED = 0, PHB_NORMAL_GRADIENT = 1, PHB_SYMMETRY = 2 };
+/* preconditioners */
+enum { PHB_PC_NONE = 0, PHB_PC_JACOBI = 1, PHB_PC_ILU0 = 2 };
+
+typedef struct phb_ctx phb_ctx;
+typedef struct phb_mesh phb_mesh;
+typedef struct phb_solver phb_solver;
+typedef struct phb_field phb_field;
+typedef struct phb_eqn phb_eqn;
+typedef struct phb_fracstep phb_fracstep;
+
+const char *phb_last_error(void);
+int phb_version(void);
+
+/* ------------------------------------------------------------------ context
+ * One context = one GPU + its streams (+ an NCCL communicator for nProcs>1).
+ * Replaces: S/Communicator.{h,cpp} (MPI_Init, rank/nProcs, point-to-point and
+ * all-reduce used around the solve, S/Communicator.cpp:11-17,81-141). */
+int phb_ctx_create(int device, phb_ctx **out);
+int phb_ctx_destroy(phb_ctx *ctx);
+/* 128-byte NCCL unique id made on rank 0, shipped by the host launcher */
+int phb_comm_unique_id(void *out128);
+int phb_ctx_init_comm(phb_ctx *ctx, int rank, int nProcs, const void *id128);
+int phb_ctx_rank(const phb_ctx *ctx);
+int phb_ctx_nprocs(const phb_ctx *ctx);
+int phb_ctx_sync(phb_ctx *ctx);
+/* number of kernels this library launched on the context so far */
+long long phb_ctx_kernel_launches(const phb_ctx *ctx);
+/* raw stream handle (cudaStream_t) the kernels run on, for CUDA-event timing */
+void *phb_ctx_stream(phb_ctx *ctx);
+
+/* --------------------------------------------------------------------- mesh
+ * Host-side build of connectivity + geometry, flattened to SoA and uploaded.
+ * Replaces: FiniteVolumeGrid2D::init(nodes,cptr,cind) + createCell + init()
+ * (UG/FiniteVolumeGrid2D.cpp:20-35,84-114,396-450), Face/Cell/Link geometry
+ * (UG/Face/Face.cpp:9-18,48-64; UG/Cell/Cell.cpp:8-29; UG/Link/ *.cpp),
+ * StructuredRectilinearGrid::init/initPatches (UG/StructuredRectilinearGrid.cpp:40-95,175-194),
+ * createPatchByNodes (UG/FiniteVolumeGrid2D.cpp:182-198). */
+int phb_mesh_create(phb_ctx *ctx, int nNodes, const double *xy, int nCells,
+                    const int *cptr, const int *cind, phb_mesh **out);
+int phb_mesh_create_rectilinear(phb_ctx *ctx, int nx, int ny, double width,
+                                double height, phb_mesh **out);
+/* synthetic unstructured variant: every quad split along alternating diagonals */
+int phb_mesh_create_triangulated(phb_ctx *ctx, int nx, int ny, double width,
+                                 double height, phb_mesh **out);
+int phb_mesh_add_patch_by_nodes(phb_mesh *m, const char *name, int nPairs,
+                                const int *nodePairs);
+int phb_mesh_patch_id(const phb_mesh *m, const char *name);
+/* build links, canonical CSR pattern, face->slot map; upload.  Must be called
+ * once after the patches are defined and before any field/equation is made. */
+int phb_mesh_finalize(phb_mesh *m);
+int phb_mesh_destroy(phb_mesh *m);
+/* sizes: [nNodes, nCells, nFaces, nPatches, rank, nProcs, nLocal, rowOffset,
+ *         nInteriorFaces, nBoundaryFaces, nnzScalar] */
+int phb_mesh_sizes(const phb_mesh *m, long long out[11]);
+/* host copies of mesh artefacts by name, for bit-exact parity checks.
+ * int arrays:  cptr cind faceN1 faceN2 faceL faceR facePatch ilPtr ilFace ilCell
+ *              blPtr blFace dlPtr dlCell rowPtr colInd slotL slotR slotDiag
+ *              owner globalId localRow globalRow bufPtr bufCell sendPtr sendCell
+ * f64 arrays:  vol cellCx cellCy faceCx faceCy faceSx faceSy faceG faceW
+ * returns the length (or <0); copies min(length, cap) entries when out != NULL */
+long long phb_mesh_get_i32(const phb_mesh *m, const char *name, int *out,
+                           long long cap);
+long long phb_mesh_get_f64(const phb_mesh *m, const char *name, double *out,
+                           long long cap);
+
+/* partition (I5): UG/FiniteVolumeGrid2D.cpp:276-392 with the partition VECTOR as
+ * an input (the reference gets it from METIS_PartMeshDual, :287-297).
+ * phb_partition_rcb: deterministic recursive coordinate bisection of cell
+ * centroids into nParts (any nParts >= 1). */
+int phb_partition_rcb(const phb_mesh *global, int nParts, int *cellPartition);
+/* local mesh of ctx's rank: owned cells + every face- or node-neighbour of an
+ * owned cell (buffer layer), reference numbering (ascending global id), halo
+ * lists as in initCommBuffers (:460-511).  `global` must be finalized. */
+int phb_mesh_create_local(phb_ctx *ctx, const phb_mesh *global,
+                          const int *cellPartition, phb_mesh **out);
+
+/* ------------------------------------------------------------ linear solver
+ * Seam 1.  Beneath class SparseMatrixSolver (M/SparseMatrixSolver.h:11-62):
+ *   setup(ptree LinearAlgebra.<eqn>)  -> phb_solver_setup(key,value) per key
+ *        keys (M/TrilinosBelosSparseMatrixSolver.cpp:44-86): solver, maxIters,
+ *        tolerance, preconditioner {none,jacobi,ilu0,schwarz}, iluFill
+ *   setRank                            -> phb_solver_set_rank
+ *   set(rowPtr,colInds,vals)           -> phb_solver_set_csr   (cols global, -1 = padding)
+ *   set(vector<SparseEntry>) / tuples  -> phb_solver_set_coo   (duplicates summed, M/SparseMatrixSolver.cpp:5-31)
+ *   setRhs / setGuess                  -> phb_solver_set_rhs / phb_solver_set_guess
+ *   solve / nIters / error             -> phb_solver_solve
+ *   x(i)                               -> phb_solver_get_x (whole vector, host)
+ * BiCGStab, right-preconditioned (Jacobi folded into the matrix, or level-
+ * scheduled ILU(0)); convergence ||r||_2 <= tolerance * ||b||_2. */
+int phb_solver_create(phb_ctx *ctx, phb_solver **out);
+int phb_solver_destroy(phb_solver *s);
+int phb_solver_setup(phb_solver *s, const char *key, const char *value);
+int phb_solver_set_rank(phb_solver *s, int nRows, int nCols);
+int phb_solver_set_csr(phb_solver *s, int nRows, const int *rowPtr,
+                       const int *colInd, const double *vals);
+int phb_solver_set_coo(phb_solver *s, int nRows, long long nEntries,
+                       const int *rows, const int *cols, const double *vals);
+/* distributed systems: owned rows are [rowOffset, rowOffset+nRows) of the
+ * global numbering; ghost columns are resolved through the mesh halo lists */
+int phb_solver_set_halo(phb_solver *s, const phb_mesh *localMesh, int nComp);
+int phb_solver_set_rhs(phb_solver *s, const double *b, int n);
+int phb_solver_set_guess(phb_solver *s, const double *x0, int n);
+int phb_solver_solve(phb_solver *s, int *iters, double *relres);
+int phb_solver_get_x(const phb_solver *s, double *x, int n);
+/* y = A x on the device copy of the last matrix set (host in/out): SpMV parity */
+int phb_solver_spmv(phb_solver *s, const double *x, double *y, int n);
+/* repeat the device SpMV `reps` times on resident data; returns mean ms/launch
+ * measured with CUDA events on the context stream (bench.py roofline leg) */
+int phb_solver_time_spmv(phb_solver *s, int reps, double *msPerLaunch);
+/* algorithmic byte counts of the current matrix: [spmv, bicgstabIteration] */
+int phb_solver_bytes(const phb_solver *s, double out[2]);
+
+/* ---------------------------------------------------------- fields, equations
+ * Seam 2.  Device mirrors of FiniteVolumeField<T> (cells + faces, BC table,
+ * one history level) and of FiniteVolumeEquation<T> on the canonical pattern
+ * row P = [P, nb in link order].
+ * Replaces: UF/FiniteVolumeField.{h,tpp}, UE/FiniteVolumeEquation.{h,tpp},
+ * UE/{Scalar,Vector}FiniteVolumeEquation.cpp. */
+int phb_field_create(phb_mesh *m, int nComp, const char *name, phb_field **out);
+int phb_field_destroy(phb_field *f);
+int phb_field_set_bc(phb_field *f, const char *patch, int type, double vx, double vy);
+/* part: "cells" | "faces" | "cells0" | "faces0" (old time level); host arrays
+ * are component-blocked: [x-block | y-block] */
+int phb_field_set(phb_field *f, const char *part, const double *v, long long n);
+int phb_field_get(const phb_field *f, const char *part, double *v, long long n);
+int phb_field_fill(phb_field *f, double vx, double vy);
+/* savePreviousTimeStep(dt,1): UF/FiniteVolumeField.tpp:208-227 */
+int phb_field_save_previous(phb_field *f);
+/* interpolateFaces(DISTANCE) + setBoundaryFaces: UF/FiniteVolumeField.tpp:129-182,
+ * UF/VectorFiniteVolumeField.cpp:140-161 */
+int phb_field_interpolate_faces(phb_field *f);
+int phb_field_set_boundary_faces(phb_field *f);
+/* ScalarGradient::compute(FACE_TO_CELL): UF/ScalarGradient.cpp:34-74 */
+int phb_field_gradient(const phb_field *phi, phb_field *grad);
+/* halo exchange of the cell values (grid_->sendMessages(field)),
+ * UG/FiniteVolumeGrid2D.tpp:3-49 */
+int phb_field_send_messages(phb_field *f);
+
+int phb_eqn_create(phb_mesh *m, int nComp, phb_eqn **out);
+int phb_eqn_destroy(phb_eqn *e);
+int phb_eqn_zero(phb_eqn *e);
+/* every assemble call ACCUMULATES sign * operator into e (sign = +1 for the
+ * left-hand side of `==`, -1 for the right-hand side):
+ *   ddt        UD/TimeDerivative.h:7-48      (rhoField may be NULL -> rhoConst)
+ *   div        UD/Divergence.h:8-53          (upwind, theta-weighted)
+ *   dive       UD/ExplicitDivergence.h:7-51
+ *   laplacian  UD/Laplacian.h:7-167, UD/Laplacian.cpp:5-119 (gammaField NULL -> gammaConst;
+ *              theta < 0 selects the steady overloads without old-time terms)
+ *   src        UD/Source.cpp:77-95           rhs += sign * field * V
+ *   src_div    UD/Source.cpp:5-25            rhs += sign * sum_f u_f . S_f  */
+int phb_assemble_ddt(phb_eqn *e, const phb_field *phi, double rhoConst,
+                     const phb_field *rhoField, double dt, double sign);
+int phb_assemble_div(phb_eqn *e, const phb_field *u, const phb_field *phi,
+                     double theta, double sign);
+int phb_assemble_dive(phb_eqn *e, const phb_field *u, const phb_field *phi,
+                      double theta, double sign);
+int phb_assemble_laplacian(phb_eqn *e, double gammaConst,
+                           const phb_field *gammaField, const phb_field *phi,
+                           double theta, double sign);
+int phb_assemble_src(phb_eqn *e, const phb_field *f, double sign);
+int phb_assemble_src_div(phb_eqn *e, const phb_field *u, double sign);
+/* rho * eqn row scaling: UE/VectorFiniteVolumeEquation.cpp:163-170 */
+int phb_eqn_scale_rows(phb_eqn *e, const phb_field *rho);
+/* relax(omega): body recovered from UE/ScalarFiniteVolumeEquation.cpp:45-55 */
+int phb_eqn_relax(phb_eqn *e, const phb_field *phi, double omega);
+/* host copy in the REFERENCE layout (I4), for parity:
+ *   layout 0: compact [P, nb...] with exact zeros dropped (any sum of operators,
+ *             M/CrsEquation.cpp:185-275); vector equations as 2N rows, y block offset N
+ *   layout 1: ELL-5 padded [nb0, P, nb1, ...,-1] (fv::laplacian(Scalar,phi), UD/Laplacian.h:49-83)
+ *   layout 2: ELL-5 padded [P, nb0, ...,-1]      (fv::laplacian(Field,phi),  UD/Laplacian.h:132-167)
+ * pass NULLs to query sizes: returns nnz (stored slots incl. padding) */
+long long phb_eqn_export_csr(const phb_eqn *e, int layout, int *rowPtr,
+                             int *colInd, double *vals, double *rhs);
+/* FiniteVolumeEquation<T>::solve: UE/FiniteVolumeEquation.tpp:64-86 -- device
+ * resident (no host round trip); the solution is written into phi's cells;
+ * phi's current cells are the initial guess when warmStart != 0 */
+int phb_eqn_solve(phb_eqn *e, phb_solver *s, phb_field *phi, int warmStart,
+                  int *iters, double *relres);
+
+/* ------------------------------------------------- fractional-step time step
+ * Device-resident FractionalStep::solve (US/FractionalStep.cpp:36-135): the
+ * caller of the hot path for configs 1-3, built from the calls above. */
+int phb_fs_create(phb_mesh *m, double rho, double mu, phb_fracstep **out);
+int phb_fs_destroy(phb_fracstep *fs);
+phb_field *phb_fs_field(phb_fracstep *fs, const char *name); /* u p gradP */
+phb_eqn *phb_fs_eqn(phb_fracstep *fs, const char *name);      /* uEqn pEqn */
+phb_solver *phb_fs_solver(phb_fracstep *fs, const char *name);
+int phb_fs_initialize(phb_fracstep *fs);
+int phb_fs_assemble_u(phb_fracstep *fs, double dt);
+int phb_fs_assemble_p(phb_fracstep *fs, double dt);
+/* stats: [itersU, itersP, relresU, relresP, maxDivergence, maxCourant] */
+int phb_fs_step(phb_fracstep *fs, double dt, double stats[6]);
+/* computeMaxTimeStep: US/FractionalStep.cpp:68-77 */
+int phb_fs_max_time_step(phb_fracstep *fs, double maxCo, double prevDt,
+                         double maxDt, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHASE_B200_H */

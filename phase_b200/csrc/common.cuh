@@ -1,0 +1,109 @@
+// common.cuh -- internal helpers shared by the translation units of libphase_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/phase_b200.h"
+
+namespace phb {
+
+void set_error(const char *fmt, ...);
+
+#define PHB_CUDA(call)                                                         \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      phb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,             \
+                     cudaGetErrorString(e__));                                 \
+      return PHB_ERR_CUDA;                                                     \
+    }                                                                          \
+  } while (0)
+
+#define PHB_CHECK(expr)                                                        \
+  do {                                                                         \
+    int rc__ = (expr);                                                         \
+    if (rc__ != PHB_OK) return rc__;                                           \
+  } while (0)
+
+#define PHB_REQUIRE(cond, ...)                                                 \
+  do {                                                                         \
+    if (!(cond)) {                                                             \
+      phb::set_error(__VA_ARGS__);                                             \
+      return PHB_ERR_ARG;                                                      \
+    }                                                                          \
+  } while (0)
+
+#define PHB_TRY_BEGIN try {
+#define PHB_TRY_END                                                            \
+  }                                                                            \
+  catch (const std::exception &ex__) {                                         \
+    phb::set_error("exception: %s", ex__.what());                              \
+    return PHB_ERR_ARG;                                                        \
+  }                                                                            \
+  catch (...) {                                                                \
+    phb::set_error("unknown exception");                                       \
+    return PHB_ERR_ARG;                                                        \
+  }
+
+// device buffer with explicit lifetime (no exceptions on the hot path)
+template <class T> struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  int alloc(size_t count) {
+    if (count == n && p) return PHB_OK;
+    release();
+    if (count == 0) return PHB_OK;
+    PHB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    n = count;
+    return PHB_OK;
+  }
+  int upload(const T *h, size_t count, cudaStream_t st) {
+    PHB_CHECK(alloc(count));
+    if (count) PHB_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    return PHB_OK;
+  }
+  int upload(const std::vector<T> &h, cudaStream_t st) { return upload(h.data(), h.size(), st); }
+  int zero(cudaStream_t st) {
+    if (n) PHB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st));
+    return PHB_OK;
+  }
+};
+
+constexpr int kSliceRows = 32;  // SELL slice height = one warp, lane <-> row
+
+}  // namespace phb
+
+struct ncclComm;
+
+struct phb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;       // compute stream (all kernels)
+  cudaStream_t commStream = nullptr;   // halo traffic
+  int numSMs = 148;
+  int rank = 0, nProcs = 1;
+  ncclComm *comm = nullptr;
+  long long launches = 0;
+  // pinned scratch for small device->host reads
+  double *pinned = nullptr;
+};
+
+#define PHB_LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
+  do {                                                                         \
+    auto kfn__ = kernel;                                                       \
+    kfn__<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);            \
+    (ctx)->launches++;                                                         \
+  } while (0)

@@ -1,0 +1,73 @@
+// ctx.cu -- context, error text, NCCL bootstrap.
+#include <cstdarg>
+#include <dlfcn.h>
+
+#include "comm.cuh"
+#include "common.cuh"
+
+namespace phb {
+static thread_local char g_err[1024] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace phb
+
+extern "C" {
+
+const char *phb_last_error(void) { return phb::g_err; }
+int phb_version(void) { return 100; }
+
+int phb_ctx_create(int device, phb_ctx **out) {
+  PHB_REQUIRE(out, "phb_ctx_create: out is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    phb::set_error("phb_ctx_create: no CUDA device (%s); this library has no CPU fallback",
+                   cudaGetErrorString(e));
+    return PHB_ERR_CUDA;
+  }
+  PHB_REQUIRE(device >= 0 && device < count, "phb_ctx_create: device %d out of range", device);
+  PHB_CUDA(cudaSetDevice(device));
+  phb_ctx *c = new phb_ctx();
+  c->device = device;
+  PHB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  PHB_CUDA(cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking));
+  PHB_CUDA(cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, device));
+  PHB_CUDA(cudaMallocHost((void **)&c->pinned, 256 * sizeof(double)));
+  *out = c;
+  return PHB_OK;
+}
+
+int phb_ctx_destroy(phb_ctx *c) {
+  if (!c) return PHB_OK;
+  cudaSetDevice(c->device);
+  phb::comm_destroy(c);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->commStream) cudaStreamDestroy(c->commStream);
+  if (c->pinned) cudaFreeHost(c->pinned);
+  delete c;
+  return PHB_OK;
+}
+
+int phb_ctx_rank(const phb_ctx *c) { return c ? c->rank : 0; }
+int phb_ctx_nprocs(const phb_ctx *c) { return c ? c->nProcs : 1; }
+long long phb_ctx_kernel_launches(const phb_ctx *c) { return c ? c->launches : 0; }
+void *phb_ctx_stream(phb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int phb_ctx_sync(phb_ctx *c) {
+  PHB_REQUIRE(c, "phb_ctx_sync: ctx is NULL");
+  PHB_CUDA(cudaStreamSynchronize(c->stream));
+  PHB_CUDA(cudaStreamSynchronize(c->commStream));
+  return PHB_OK;
+}
+
+int phb_comm_unique_id(void *out128) { return phb::comm_unique_id(out128); }
+int phb_ctx_init_comm(phb_ctx *c, int rank, int nProcs, const void *id128) {
+  PHB_REQUIRE(c, "phb_ctx_init_comm: ctx is NULL");
+  return phb::comm_init(c, rank, nProcs, id128);
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+// fracstep.cu -- device-resident FractionalStep::solve: the caller of the hot
+// path (US/FractionalStep.cpp:36-135), built from the fv:: kernels and the
+// BiCGStab solver so that a whole time step runs without host<->device field
+// traffic.  Fields, equations and solvers are exposed so callers can drive the
+// pieces themselves (the C++ mirror in include/phase/ does).
+#include <cmath>
+
+#include "comm.cuh"
+#include "fv.cuh"
+#include "solver.cuh"
+
+struct phb_fracstep {
+  phb_mesh *m = nullptr;
+  double rho = 1., mu = 1.;
+  phb_field *u = nullptr, *p = nullptr, *gradP = nullptr;
+  phb_eqn *uEqn = nullptr, *pEqn = nullptr;
+  phb_solver *uSolver = nullptr, *pSolver = nullptr;
+  phb::DevBuf<double> scratch, partials, out;
+  phb::DevBuf<unsigned> ticket;
+  bool warmStart = true;
+};
+
+extern "C" {
+
+int phb_fs_create(phb_mesh *m, double rho, double mu, phb_fracstep **out) {
+  PHB_REQUIRE(m && out && rho > 0., "phb_fs_create: bad argument");
+  PHB_REQUIRE(m->finalized, "phb_fs_create: mesh is not finalized");
+  phb_fracstep *fs = new phb_fracstep();
+  fs->m = m; fs->rho = rho; fs->mu = mu;
+  PHB_CHECK(phb_field_create(m, 2, "u", &fs->u));
+  PHB_CHECK(phb_field_create(m, 1, "p", &fs->p));
+  PHB_CHECK(phb_field_create(m, 2, "gradP", &fs->gradP));
+  PHB_CHECK(phb_eqn_create(m, 2, &fs->uEqn));
+  PHB_CHECK(phb_eqn_create(m, 1, &fs->pEqn));
+  PHB_CHECK(phb_solver_create(m->ctx, &fs->uSolver));
+  PHB_CHECK(phb_solver_create(m->ctx, &fs->pSolver));
+  PHB_CHECK(fs->out.alloc(4));
+  PHB_CHECK(fs->out.zero(m->ctx->stream));
+  *out = fs;
+  return PHB_OK;
+}
+
+int phb_fs_destroy(phb_fracstep *fs) {
+  if (!fs) return PHB_OK;
+  phb_field_destroy(fs->u); phb_field_destroy(fs->p); phb_field_destroy(fs->gradP);
+  phb_eqn_destroy(fs->uEqn); phb_eqn_destroy(fs->pEqn);
+  phb_solver_destroy(fs->uSolver); phb_solver_destroy(fs->pSolver);
+  delete fs;
+  return PHB_OK;
+}
+
+phb_field *phb_fs_field(phb_fracstep *fs, const char *name) {
+  if (!fs || !name) return nullptr;
+  if (!strcmp(name, "u")) return fs->u;
+  if (!strcmp(name, "p")) return fs->p;
+  if (!strcmp(name, "gradP")) return fs->gradP;
+  return nullptr;
+}
+phb_eqn *phb_fs_eqn(phb_fracstep *fs, const char *name) {
+  if (!fs || !name) return nullptr;
+  if (!strcmp(name, "uEqn")) return fs->uEqn;
+  if (!strcmp(name, "pEqn")) return fs->pEqn;
+  return nullptr;
+}
+phb_solver *phb_fs_solver(phb_fracstep *fs, const char *name) {
+  if (!fs || !name) return nullptr;
+  if (!strcmp(name, "uEqn")) return fs->uSolver;
+  if (!strcmp(name, "pEqn")) return fs->pSolver;
+  return nullptr;
+}
+
+// FractionalStep::initialize (US/FractionalStep.cpp:25-28)
+int phb_fs_initialize(phb_fracstep *fs) {
+  PHB_REQUIRE(fs, "phb_fs_initialize: NULL argument");
+  PHB_CHECK(phb::field_send_messages(fs->u));
+  PHB_CHECK(phb::field_interpolate_faces(fs->u));
+  PHB_CHECK(phb::field_set_boundary_faces(fs->p));
+  return PHB_OK;
+}
+
+// uEqn_ = (fv::ddt(u,dt) + fv::div(u,u,0.) == fv::laplacian(mu/rho,u,0.5) - src::src(gradP))
+// (US/FractionalStep.cpp:82-83); expects u.savePreviousTimeStep to have run.
+int phb_fs_assemble_u(phb_fracstep *fs, double dt) {
+  PHB_REQUIRE(fs && dt > 0., "phb_fs_assemble_u: bad argument");
+  PHB_CHECK(phb_eqn_zero(fs->uEqn));
+  PHB_CHECK(phb_assemble_ddt(fs->uEqn, fs->u, 1., nullptr, dt, +1.));
+  PHB_CHECK(phb_assemble_div(fs->uEqn, fs->u, fs->u, 0., +1.));
+  PHB_CHECK(phb_assemble_laplacian(fs->uEqn, fs->mu / fs->rho, nullptr, fs->u, 0.5, -1.));
+  PHB_CHECK(phb_assemble_src(fs->uEqn, fs->gradP, +1.));  // == (... - src)  ->  rhs_ += src
+  return PHB_OK;
+}
+
+// pEqn_ = (fv::laplacian(dt, p) == src::div(u))  (US/FractionalStep.cpp:97)
+int phb_fs_assemble_p(phb_fracstep *fs, double dt) {
+  PHB_REQUIRE(fs && dt > 0., "phb_fs_assemble_p: bad argument");
+  PHB_CHECK(phb_eqn_zero(fs->pEqn));
+  PHB_CHECK(phb_assemble_laplacian(fs->pEqn, dt, nullptr, fs->p, -1., +1.));
+  PHB_CHECK(phb_assemble_src_div(fs->pEqn, fs->u, -1.));
+  return PHB_OK;
+}
+
+int phb_fs_step(phb_fracstep *fs, double dt, double stats[6]) {
+  PHB_REQUIRE(fs && dt > 0., "phb_fs_step: bad argument");
+  phb_ctx *c = fs->m->ctx;
+  int itU = 0, itP = 0;
+  double rrU = 0., rrP = 0.;
+  // ---- solveUEqn (US/FractionalStep.cpp:79-94)
+  PHB_CHECK(phb_field_save_previous(fs->u));
+  PHB_CHECK(phb_fs_assemble_u(fs, dt));
+  PHB_CHECK(phb_eqn_solve(fs->uEqn, fs->uSolver, fs->u, fs->warmStart, &itU, &rrU));
+  PHB_CHECK(phb::field_axpy_cells(fs->u, dt, fs->gradP));
+  PHB_CHECK(phb::field_send_messages(fs->u));
+  PHB_CHECK(phb::field_interpolate_faces(fs->u));
+  // ---- solvePEqn (:96-107)
+  PHB_CHECK(phb_fs_assemble_p(fs, dt));
+  PHB_CHECK(phb_eqn_solve(fs->pEqn, fs->pSolver, fs->p, fs->warmStart, &itP, &rrP));
+  PHB_CHECK(phb::field_send_messages(fs->p));
+  PHB_CHECK(phb::field_set_boundary_faces(fs->p));
+  PHB_CHECK(phb::field_gradient(fs->p, fs->gradP));
+  // ---- correctVelocity (:109-117)
+  PHB_CHECK(phb::field_axpy_cells(fs->u, -dt, fs->gradP));
+  PHB_CHECK(phb::field_send_messages(fs->u));
+  PHB_CHECK(phb::field_axpy_faces(fs->u, -dt, fs->gradP));
+  // ---- diagnostics (:41-43): max divergence error, max CFL
+  PHB_CHECK(phb::field_flux_max(fs->u, 0, dt, fs->scratch, fs->partials, fs->ticket, fs->out.p));
+  PHB_CHECK(phb::field_flux_max(fs->u, 1, dt, fs->scratch, fs->partials, fs->ticket, fs->out.p + 1));
+  PHB_CUDA(cudaMemcpyAsync(c->pinned + 64, fs->out.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PHB_CUDA(cudaStreamSynchronize(c->stream));
+  if (stats) {
+    stats[0] = itU; stats[1] = itP; stats[2] = rrU; stats[3] = rrP;
+    stats[4] = c->pinned[64]; stats[5] = c->pinned[65];
+  }
+  return PHB_OK;
+}
+
+// computeMaxTimeStep (US/FractionalStep.cpp:68-77)
+int phb_fs_max_time_step(phb_fracstep *fs, double maxCo, double prevDt, double maxDt, double *out) {
+  PHB_REQUIRE(fs && out && prevDt > 0., "phb_fs_max_time_step: bad argument");
+  phb_ctx *c = fs->m->ctx;
+  PHB_CHECK(phb::field_flux_max(fs->u, 1, prevDt, fs->scratch, fs->partials, fs->ticket, fs->out.p + 1));
+  PHB_CUDA(cudaMemcpyAsync(c->pinned + 64, fs->out.p + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PHB_CUDA(cudaStreamSynchronize(c->stream));
+  const double co = c->pinned[64];
+  const double l1 = 0.1, l2 = 1.2;
+  *out = std::fmin(std::fmin(maxCo / co * prevDt, (1 + l1 * maxCo / co) * prevDt), std::fmin(l2 * prevDt, maxDt));
+  return PHB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,16 @@
+// fv.cuh -- internal field/equation helpers shared by fv.cu and fracstep.cu.
+#pragma once
+#include "structs.cuh"
+
+namespace phb {
+int field_face_types(phb_field *f);
+int field_interpolate_faces(phb_field *f);
+int field_set_boundary_faces(phb_field *f);
+int field_gradient(const phb_field *phi, phb_field *grad);
+int field_axpy_cells(phb_field *y, double a, const phb_field *x);  // owned cells
+int field_axpy_faces(phb_field *y, double a, const phb_field *x);  // all faces
+int field_send_messages(phb_field *f);
+// device max over owned cells of |sum_f u_f.S_f| (mode 0) or the Courant number (mode 1)
+int field_flux_max(const phb_field *u, int mode, double dt, DevBuf<double> &scratch, DevBuf<double> &partials,
+                   DevBuf<unsigned> &ticket, double *devOut);
+}  // namespace phb

@@ -1,0 +1,92 @@
+// kernels.cuh -- device helpers shared by the solver and assembly kernels:
+// deterministic block + grid reductions (warp shuffles, fixed-order partials,
+// last-block finish) and streaming load wrappers.
+#pragma once
+#include "common.cuh"
+
+namespace phb {
+
+struct SellView {
+  const int *sliceOff;
+  const int *col;
+  int nRows, nSlices, nCols;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// streaming (read-once) loads: keep them out of L1 and first in line for L2 eviction
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
+
+constexpr int kMaxBlockWarps = 32;
+
+// Sum NS per-thread values over the grid, deterministically:
+//   warp shuffle -> shared -> one partial per block -> the last block to arrive
+//   (ticket counter) adds the partials in fixed order and writes out[0..NS).
+// `ticket` must be zero on entry and is reset for the next launch.
+template <int NS, bool MAX = false>
+__device__ __forceinline__ void grid_reduce(double (&v)[NS], double *partials, unsigned *ticket,
+                                            double *out) {
+  __shared__ double sh[NS][kMaxBlockWarps];
+  __shared__ bool isLast;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const double w = MAX ? warp_max(v[j]) : warp_sum(v[j]);
+    if (lane == 0) sh[j][warp] = w;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      double w = lane < nWarps ? sh[j][lane] : (MAX ? -1e300 : 0.);
+      w = MAX ? warp_max(w) : warp_sum(w);
+      if (lane == 0) partials[(size_t)blockIdx.x * NS + j] = w;
+    }
+    if (lane == 0) {
+      __threadfence();
+      const unsigned t = atomicAdd(ticket, 1u);
+      isLast = (t == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (!isLast) return;
+  __threadfence();
+  double acc[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) acc[j] = MAX ? -1e300 : 0.;
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const double w = __ldcg(&partials[(size_t)b * NS + j]);
+      acc[j] = MAX ? fmax(acc[j], w) : acc[j] + w;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const double w = MAX ? warp_max(acc[j]) : warp_sum(acc[j]);
+    if (lane == 0) sh[j][warp] = w;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      double w = lane < nWarps ? sh[j][lane] : (MAX ? -1e300 : 0.);
+      w = MAX ? warp_max(w) : warp_sum(w);
+      if (lane == 0) out[j] = w;
+    }
+    if (lane == 0) *ticket = 0u;
+  }
+}
+
+}  // namespace phb

@@ -1,0 +1,60 @@
+// solver.cuh -- internal definition of phb_solver.
+#pragma once
+#include "structs.cuh"
+
+// device-resident Krylov scalars (one cache line)
+struct KrylovSums {
+  double rho[2];   // (rhat . r), parity-indexed by iteration
+  double sigma;    // (rhat . v)
+  double ts, tt;   // (t . s), (t . t)
+  double rr;       // ||r||^2
+  double bb;       // ||b||^2
+  double thresh;   // tol^2 * bb
+  double iters;    // iterations actually performed
+  double pad[7];
+};
+
+struct phb_solver {
+  phb_ctx *ctx = nullptr;
+  // configuration (keys of LinearAlgebra.<eqn>, M/TrilinosBelosSparseMatrixSolver.cpp:44-86)
+  int maxIters = 500;
+  double tol = 1e-8;
+  int precond = PHB_PC_JACOBI;
+  std::string method = "BICGSTAB";
+  int itersPerGraph = 8;
+  bool useGraph = true;
+  // ---- matrix as handed over by set_csr (host CSR cache for pattern reuse)
+  int nRows = 0, nColsGlobal = 0;
+  std::vector<int> cRowPtr, cColInd;
+  SellPattern own;
+  phb::DevBuf<int> csr2slot;
+  phb::DevBuf<double> csrVals, ownVals;
+  bool haveMatrix = false;
+  // ---- active system (either `own` or borrowed from an equation)
+  const SellPattern *pat = nullptr;
+  const double *dVals = nullptr;
+  int nComp = 1;
+  int ld = 0;  // vector leading dimension (= pat->nCols)
+  const phb_mesh *halo = nullptr;  // halo lists (nProcs > 1)
+  phb::DevBuf<double> scaled, dinv;
+  phb::DevBuf<double> b, x, r, rhat, p, v, s, t;
+  phb::DevBuf<double> partials;
+  phb::DevBuf<unsigned> ticket;
+  phb::DevBuf<KrylovSums> sums;
+  bool haveRhs = false, haveGuess = false;
+  // CUDA graph of `itersPerGraph` iterations, keyed on the active buffers
+  cudaGraphExec_t graphExec = nullptr;
+  const void *graphKey[4] = {nullptr, nullptr, nullptr, nullptr};
+  // results
+  int lastIters = 0;
+  double lastRelres = 0.;
+  std::vector<double> hostX;
+};
+
+namespace phb {
+// core entry used by phb_solver_solve and phb_eqn_solve: solves A x = b with the
+// device vectors already in s->b / s->x (x = initial guess), matrix (pat,dVals).
+int solver_run(phb_solver *s, int *iters, double *relres);
+int solver_bind(phb_solver *s, const SellPattern *pat, const double *dVals, int nComp,
+                const phb_mesh *halo);
+}  // namespace phb

@@ -1,0 +1,58 @@
+"""End-to-end parity of the device-resident fractional step against the oracle
+driven by an exact direct solve (the snapshot's lib eigen = SparseLU): fields
+after K steps within rel-L2 1e-6 (north-star tolerance); p compared minus its
+mean because every p patch is normal_gradient (singular pEqn_)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from tests.util import oracle_cavity, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6  # north_star: converged fp64 fields within relative L2 <= 1e-6
+
+
+@pytest.fixture(scope="module")
+def comm():
+    from phase_b200.api import Communicator
+    c = Communicator(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("kind,nx,ny,K", [("rect", 32, 32, 10), ("tri", 20, 16, 8), ("rect", 100, 100, 5)])
+def test_cavity_k_steps(comm, kind, nx, ny, K):
+    from phase_b200.api import FiniteVolumeGrid2D as G, lid_driven_cavity
+    om, ofs = oracle_cavity(kind, nx, ny, 1.0, 1.0, 1.0, 0.1)
+    ofs.use_direct_solver()
+    g = (G.rectilinear if kind == "rect" else G.triangulated)(comm, nx, ny, 1.0, 1.0)
+    gfs = lid_driven_cavity(g, 1.0, 0.1, solver=dict(tolerance=1e-11, maxIters=50000))
+    dt = 0.5 * (1.0 / nx)          # maxCo 0.5 with the unit lid speed
+    for k in range(K):
+        ofs.step(dt)
+        st = gfs.solve(dt)
+        assert st["errorU"] <= 1e-10 and st["errorP"] <= 1e-10
+    u = gfs.u.get("cells")
+    assert rel_l2(u[0], ofs.view("ux")) < TOL
+    assert rel_l2(u[1], ofs.view("uy")) < TOL
+    p, po = gfs.p.get("cells"), ofs.view("p").copy()
+    assert rel_l2(p - p.mean(), po - po.mean()) < TOL
+    uf = gfs.u.get("faces")
+    assert rel_l2(uf[0], ofs.view("ufx")) < TOL
+    assert st["maxDivergence"] < 1e-8 and abs(st["maxDivergence"] - ofs.max_divergence()) < 1e-8
+    assert abs(st["maxCourant"] - ofs.max_courant(dt)) < 1e-6
+    gfs.close(); g.close()
+
+
+def test_time_step_control(comm):
+    from phase_b200.api import FiniteVolumeGrid2D as G, lid_driven_cavity
+    g = G.rectilinear(comm, 16, 16)
+    gfs = lid_driven_cavity(g, 1.0, 0.1)
+    dt = 0.01
+    gfs.solve(dt)
+    co = gfs.solve(dt)["maxCourant"]
+    new = gfs.computeMaxTimeStep(0.5, dt, 1.0)
+    want = min(0.5 / co * dt, (1 + 0.1 * 0.5 / co) * dt, 1.2 * dt, 1.0)   # US/FractionalStep.cpp:68-77
+    assert np.isclose(new, want, rtol=1e-6)
+    gfs.close(); g.close()

@@ -1,0 +1,116 @@
+"""Seam 1 through the C ABI: SpMV and BiCGStab against the oracle (scipy LU and
+the C BiCGStab) on matrices in the reference's own hand-off layouts."""
+import numpy as np
+import pytest
+
+import oracle as O
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def comm():
+    from phase_b200.api import Communicator
+    c = Communicator(0)
+    yield c
+    c.close()
+
+
+def poisson_system(kind, nx, ny, fixed_top=True, seed=0):
+    om = (O.Mesh.rectilinear if kind == "rect" else O.Mesh.triangulated)(nx, ny, 1.0, 1.0)
+    fs = O.FracStep(om, 1.0, 1.0)
+    if fixed_top:
+        fs.set_bc("p", "y+", O.FIXED, 0.5)
+    fs.initialize()
+    rng = np.random.default_rng(seed)
+    fs.view("ufx")[:] = rng.standard_normal(om.sizes["nFaces"])
+    fs.view("ufy")[:] = rng.standard_normal(om.sizes["nFaces"])
+    rp, ci, va, rhs = fs.assemble_p(0.05).export()       # padded [nb0,P,...,-1]
+    return rp, ci, va, -rhs
+
+
+@pytest.mark.parametrize("kind,nx,ny", [("rect", 20, 13), ("tri", 9, 11), ("rect", 1, 1), ("rect", 70, 1)])
+def test_spmv_padded_csr(comm, kind, nx, ny):
+    from phase_b200.api import SparseMatrixSolver
+    rp, ci, va, b = poisson_system(kind, nx, ny)
+    s = SparseMatrixSolver(comm)
+    s.setRank(len(b))
+    s.set(rp, ci, va)
+    x = np.random.default_rng(1).standard_normal(len(b))
+    y = s.spmv(x)
+    ref = O.csr_to_scipy(rp, ci, va) @ x
+    assert np.allclose(y, ref, rtol=1e-13, atol=1e-13)
+    s.close()
+
+
+@pytest.mark.parametrize("pc", ["none", "jacobi"])
+@pytest.mark.parametrize("kind,nx,ny", [("rect", 40, 40), ("tri", 24, 20)])
+def test_bicgstab_vs_direct(comm, kind, nx, ny, pc):
+    from phase_b200.api import SparseMatrixSolver
+    rp, ci, va, b = poisson_system(kind, nx, ny)
+    xd = O.direct_solve(rp, ci, va, b)
+    s = SparseMatrixSolver(comm).setup(dict(solver="BICGSTAB", maxIters=5000, tolerance=1e-11, preconditioner=pc))
+    s.setRank(len(b))
+    s.set(rp, ci, va)
+    s.setRhs(b)
+    err = s.solve()
+    assert err <= 1e-11 and s.nIters() > 0
+    x = s.x()
+    A = O.csr_to_scipy(rp, ci, va)
+    assert np.linalg.norm(b - A @ x) <= 1.0000001e-11 * np.linalg.norm(b) * 1.01
+    assert rel_l2(x, xd) < 1e-8
+    # same matrix again (pattern cache) with a new rhs and a warm start
+    s.set(rp, ci, va * 1.0)
+    s.setRhs(2.0 * b)
+    s.setGuess(2.0 * x)
+    s.solve()
+    assert s.nIters() <= 2 and rel_l2(s.x(), 2 * xd) < 1e-8
+    s.close()
+
+
+def test_singular_neumann_system_converges(comm):
+    from phase_b200.api import SparseMatrixSolver
+    rp, ci, va, b = poisson_system("rect", 32, 32, fixed_top=False)
+    b = b - b.mean()                      # compatible right-hand side
+    s = SparseMatrixSolver(comm).setup(dict(maxIters=5000, tolerance=1e-10, preconditioner="jacobi"))
+    s.set(rp, ci, va)
+    s.setRhs(b)
+    s.solve()
+    x, xd = s.x(), O.direct_solve(rp, ci, va, b)
+    assert rel_l2(x - x.mean(), xd - xd.mean()) < 1e-7
+    s.close()
+
+
+def test_coo_duplicates_summed_and_errors(comm):
+    from phase_b200.api import SparseMatrixSolver, PhaseB200Error
+    s = SparseMatrixSolver(comm).setup(dict(tolerance=1e-12, preconditioner="jacobi"))
+    rows = [0, 0, 0, 1, 1, 2, 2, 2]
+    cols = [0, 0, 1, 1, 0, 2, 1, 2]
+    vals = [2.0, 2.0, -1.0, 4.0, -1.0, 2.0, -1.0, 2.0]   # duplicates (0,0) and (2,2) summed
+    s.setEntries(3, rows, cols, vals)
+    s.setRhs(np.array([1.0, 2.0, 3.0]))
+    s.solve()
+    A = np.array([[4.0, -1, 0], [-1, 4, 0], [0, -1, 4]])
+    assert np.allclose(s.x(), np.linalg.solve(A, [1, 2, 3]), rtol=1e-10)
+    with pytest.raises(PhaseB200Error):
+        s.setup(dict(solver="GMRES"))
+    with pytest.raises(PhaseB200Error):
+        s.setRhs(np.zeros(5))
+    s2 = SparseMatrixSolver(comm)
+    with pytest.raises(PhaseB200Error):
+        s2.solve()                        # nothing set
+    s.close(); s2.close()
+
+
+def test_matches_oracle_bicgstab_iteration_count(comm):
+    """Same algorithm (right-preconditioned BiCGStab + Jacobi), same tolerance:
+    iteration counts of the CUDA path and the C oracle agree to round-off effects."""
+    from phase_b200.api import SparseMatrixSolver
+    rp, ci, va, b = poisson_system("rect", 48, 48)
+    xo, ito, rro = O.bicgstab(rp, ci, va, b, tol=1e-9, max_iters=5000, precond=1)
+    s = SparseMatrixSolver(comm).setup(dict(maxIters=5000, tolerance=1e-9, preconditioner="jacobi"))
+    s.set(rp, ci, va); s.setRhs(b); s.solve()
+    assert abs(s.nIters() - ito) <= max(8, ito // 4)
+    assert rel_l2(s.x(), xo) < 1e-6
+    s.close()
