@@ -53,6 +53,11 @@ int phb_version(void);
  * One context = one GPU + its streams (+ an NCCL communicator for nProcs>1).
  * Replaces: S/Communicator.{h,cpp} (MPI_Init, rank/nProcs, point-to-point and
  * all-reduce used around the solve, S/Communicator.cpp:11-17,81-141). */
+/* device >= 0: a CUDA device (fails when none is present: there is no CPU
+ * fallback).  PHB_DEVICE_HOST_ONLY: a context that can only build meshes,
+ * partitions and halo maps on the host (integer artefacts I1-I5); creating a
+ * field, equation or solver on it fails with PHB_ERR_STATE. */
+#define PHB_DEVICE_HOST_ONLY (-1)
 int phb_ctx_create(int device, phb_ctx **out);
 int phb_ctx_destroy(phb_ctx *ctx);
 /* 128-byte NCCL unique id made on rank 0, shipped by the host launcher */
@@ -111,6 +116,12 @@ int phb_partition_rcb(const phb_mesh *global, int nParts, int *cellPartition);
  * lists as in initCommBuffers (:460-511).  `global` must be finalized. */
 int phb_mesh_create_local(phb_ctx *ctx, const phb_mesh *global,
                           const int *cellPartition, phb_mesh **out);
+
+/* local mesh of ctx's rank for a y-strip partition of an nx x ny rectilinear
+ * grid (rank r owns rows [r ny/P, (r+1) ny/P)) built without the global mesh;
+ * same result as create_rectilinear + that partition + create_local. */
+int phb_mesh_create_rect_strip(phb_ctx *ctx, int nx, int ny, double width,
+                               double height, phb_mesh **out);
 
 /* ------------------------------------------------------------ linear solver
  * Seam 1.  Beneath class SparseMatrixSolver (M/SparseMatrixSolver.h:11-62):

@@ -27,13 +27,15 @@ def _dp(a):
 class Communicator:
     """One GPU + streams (+ NCCL communicator): the S/Communicator analogue."""
 
+    HOST_ONLY = -1   # mesh / partition / halo maps only (no kernels): host-logic tests
+
     def __init__(self, device=0, rank=0, nprocs=1, unique_id=None):
         self.L = _capi.lib()
         h = C.c_void_p()
         check(self.L.phb_ctx_create(device, C.byref(h)))
         self.h = h
         if nprocs > 1:
-            buf = C.create_string_buffer(bytes(unique_id), 128)
+            buf = C.create_string_buffer(bytes(unique_id or b""), 128)
             check(self.L.phb_ctx_init_comm(self.h, rank, nprocs, buf))
 
     @staticmethod
@@ -91,6 +93,13 @@ class FiniteVolumeGrid2D:
         check(comm.L.phb_mesh_create_triangulated(comm.h, nx, ny, width, height, C.byref(h)))
         g = cls(comm, h)
         return g.finalize() if finalize else g
+
+    @classmethod
+    def rectilinear_strip(cls, comm, nx, ny, width=1.0, height=1.0):
+        """Local mesh of comm's rank for a y-strip partition (no global mesh is built)."""
+        h = C.c_void_p()
+        check(comm.L.phb_mesh_create_rect_strip(comm.h, nx, ny, width, height, C.byref(h)))
+        return cls(comm, h)
 
     def createPatchByNodes(self, name, pairs):
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1)

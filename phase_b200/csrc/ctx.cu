@@ -22,6 +22,13 @@ int phb_version(void) { return 100; }
 
 int phb_ctx_create(int device, phb_ctx **out) {
   PHB_REQUIRE(out, "phb_ctx_create: out is NULL");
+  if (device == PHB_DEVICE_HOST_ONLY) {
+    // mesh / partition / halo-map construction only (host logic); no kernels can run
+    phb_ctx *c = new phb_ctx();
+    c->device = -1;
+    *out = c;
+    return PHB_OK;
+  }
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {
@@ -43,6 +50,10 @@ int phb_ctx_create(int device, phb_ctx **out) {
 
 int phb_ctx_destroy(phb_ctx *c) {
   if (!c) return PHB_OK;
+  if (c->device < 0) {
+    delete c;
+    return PHB_OK;
+  }
   cudaSetDevice(c->device);
   phb::comm_destroy(c);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -59,6 +70,7 @@ void *phb_ctx_stream(phb_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 int phb_ctx_sync(phb_ctx *c) {
   PHB_REQUIRE(c, "phb_ctx_sync: ctx is NULL");
+  if (c->device < 0) return PHB_OK;
   PHB_CUDA(cudaStreamSynchronize(c->stream));
   PHB_CUDA(cudaStreamSynchronize(c->commStream));
   return PHB_OK;
@@ -67,6 +79,12 @@ int phb_ctx_sync(phb_ctx *c) {
 int phb_comm_unique_id(void *out128) { return phb::comm_unique_id(out128); }
 int phb_ctx_init_comm(phb_ctx *c, int rank, int nProcs, const void *id128) {
   PHB_REQUIRE(c, "phb_ctx_init_comm: ctx is NULL");
+  if (c->device < 0) {  // host-only: just record the rank layout
+    PHB_REQUIRE(nProcs >= 1 && rank >= 0 && rank < nProcs, "phb_ctx_init_comm: bad rank %d/%d", rank, nProcs);
+    c->rank = rank;
+    c->nProcs = nProcs;
+    return PHB_OK;
+  }
   return phb::comm_init(c, rank, nProcs, id128);
 }
 

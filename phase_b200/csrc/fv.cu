@@ -598,6 +598,7 @@ extern "C" {
 int phb_field_create(phb_mesh *m, int nComp, const char *name, phb_field **out) {
   PHB_REQUIRE(m && out && (nComp == 1 || nComp == 2), "phb_field_create: bad argument");
   PHB_REQUIRE(m->finalized, "phb_field_create: mesh is not finalized");
+  if (m->ctx->device < 0) { phb::set_error("phb_field_create: host-only context"); return PHB_ERR_STATE; }
   std::unique_ptr<phb_field> f(new phb_field());
   f->m = m; f->nComp = nComp; f->name = name ? name : "";
   f->bc.assign(m->patchNames.size(), BcEntry());
@@ -737,6 +738,7 @@ int phb_field_send_messages(phb_field *f) {
 int phb_eqn_create(phb_mesh *m, int nComp, phb_eqn **out) {
   PHB_REQUIRE(m && out && (nComp == 1 || nComp == 2), "phb_eqn_create: bad argument");
   PHB_REQUIRE(m->finalized, "phb_eqn_create: mesh is not finalized");
+  if (m->ctx->device < 0) { phb::set_error("phb_eqn_create: host-only context"); return PHB_ERR_STATE; }
   std::unique_ptr<phb_eqn> e(new phb_eqn());
   e->m = m; e->nComp = nComp;
   PHB_CHECK(e->vals.alloc((size_t)m->sell.nSlots));

@@ -253,6 +253,7 @@ int rect_patches(phb_mesh *m, int nx, int ny) {
 // device numbering + SELL pattern + SoA upload
 int upload(phb_mesh *m) {
   cudaStream_t st = m->ctx->stream;
+  const bool hostOnly = m->ctx->device < 0;  // numbering is still built; nothing is uploaded
   const int N = m->nCells, F = m->nFaces, nL = m->nLocal, P = m->nProcs;
   // device order: owned cells by IndexMap local row, then ghosts grouped by owner
   m->cell2dev.assign(N, -1);
@@ -312,6 +313,7 @@ int upload(phb_mesh *m) {
       }
     }
   }
+  if (hostOnly) return PHB_OK;
   PHB_CHECK(S.sliceOff.upload(S.hSliceOff, st));
   PHB_CHECK(S.rowLen.upload(S.hRowLen, st));
   PHB_CHECK(S.col.upload(S.hCol, st));
@@ -350,6 +352,40 @@ int upload(phb_mesh *m) {
   PHB_CHECK(m->dCell2Dev.upload(m->cell2dev, st));
   PHB_CUDA(cudaStreamSynchronize(st));
   return PHB_OK;
+}
+
+
+// ownership, IndexMap (1 index), buffer and send groups of a local mesh whose
+// cells are the global cells `keep` (ascending).  UG/FiniteVolumeGrid2D.cpp:379-387,
+// 460-511; UE/IndexMap.cpp:15-40.  The send group for peer q is what q keeps of
+// ours, in q's local (= ascending global id) order, so no handshake is needed.
+template <class PartOf, class Touches, class GRowOf>
+void finish_local(phb_mesh *m, int rank, int P, const std::vector<int> &keep, PartOf partOf, Touches touches,
+                  const std::vector<int> &offs, GRowOf gRowOf) {
+  const int n = (int)keep.size();
+  m->rank = rank; m->nProcs = P;
+  m->nLocal = offs[rank + 1] - offs[rank]; m->rowOffset = offs[rank];
+  m->owner.resize(n); m->globalId.resize(n); m->localRow.assign(n, -1); m->globalRow.resize(n);
+  m->bufPtr.assign(P + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    const int c = keep[i], q = partOf(c);
+    m->owner[i] = q; m->globalId[i] = c; m->globalRow[i] = gRowOf(c);
+    if (q == rank) m->localRow[i] = m->globalRow[i] - offs[rank];
+    else m->bufPtr[q + 1]++;
+  }
+  std::partial_sum(m->bufPtr.begin(), m->bufPtr.end(), m->bufPtr.begin());
+  m->bufCell.resize(m->bufPtr[P]);
+  std::vector<int> fill(P, 0);
+  for (int i = 0; i < n; ++i)
+    if (m->owner[i] != rank) m->bufCell[m->bufPtr[m->owner[i]] + fill[m->owner[i]]++] = i;
+  m->sendPtr.assign(P + 1, 0);
+  m->sendCell.clear();
+  for (int q = 0; q < P; ++q) {
+    if (q != rank)
+      for (int i = 0; i < n; ++i)
+        if (m->owner[i] == rank && touches(keep[i], q)) m->sendCell.push_back(i);
+    m->sendPtr[q + 1] = (int)m->sendCell.size();
+  }
 }
 
 }  // namespace
@@ -599,9 +635,6 @@ int phb_mesh_create_local(phb_ctx *ctx, const phb_mesh *g, const int *part, phb_
     if (!pr.empty() && phb_mesh_add_patch_by_nodes(m, g->patchNames[p].c_str(), (int)pr.size() / 2, pr.data()) < 0)
       return PHB_ERR_ARG;
   }
-  // ownership, IndexMap (1 index), buffer groups
-  const int n = (int)keep.size();
-  m->rank = rank; m->nProcs = P;
   std::vector<int> nLocalOf(P, 0);
   for (int c = 0; c < N; ++c) nLocalOf[part[c]]++;
   std::vector<int> offs(P + 1, 0);
@@ -609,29 +642,74 @@ int phb_mesh_create_local(phb_ctx *ctx, const phb_mesh *g, const int *part, phb_
   // global row of every global cell: owner offset + rank among the owner's cells (ascending id)
   std::vector<int> gRow(N), cnt(P, 0);
   for (int c = 0; c < N; ++c) gRow[c] = offs[part[c]] + cnt[part[c]]++;
-  m->nLocal = nLocalOf[rank]; m->rowOffset = offs[rank];
-  m->owner.resize(n); m->globalId.resize(n); m->localRow.assign(n, -1); m->globalRow.resize(n);
-  m->bufPtr.assign(P + 1, 0);
-  for (int i = 0; i < n; ++i) {
-    const int c = keep[i];
-    m->owner[i] = part[c]; m->globalId[i] = c; m->globalRow[i] = gRow[c];
-    if (part[c] == rank) m->localRow[i] = gRow[c] - offs[rank];
-    else m->bufPtr[part[c] + 1]++;
+  finish_local(m, rank, P, keep, [&](int c) { return part[c]; }, touches, offs, [&](int c) { return gRow[c]; });
+  PHB_CHECK(phb_mesh_finalize(m));
+  *out = guard.release();
+  return PHB_OK;
+  PHB_TRY_END
+}
+
+// Local mesh of a y-strip partition of an nx x ny rectilinear grid, built WITHOUT
+// materialising the global mesh (weak-scaling runs): rank r owns rows
+// [r ny/P, (r+1) ny/P); the result is identical (numbering, patches, halo maps) to
+// phb_mesh_create_rectilinear + that partition vector + phb_mesh_create_local.
+int phb_mesh_create_rect_strip(phb_ctx *ctx, int nx, int ny, double w, double h, phb_mesh **out) {
+  PHB_TRY_BEGIN
+  PHB_REQUIRE(ctx && out && nx > 0 && ny > 0 && w > 0 && h > 0, "phb_mesh_create_rect_strip: bad argument");
+  const int rank = ctx->rank, P = ctx->nProcs;
+  PHB_REQUIRE(ny >= P, "phb_mesh_create_rect_strip: fewer rows than ranks");
+  auto rowOwner = [&](int j) { return (int)(((long long)j * P) / ny); };
+  auto firstRow = [&](int q) { return (int)(((long long)q * ny + P - 1) / P); };
+  const int j0 = firstRow(rank), j1 = (rank + 1 < P) ? firstRow(rank + 1) : ny;
+  const int jlo = std::max(0, j0 - 1), jhi = std::min(ny, j1 + 1);  // kept rows: face/node neighbours
+  const double hx0 = w / nx, hy0 = h / ny;
+  const int nnx = nx + 1;
+  std::vector<int> keep, cptr(1, 0), cind, localNode((size_t)(jhi - jlo + 1) * nnx, -1);
+  std::vector<double> xy;
+  keep.reserve((size_t)(jhi - jlo) * nx);
+  auto nodeId = [&](int i, int j) -> int {
+    int &ln = localNode[(size_t)(j - jlo) * nnx + i];
+    if (ln < 0) {
+      ln = (int)(xy.size() / 2);
+      xy.push_back(i * hx0); xy.push_back(j * hy0);
+    }
+    return ln;
+  };
+  for (int j = jlo; j < jhi; ++j)
+    for (int i = 0; i < nx; ++i) {
+      keep.push_back(j * nx + i);
+      cind.push_back(nodeId(i, j)); cind.push_back(nodeId(i + 1, j));
+      cind.push_back(nodeId(i + 1, j + 1)); cind.push_back(nodeId(i, j + 1));
+      cptr.push_back((int)cind.size());
+    }
+  phb_mesh *m = nullptr;
+  PHB_CHECK(mesh_from_arrays(ctx, (int)(xy.size() / 2), xy.data(), (int)keep.size(), cptr.data(), cind.data(), &m));
+  std::unique_ptr<phb_mesh> guard(m);
+  auto ln = [&](int i, int j) { return localNode[(size_t)(j - jlo) * nnx + i]; };
+  std::vector<int> pr;
+  // same creation order as the global grid: x-, x+, y-, y+ (a patch absent locally keeps its id)
+  for (int side = 0; side < 2; ++side) {
+    pr.clear();
+    const int i = side ? nx : 0;
+    for (int j = jlo; j < jhi; ++j) { pr.push_back(ln(i, j)); pr.push_back(ln(i, j + 1)); }
+    if (!pr.empty() && phb_mesh_add_patch_by_nodes(m, side ? "x+" : "x-", (int)pr.size() / 2, pr.data()) < 0)
+      return PHB_ERR_ARG;
   }
-  std::partial_sum(m->bufPtr.begin(), m->bufPtr.end(), m->bufPtr.begin());
-  m->bufCell.resize(m->bufPtr[P]);
-  std::vector<int> fill(P, 0);
-  for (int i = 0; i < n; ++i)
-    if (m->owner[i] != rank) m->bufCell[m->bufPtr[m->owner[i]] + fill[m->owner[i]]++] = i;
-  // send groups: what peer q keeps of mine, in q's local (= ascending global) order
-  m->sendPtr.assign(P + 1, 0);
-  m->sendCell.clear();
-  for (int q = 0; q < P; ++q) {
-    if (q != rank)
-      for (int i = 0; i < n; ++i)
-        if (m->owner[i] == rank && touches(keep[i], q)) m->sendCell.push_back(i);
-    m->sendPtr[q + 1] = (int)m->sendCell.size();
-  }
+  pr.clear();
+  if (jlo == 0) for (int i = 0; i < nx; ++i) { pr.push_back(ln(i, 0)); pr.push_back(ln(i + 1, 0)); }
+  if (!pr.empty() && phb_mesh_add_patch_by_nodes(m, "y-", (int)pr.size() / 2, pr.data()) < 0) return PHB_ERR_ARG;
+  pr.clear();
+  if (jhi == ny) for (int i = 0; i < nx; ++i) { pr.push_back(ln(i, ny)); pr.push_back(ln(i + 1, ny)); }
+  if (!pr.empty() && phb_mesh_add_patch_by_nodes(m, "y+", (int)pr.size() / 2, pr.data()) < 0) return PHB_ERR_ARG;
+  std::vector<int> offs(P + 1, 0);
+  for (int q = 0; q < P; ++q) offs[q + 1] = ((q + 1 < P) ? firstRow(q + 1) : ny) * nx;
+  auto partOf = [&](int c) { return rowOwner(c / nx); };
+  auto touches = [&](int c, int q) {
+    const int j = c / nx;
+    for (int jj = std::max(0, j - 1); jj <= std::min(ny - 1, j + 1); ++jj) if (rowOwner(jj) == q) return true;
+    return false;
+  };
+  finish_local(m, rank, P, keep, partOf, touches, offs, [](int c) { return c; });
   PHB_CHECK(phb_mesh_finalize(m));
   *out = guard.release();
   return PHB_OK;

@@ -509,6 +509,7 @@ extern "C" {
 
 int phb_solver_create(phb_ctx *ctx, phb_solver **out) {
   PHB_REQUIRE(ctx && out, "phb_solver_create: NULL argument");
+  if (ctx->device < 0) { set_error("phb_solver_create: host-only context"); return PHB_ERR_STATE; }
   phb_solver *s = new phb_solver();
   s->ctx = ctx;
   if (getenv("PHB_NO_GRAPH")) s->useGraph = false;
