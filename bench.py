@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--n", type=int, default=2000, help="cells per side per GPU (2000 -> 4M cells)")
+    ap.add_argument("--side", dest="n", type=int, default=2000, help="cells per side per GPU (2000 -> 4M cells)")
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--max-iters", type=int, default=20000)
     ap.add_argument("--precond", default="jacobi")
@@ -289,6 +289,8 @@ def main():
     d2h_all = (2 * N + N + 2 * F + F + 2 * N) * 8
 
     if rank != 0:
+        fs.close(); grid.close(); comm.close()
+        dist.destroy_process_group()
         return
     iters_u = float(np.mean([s["itersU"] for s in timed]))
     iters_p = float(np.mean([s["itersP"] for s in timed]))
@@ -316,8 +318,10 @@ def main():
                                 "sample": "1 assembled 4M-cell step + 12 BiCGStab(Jacobi) iterations per solve on %d "
                                           "OpenMP threads, scaled to this run's %.0f/%.0f iterations per solve" %
                                           (cores, iters_u, iters_p), "detail": detail}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     fs.close(); grid.close(); comm.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -618,6 +618,9 @@ int phb_field_set_bc(phb_field *f, const char *patch, int type, double vx, doubl
               "phb_field_set_bc: unrecognized boundary type %d", type);
   phb_mesh *m = f->m;
   const int p = phb_mesh_patch_id(m, patch);
+  // a partitioned mesh only carries the patches that touch it: boundary input for
+  // the others is ignored, as setBoundaryTypes does (UF/FiniteVolumeField.tpp:452-476)
+  if (p < 0 && m->nProcs > 1) return PHB_OK;
   PHB_REQUIRE(p >= 0, "phb_field_set_bc: no patch named \"%s\"", patch);
   f->bc[p].type = type; f->bc[p].vx = vx; f->bc[p].vy = vy;
   f->bcDirty = true;
