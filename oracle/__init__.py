@@ -95,6 +95,10 @@ def lib():
         L.or_fs_last_iters.argtypes = [vp, C.c_int]
         L.or_op_laplacian_field.restype = vp
         L.or_op_laplacian_field.argtypes = [vp, C.POINTER(C.c_double)]
+        L.or_op_ueqn_multiphase.restype = vp
+        L.or_op_ueqn_multiphase.argtypes = [vp, C.c_double] + [C.POINTER(C.c_double)] * 5
+        L.or_op_scalar_transport.restype = vp
+        L.or_op_scalar_transport.argtypes = [vp, C.c_double, C.c_double] + [C.POINTER(C.c_double)] * 4
         L.or_bicgstab.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int,
@@ -359,6 +363,14 @@ class FracStep:
     def laplacian_field(self, gamma_face):
         g = np.ascontiguousarray(gamma_face, dtype=np.float64)
         return Crs(handle=lib().or_op_laplacian_field(self.h, _dp(g)))
+
+    def ueqn_multiphase(self, dt, rho_cell, mu_face, mu0_face, fx, fy):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (rho_cell, mu_face, mu0_face, fx, fy)]
+        return Crs(handle=lib().or_op_ueqn_multiphase(self.h, dt, *[_dp(v) for v in a]))
+
+    def scalar_transport(self, dt, theta, rho, rho0, phi0, phi0f):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (rho, rho0, phi0, phi0f)]
+        return Crs(handle=lib().or_op_scalar_transport(self.h, dt, theta, *[_dp(v) for v in a]))
 
     def view(self, name):
         """Writable numpy view of a field array (ux, uy, ufx, ufy, p, pf, gpx, ...)."""

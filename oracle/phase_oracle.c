@@ -1211,6 +1211,156 @@ OrCrs *or_op_laplacian_field(OrFracStep *s, const double *gammaFace) {
   return e;
 }
 
+
+/* ---------------------------------------------- multiphase-style operators */
+/* FiniteVolumeEquation<Vector2D> operator*(ScalarField rho, eqn): scaleRow of
+ * rows (P,0),(P,1): UE/VectorFiniteVolumeEquation.cpp:163-170, M/CrsEquation.cpp:153-159 */
+static void veq_scale_rows(OrFracStep *s, OrCrs *e, const double *rho) {
+  OrMesh *m = s->m;
+  for (int c = 0; c < m->nCells; ++c) {
+    if (m->owner[c] != m->rank) continue;
+    or_crs_scale_row(e, m->localRow[c], rho[c]);
+    or_crs_scale_row(e, m->nLocal + m->localRow[c], rho[c]);
+  }
+}
+
+/* uEqn_ = (rho*fv::ddt(u,dt) + rho*fv::dive(u,u,0.5) == fv::laplacian(mu,u,0.5) + src::src(f)):
+ * US/FractionalStepMultiphase.cpp:111-112; UD/TimeDerivative.h:37-48; UD/ExplicitDivergence.h:7-51
+ * (oldField(0) and oldField(1) are the SAME buffer); UD/Laplacian.cpp:66-119
+ * (field gamma, diagonal added first); UD/Source.cpp:86-95.  f = cell vector field (fx, fy). */
+OrCrs *or_op_ueqn_multiphase(OrFracStep *s, double dt, const double *rhoCell,
+                             const double *muFace, const double *mu0Face,
+                             const double *fx, const double *fy) {
+  OrMesh *m = s->m;
+  int N = m->nCells, nl = m->nLocal;
+  double theta = 0.5;
+  OrCrs *e1 = or_crs_create(2 * nl, 5);
+  for (int c = 0; c < N; ++c) {
+    if (m->owner[c] != m->rank) continue;
+    veq_add(s, e1, c, c, m->vol[c] / dt);
+    int r = m->localRow[c];
+    e1->rhs[r] += -m->vol[c] * s->u0x[c] / dt;
+    e1->rhs[nl + r] += -m->vol[c] * s->u0y[c] / dt;
+  }
+  veq_scale_rows(s, e1, rhoCell);
+  OrCrs *e2 = or_crs_create(2 * nl, 5);
+  for (int c = 0; c < N; ++c) {
+    if (m->owner[c] != m->rank) continue;
+    int r = m->localRow[c];
+    for (int j = m->ilPtr[c]; j < m->ilPtr[c + 1]; ++j) {
+      int f = m->ilFace[j], nb = m->ilCell[j];
+      double flux0 = s->u0fx[f] * m->ilSx[j] + s->u0fy[f] * m->ilSy[j];
+      double flux1 = flux0; /* aliased history */
+      double a0 = theta * fmax(flux0, 0.), b0 = theta * fmin(flux0, 0.);
+      double a1 = (1. - theta) * fmax(flux1, 0.), b1 = (1. - theta) * fmin(flux1, 0.);
+      e2->rhs[r] += a0 * s->u0x[c]; e2->rhs[nl + r] += a0 * s->u0y[c];
+      e2->rhs[r] += b0 * s->u0x[nb]; e2->rhs[nl + r] += b0 * s->u0y[nb];
+      e2->rhs[r] += a1 * s->u0x[c]; e2->rhs[nl + r] += a1 * s->u0y[c];
+      e2->rhs[r] += b1 * s->u0x[nb]; e2->rhs[nl + r] += b1 * s->u0y[nb];
+    }
+    for (int j = m->blPtr[c]; j < m->blPtr[c + 1]; ++j) {
+      int f = m->blFace[j];
+      int t = bc_type(s->ubc, m, f);
+      if (t != OR_FIXED && t != OR_NORMAL_GRADIENT) continue;
+      double flux0 = s->u0fx[f] * m->blSx[j] + s->u0fy[f] * m->blSy[j];
+      double flux1 = flux0;
+      e2->rhs[r] += theta * flux0 * s->u0fx[f]; e2->rhs[nl + r] += theta * flux0 * s->u0fy[f];
+      e2->rhs[r] += (1. - theta) * flux1 * s->u0fx[f]; e2->rhs[nl + r] += (1. - theta) * flux1 * s->u0fy[f];
+    }
+  }
+  veq_scale_rows(s, e2, rhoCell);
+  or_crs_add_eq(e1, e2);
+  or_crs_destroy(e2);
+  OrCrs *e3 = or_crs_create(2 * nl, 5);
+  for (int c = 0; c < N; ++c) {
+    if (m->owner[c] != m->rank) continue;
+    int r = m->localRow[c];
+    for (int j = m->ilPtr[c]; j < m->ilPtr[c + 1]; ++j) {
+      int f = m->ilFace[j], nb = m->ilCell[j];
+      double g = (m->ilRcx[j] * m->ilSx[j] + m->ilRcy[j] * m->ilSy[j]) /
+                 (m->ilRcx[j] * m->ilRcx[j] + m->ilRcy[j] * m->ilRcy[j]);
+      double coeff = muFace[f] * g, coeff0 = mu0Face[f] * g;
+      veq_add(s, e3, c, c, theta * -coeff);
+      veq_add(s, e3, c, nb, theta * coeff);
+      double a = (1. - theta) * coeff0;
+      e3->rhs[r] += a * (s->u0x[nb] - s->u0x[c]);
+      e3->rhs[nl + r] += a * (s->u0y[nb] - s->u0y[c]);
+    }
+    for (int j = m->blPtr[c]; j < m->blPtr[c + 1]; ++j) {
+      int f = m->blFace[j];
+      if (bc_type(s->ubc, m, f) != OR_FIXED) continue;
+      double g = (m->blRfx[j] * m->blSx[j] + m->blRfy[j] * m->blSy[j]) /
+                 (m->blRfx[j] * m->blRfx[j] + m->blRfy[j] * m->blRfy[j]);
+      double coeff = muFace[f] * g, coeff0 = mu0Face[f] * g;
+      veq_add(s, e3, c, c, theta * -coeff);
+      e3->rhs[r] += theta * coeff * s->ufx[f]; e3->rhs[nl + r] += theta * coeff * s->ufy[f];
+      double a = (1. - theta) * coeff0;
+      e3->rhs[r] += a * (s->u0fx[f] - s->u0x[c]);
+      e3->rhs[nl + r] += a * (s->u0fy[f] - s->u0y[c]);
+    }
+  }
+  for (int c = 0; c < N; ++c) { /* + src::src(f) */
+    if (m->owner[c] != m->rank) continue;
+    int r = m->localRow[c];
+    e3->rhs[r] += fx[c] * m->vol[c];
+    e3->rhs[nl + r] += fy[c] * m->vol[c];
+  }
+  or_crs_sub_eq(e1, e3);
+  or_crs_destroy(e3);
+  return e1;
+}
+
+/* scalar transport on the "p" field: (fv::ddt(rho, phi, dt) + fv::div(u, phi, theta) == 0):
+ * UD/TimeDerivative.h:21-35 (rho(cell), rho0(cell)); UD/Divergence.h:8-53 with the
+ * theta-weighted matrix part and FIXED / NORMAL_GRADIENT boundary handling.
+ * phi = s->p / s->pf, old level phi0 given. */
+OrCrs *or_op_scalar_transport(OrFracStep *s, double dt, double theta, const double *rho,
+                              const double *rho0, const double *phi0, const double *phi0f) {
+  OrMesh *m = s->m;
+  int N = m->nCells, nl = m->nLocal;
+  OrCrs *e1 = or_crs_create(nl, 5);
+  for (int c = 0; c < N; ++c) {
+    if (m->owner[c] != m->rank) continue;
+    int r = m->localRow[c];
+    or_crs_add_coeff(e1, r, m->globalRow[c], rho[c] * m->vol[c] / dt);
+    e1->rhs[r] += -rho0[c] * m->vol[c] * phi0[c] / dt;
+  }
+  OrCrs *e2 = or_crs_create(nl, 5);
+  for (int c = 0; c < N; ++c) {
+    if (m->owner[c] != m->rank) continue;
+    int r = m->localRow[c];
+    for (int j = m->ilPtr[c]; j < m->ilPtr[c + 1]; ++j) {
+      int f = m->ilFace[j], nb = m->ilCell[j];
+      double flux = s->ufx[f] * m->ilSx[j] + s->ufy[f] * m->ilSy[j];
+      double flux0 = s->u0fx[f] * m->ilSx[j] + s->u0fy[f] * m->ilSy[j];
+      or_crs_add_coeff(e2, r, m->globalRow[c], theta * fmax(flux, 0.));
+      or_crs_add_coeff(e2, r, m->globalRow[nb], theta * fmin(flux, 0.));
+      e2->rhs[r] += (1. - theta) * fmax(flux0, 0.) * phi0[c];
+      e2->rhs[r] += (1. - theta) * fmin(flux0, 0.) * phi0[nb];
+    }
+    for (int j = m->blPtr[c]; j < m->blPtr[c + 1]; ++j) {
+      int f = m->blFace[j];
+      double flux = s->ufx[f] * m->blSx[j] + s->ufy[f] * m->blSy[j];
+      double flux0 = s->u0fx[f] * m->blSx[j] + s->u0fy[f] * m->blSy[j];
+      switch (bc_type(s->pbc, m, f)) {
+      case OR_FIXED:
+        e2->rhs[r] += theta * flux * s->pf[f];
+        e2->rhs[r] += (1. - theta) * flux0 * phi0f[f];
+        break;
+      case OR_NORMAL_GRADIENT:
+        or_crs_add_coeff(e2, r, m->globalRow[c], theta * flux);
+        e2->rhs[r] += (1. - theta) * flux0 * phi0[c];
+        break;
+      default:
+        break;
+      }
+    }
+  }
+  or_crs_add_eq(e1, e2);
+  or_crs_destroy(e2);
+  return e1;
+}
+
 const OrCrs *or_fs_ueqn(const OrFracStep *s) { return s->uEqn; }
 const OrCrs *or_fs_peqn(const OrFracStep *s) { return s->pEqn; }
 

@@ -107,6 +107,14 @@ int or_fs_last_iters(const OrFracStep *s, int which);
  * (FractionalStepMultiphase::solvePEqn), gammaCell/gammaFace given. */
 OrCrs *or_op_laplacian_field(OrFracStep *s, const double *gammaFace);
 
+/* uEqn_ of FractionalStepMultiphase (rho*ddt + rho*dive == laplacian(mu) + src(f)) */
+OrCrs *or_op_ueqn_multiphase(OrFracStep *s, double dt, const double *rhoCell,
+                             const double *muFace, const double *mu0Face,
+                             const double *fx, const double *fy);
+/* (fv::ddt(rho, phi, dt) + fv::div(u, phi, theta) == 0) on the scalar field "p" */
+OrCrs *or_op_scalar_transport(OrFracStep *s, double dt, double theta, const double *rho,
+                              const double *rho0, const double *phi0, const double *phi0f);
+
 /* ---- built-in CPU solver (OpenMP BiCGStab, Jacobi or ILU(0)) ---- */
 /* precond: 0 none, 1 Jacobi, 2 ILU(0).  returns iterations, *relres out.
  * x holds the initial guess on entry. */

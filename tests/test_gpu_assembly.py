@@ -107,3 +107,79 @@ def test_field_glue_matches_oracle(comm):
     assert np.allclose(uf[1], ofs.view("ufy"), rtol=1e-14, atol=1e-15)
     assert np.allclose(gfs.p.get("faces"), ofs.view("pf"), rtol=0, atol=0)
     gfs.close(); g.close()
+
+
+def test_multiphase_momentum_equation(comm):
+    """uEqn_ = (rho*fv::ddt(u,dt) + rho*fv::dive(u,u,0.5) == fv::laplacian(mu,u,0.5) + src::src(f)),
+    US/FractionalStepMultiphase.cpp:111-112: ddt, dive (aliased history), field laplacian with theta,
+    row scaling, vector source."""
+    from phase_b200.api import FiniteVolumeField, FiniteVolumeEquation
+    om, ofs = oracle_cavity("tri", 6, 7, 1.0, 1.2)
+    g, gfs = gpu_cavity(comm, "tri", 6, 7, 1.0, 1.2)
+    set_random_state(ofs, gfs, seed=9)
+    rng = np.random.default_rng(10)
+    N, F = om.sizes["nCells"], om.sizes["nFaces"]
+    rho = rng.uniform(1.0, 900.0, N)
+    mu, mu0 = rng.uniform(1e-3, 1.0, F), rng.uniform(1e-3, 1.0, F)
+    fx, fy = rng.standard_normal(N), rng.standard_normal(N)
+    dt = 0.004
+    want = ofs.ueqn_multiphase(dt, rho, mu, mu0, fx, fy).export()
+    rhoF, muF, fF = FiniteVolumeField(g, 1, "rho"), FiniteVolumeField(g, 1, "mu"), FiniteVolumeField(g, 2, "f")
+    rhoF.set("cells", rho)
+    muF.set("faces", mu0); muF.savePreviousTimeStep(); muF.set("faces", mu)
+    fF.set("cells", np.concatenate([fx, fy]))
+    eq = FiniteVolumeEquation(gfs.u).zero()
+    eq.ddt(gfs.u, dt).dive(gfs.u, gfs.u, 0.5).scaleRows(rhoF)
+    eq.laplacian(muF, gfs.u, 0.5, sign=-1.0).src(fF, sign=-1.0)
+    assert_eqn_equal(eq.export(0), want, rtol=5e-13)
+    for o in (eq, rhoF, muF, fF, gfs, g):
+        o.close()
+
+
+@pytest.mark.parametrize("theta", [1.0, 0.5])
+def test_scalar_transport_with_density_field(comm, theta):
+    """(fv::ddt(rho, phi, dt) + fv::div(u, phi, theta) == 0): implicit upwind matrix part,
+    FIXED and NORMAL_GRADIENT boundary branches (UD/Divergence.h:27-45), rho/rho0 fields."""
+    from phase_b200.api import FiniteVolumeGrid2D as G, FractionalStep, FiniteVolumeField, FiniteVolumeEquation, FIXED, NORMAL_GRADIENT
+    om = O.Mesh.rectilinear(11, 6, 2.0, 1.0)
+    ofs = O.FracStep(om, 1.0, 1.0)
+    g = G.rectilinear(comm, 11, 6, 2.0, 1.0)
+    gfs = FractionalStep(g, 1.0, 1.0)
+    for pt, t, v in (("x-", FIXED, 1.0), ("x+", NORMAL_GRADIENT, 0.0), ("y-", NORMAL_GRADIENT, 0.0), ("y+", FIXED, 0.0)):
+        ofs.set_bc("p", pt, t, v); gfs.p.setBoundary(pt, t, v)
+    ofs.initialize(); gfs.initialize()
+    set_random_state(ofs, gfs, seed=21)
+    # the random state overwrote boundary faces of p on both sides identically: fine for parity
+    rng = np.random.default_rng(22)
+    N, F = om.sizes["nCells"], om.sizes["nFaces"]
+    rho, rho0 = rng.uniform(1, 5, N), rng.uniform(1, 5, N)
+    phi0, phi0f = rng.standard_normal(N), rng.standard_normal(F)
+    dt = 0.01
+    want = ofs.scalar_transport(dt, theta, rho, rho0, phi0, phi0f).export()
+    rhoF = FiniteVolumeField(g, 1, "rho")
+    rhoF.set("cells", rho0); rhoF.savePreviousTimeStep(); rhoF.set("cells", rho)
+    pc, pf = gfs.p.get("cells").copy(), gfs.p.get("faces").copy()
+    gfs.p.set("cells", phi0); gfs.p.set("faces", phi0f); gfs.p.savePreviousTimeStep()
+    gfs.p.set("cells", pc); gfs.p.set("faces", pf)
+    eq = FiniteVolumeEquation(gfs.p).zero().ddt(gfs.p, dt, rho=rhoF).div(gfs.u, gfs.p, theta)
+    assert_eqn_equal(eq.export(0), want, rtol=5e-13)
+    for o in (eq, rhoF, gfs, g):
+        o.close()
+
+
+def test_relax(comm):
+    """relax(omega): a_PP /= omega; rhs_P -= (1-omega) a_PP phi_P (UE/ScalarFiniteVolumeEquation.cpp:45-55)."""
+    om, ofs = oracle_cavity("rect", 7, 6)
+    g, gfs = gpu_cavity(comm, "rect", 7, 6)
+    set_random_state(ofs, gfs, seed=4)
+    eq = gfs.assembleU(0.01)
+    rp, ci, va, rhs = eq.export(0)
+    u = gfs.u.get("cells").reshape(-1)
+    eq.relax(0.8)
+    rp2, ci2, va2, rhs2 = eq.export(0)
+    assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2)
+    diag = rp[:-1]
+    va_want = va.copy(); va_want[diag] = va[diag] / 0.8
+    assert np.allclose(va2, va_want, rtol=1e-15)
+    assert np.allclose(rhs2, rhs - 0.2 * va_want[diag] * u, rtol=1e-14, atol=1e-14)
+    gfs.close(); g.close()
