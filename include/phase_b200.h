@@ -122,6 +122,9 @@ int phb_mesh_create_local(phb_ctx *ctx, const phb_mesh *global,
  * same result as create_rectilinear + that partition + create_local. */
 int phb_mesh_create_rect_strip(phb_ctx *ctx, int nx, int ny, double width,
                                double height, phb_mesh **out);
+/* same for a px x py block partition (rank q = bj*px + bi); px*py = nProcs */
+int phb_mesh_create_rect_block(phb_ctx *ctx, int nx, int ny, double width,
+                               double height, int px, int py, phb_mesh **out);
 
 /* ------------------------------------------------------------ linear solver
  * Seam 1.  Beneath class SparseMatrixSolver (M/SparseMatrixSolver.h:11-62):

@@ -39,6 +39,7 @@ SIGNATURES = {
     "phb_partition_rcb": (ci, [vp, ci, pi]),
     "phb_mesh_create_local": (ci, [vp, vp, pi, pvp]),
     "phb_mesh_create_rect_strip": (ci, [vp, ci, ci, cd, cd, pvp]),
+    "phb_mesh_create_rect_block": (ci, [vp, ci, ci, cd, cd, ci, ci, pvp]),
     "phb_solver_create": (ci, [vp, pvp]),
     "phb_solver_destroy": (ci, [vp]),
     "phb_solver_setup": (ci, [vp, cs, cs]),

@@ -101,6 +101,13 @@ class FiniteVolumeGrid2D:
         check(comm.L.phb_mesh_create_rect_strip(comm.h, nx, ny, width, height, C.byref(h)))
         return cls(comm, h)
 
+    @classmethod
+    def rectilinear_block(cls, comm, nx, ny, width, height, px, py):
+        """Local mesh of comm's rank for a px x py block partition (no global mesh is built)."""
+        h = C.c_void_p()
+        check(comm.L.phb_mesh_create_rect_block(comm.h, nx, ny, width, height, px, py, C.byref(h)))
+        return cls(comm, h)
+
     def createPatchByNodes(self, name, pairs):
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1)
         return check(self.L.phb_mesh_add_patch_by_nodes(self.h, name.encode(), len(pairs) // 2, _ip(pairs)))

@@ -1,0 +1,315 @@
+// ilu.cu -- ILU(0) preconditioner (K10): symbolic analysis on the host, numeric
+// factorisation and the two triangular sweeps on the device, scheduled by
+// independent-set blocks ("levels").
+//
+// Replaces what the reference gets from Ifpack2: additive Schwarz (overlap 0) with
+// an inner RILUK, fill level 0 (M/TrilinosBelosSparseMatrixSolver.cpp:63-83).  The
+// preconditioner is rank-local: ghost columns are ignored, which is exactly
+// Schwarz overlap 0.
+//
+// Scheduling.  Rows are split into ordered independent sets (no two rows of a set
+// are adjacent), either by greedy multicolouring ("multicolor": 2 sets for quads,
+// 3-4 for triangles) or by the wavefront levels of the given ordering ("levels":
+// the natural-order ILU(0), ~2 sqrt(N) sets on grid-like meshes).  The system is
+// symmetrically permuted so that every set is a contiguous row range; L holds the
+// entries whose column lies in an earlier set, U those in a later one.  One launch
+// per set and sweep; sets without lower (upper) entries need no matrix read.
+#include <algorithm>
+#include <numeric>
+
+#include "kernels.cuh"
+#include "solver.cuh"
+
+using namespace phb;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct IluView {
+  const int *sliceOff, *col, *rowLen, *diagK, *blockOf;
+  const signed char *kind;
+  int nRows;
+};
+
+__device__ __forceinline__ size_t slot_of(const int *sliceOff, int row, int k) {
+  return (size_t)sliceOff[row >> 5] + (size_t)k * 32 + (row & 31);
+}
+
+__global__ void k_permute_vals(long long nSlots, const int *__restrict__ slotMap, const double *__restrict__ src,
+                               double *__restrict__ a, double *__restrict__ lu) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nSlots;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int o = slotMap[i];
+    const double v = o >= 0 ? src[o] : 0.;
+    a[i] = v;
+    lu[i] = v;
+  }
+}
+
+// numeric ILU(0) of the rows [r0, r1) of one set: IKJ with the lower entries taken
+// in ascending set order; rows of earlier sets are final.
+__global__ void k_ilu_factor(IluView V, double *__restrict__ lu, int r0, int r1) {
+  const int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= r1) return;
+  const int len = V.rowLen[i];
+  unsigned long long done = 0ull;
+  for (;;) {
+    int e = -1, eb = 0x7fffffff;
+    for (int k = 0; k < len && k < 64; ++k) {
+      if ((done >> k) & 1ull) continue;
+      const size_t sl = slot_of(V.sliceOff, i, k);
+      if (V.kind[sl] != 1) continue;
+      const int b = V.blockOf[V.col[sl]];
+      if (b < eb) { eb = b; e = k; }
+    }
+    if (e < 0) break;
+    done |= 1ull << e;
+    const size_t se = slot_of(V.sliceOff, i, e);
+    const int kr = V.col[se];
+    const double lik = lu[se] / lu[slot_of(V.sliceOff, kr, V.diagK[kr])];
+    lu[se] = lik;
+    const int klen = V.rowLen[kr];
+    for (int f = 0; f < klen; ++f) {
+      const size_t sf = slot_of(V.sliceOff, kr, f);
+      if (V.kind[sf] != 3) continue;
+      const int j = V.col[sf];
+      for (int g = 0; g < len; ++g) {
+        const size_t sg = slot_of(V.sliceOff, i, g);
+        if (V.kind[sg] != 0 && V.col[sg] == j) { lu[sg] -= lik * lu[sf]; break; }
+      }
+    }
+  }
+}
+
+// forward sweep of one set: z_i = r_i - sum_{lower} l_ik z_k   (unit diagonal)
+template <int NC, bool HAS_LOWER>
+__global__ void k_ilu_fwd(IluView V, const double *__restrict__ lu, const double *__restrict__ r,
+                          double *__restrict__ z, int ld, int r0, int r1) {
+  const int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= r1) return;
+  double acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = r[(size_t)c * ld + i];
+  if (HAS_LOWER) {
+    const int len = V.rowLen[i];
+    for (int k = 0; k < len; ++k) {
+      const size_t sl = slot_of(V.sliceOff, i, k);
+      if (V.kind[sl] != 1) continue;
+      const double l = lu[sl];
+      const int j = V.col[sl];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] -= l * z[(size_t)c * ld + j];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) z[(size_t)c * ld + i] = acc[c];
+}
+
+// backward sweep of one set: z_i = (z_i - sum_{upper} u_ij z_j) / u_ii
+template <int NC, bool HAS_UPPER>
+__global__ void k_ilu_bwd(IluView V, const double *__restrict__ lu, double *__restrict__ z, int ld, int r0,
+                          int r1) {
+  const int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= r1) return;
+  double acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = z[(size_t)c * ld + i];
+  if (HAS_UPPER) {
+    const int len = V.rowLen[i];
+    for (int k = 0; k < len; ++k) {
+      const size_t sl = slot_of(V.sliceOff, i, k);
+      if (V.kind[sl] != 3) continue;
+      const double u = lu[sl];
+      const int j = V.col[sl];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] -= u * z[(size_t)c * ld + j];
+    }
+  }
+  const double d = lu[slot_of(V.sliceOff, i, V.diagK[i])];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) z[(size_t)c * ld + i] = acc[c] / d;
+}
+
+// y[c][new] = x[c][old] (gather, dir 0) or y[c][old] = x[c][new] (scatter, dir 1) over owned rows
+__global__ void k_permute_vec(int n, int nc, int ld, const int *__restrict__ new2old,
+                              const double *__restrict__ x, double *__restrict__ y, int dir) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)n * nc;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t / n), i = (int)(t - (long long)c * n);
+    const int o = new2old[i];
+    if (dir == 0) y[(size_t)c * ld + i] = x[(size_t)c * ld + o];
+    else y[(size_t)c * ld + o] = x[(size_t)c * ld + i];
+  }
+}
+
+IluView view_of(const IluData &D) {
+  IluView v;
+  v.sliceOff = D.pat.sliceOff.p; v.col = D.pat.col.p; v.rowLen = D.pat.rowLen.p;
+  v.diagK = D.diagK.p; v.blockOf = D.blockOf.p; v.kind = D.kind.p; v.nRows = D.pat.nRows;
+  return v;
+}
+
+}  // namespace
+
+namespace phb {
+
+// symbolic phase, cached per (pattern, ordering)
+int ilu_prepare(phb_solver *s, const SellPattern *P, const phb_mesh *halo) {
+  IluData &D = s->ilu;
+  if (D.src == P && D.ordering == s->iluOrdering && D.srcSlots == P->nSlots) return PHB_OK;
+  cudaStream_t st = s->ctx->stream;
+  const int n = P->nRows;
+  auto oslot = [&](int r, int k) { return (size_t)P->hSliceOff[r >> 5] + (size_t)k * 32 + (r & 31); };
+  // ordered independent sets
+  std::vector<int> block(n, 0);
+  int nBlocks = 1;
+  if (s->iluOrdering == 0) {  // greedy multicolouring in the given order
+    std::vector<int> mark;
+    for (int i = 0; i < n; ++i) {
+      mark.assign(16, 0);
+      for (int k = 0; k < P->hRowLen[i]; ++k) {
+        const int j = P->hCol[oslot(i, k)];
+        if (j >= n || j >= i) continue;
+        if (block[j] >= (int)mark.size()) mark.resize(block[j] + 1, 0);
+        mark[block[j]] = 1;
+      }
+      int c = 0;
+      while (c < (int)mark.size() && mark[c]) ++c;
+      block[i] = c;
+      nBlocks = std::max(nBlocks, c + 1);
+    }
+  } else {  // wavefront levels of the given (natural) ordering
+    for (int i = 0; i < n; ++i) {
+      int lv = 0;
+      for (int k = 0; k < P->hRowLen[i]; ++k) {
+        const int j = P->hCol[oslot(i, k)];
+        if (j < i) lv = std::max(lv, block[j] + 1);
+      }
+      block[i] = lv;
+      nBlocks = std::max(nBlocks, lv + 1);
+    }
+  }
+  // symmetric permutation: rows sorted by set (stable)
+  std::vector<int> new2old(n), old2new(n);
+  std::iota(new2old.begin(), new2old.end(), 0);
+  std::stable_sort(new2old.begin(), new2old.end(), [&](int a, int b) { return block[a] < block[b]; });
+  for (int i = 0; i < n; ++i) old2new[new2old[i]] = i;
+  D.blockPtr.assign(nBlocks + 1, 0);
+  for (int i = 0; i < n; ++i) D.blockPtr[block[i] + 1]++;
+  std::partial_sum(D.blockPtr.begin(), D.blockPtr.end(), D.blockPtr.begin());
+  // permuted sliced-ELL pattern
+  SellPattern &Q = D.pat;
+  Q.nRows = n; Q.nCols = P->nCols; Q.nSlices = (n + 31) / 32; Q.nnz = P->nnz;
+  Q.hRowLen.resize(n);
+  for (int i = 0; i < n; ++i) Q.hRowLen[i] = P->hRowLen[new2old[i]];
+  Q.hSliceOff.assign(Q.nSlices + 1, 0);
+  for (int sl = 0; sl < Q.nSlices; ++sl) {
+    int w = 1;
+    for (int r = sl * 32; r < std::min(n, sl * 32 + 32); ++r) w = std::max(w, Q.hRowLen[r]);
+    Q.hSliceOff[sl + 1] = Q.hSliceOff[sl] + w * 32;
+  }
+  Q.nSlots = Q.hSliceOff[Q.nSlices];
+  Q.hCol.assign(Q.nSlots, 0);
+  std::vector<int> slotMap(Q.nSlots, -1), diagK(n, 0), blockOf(n);
+  std::vector<signed char> kind(Q.nSlots, 0);
+  D.hasLower.assign(nBlocks, 0); D.hasUpper.assign(nBlocks, 0);
+  for (int i = 0; i < n; ++i) blockOf[i] = block[new2old[i]];
+  for (int sl = 0; sl < Q.nSlices; ++sl) {
+    const int w = (Q.hSliceOff[sl + 1] - Q.hSliceOff[sl]) / 32;
+    for (int lane = 0; lane < 32; ++lane) {
+      const int r = sl * 32 + lane;
+      for (int k = 0; k < w; ++k) {
+        const size_t ns = (size_t)Q.hSliceOff[sl] + (size_t)k * 32 + lane;
+        if (r >= n) { Q.hCol[ns] = n - 1; continue; }
+        if (k >= Q.hRowLen[r]) { Q.hCol[ns] = r; continue; }
+        const int o = new2old[r];
+        const size_t os = oslot(o, k);
+        const int oc = P->hCol[os];
+        slotMap[ns] = (int)os;
+        if (oc >= n) { Q.hCol[ns] = oc; continue; }   // ghost column: not part of the local factor
+        const int nc = old2new[oc];
+        Q.hCol[ns] = nc;
+        if (nc == r) { kind[ns] = 2; diagK[r] = k; }
+        else if (blockOf[nc] < blockOf[r]) { kind[ns] = 1; D.hasLower[blockOf[r]] = 1; }
+        else { kind[ns] = 3; D.hasUpper[blockOf[r]] = 1; }
+      }
+    }
+  }
+  PHB_CHECK(Q.sliceOff.upload(Q.hSliceOff, st)); PHB_CHECK(Q.rowLen.upload(Q.hRowLen, st));
+  PHB_CHECK(Q.col.upload(Q.hCol, st));
+  PHB_CHECK(D.slotMap.upload(slotMap, st)); PHB_CHECK(D.diagK.upload(diagK, st));
+  PHB_CHECK(D.blockOf.upload(blockOf, st)); PHB_CHECK(D.kind.upload(kind, st));
+  PHB_CHECK(D.new2old.upload(new2old, st));
+  PHB_CHECK(D.vals.alloc((size_t)Q.nSlots)); PHB_CHECK(D.lu.alloc((size_t)Q.nSlots));
+  // halo send list in the permuted numbering
+  std::vector<int> send;
+  if (halo)
+    for (int d : halo->hSendDev) send.push_back(old2new[d]);
+  PHB_CHECK(D.sendDev.upload(send, st));
+  PHB_CUDA(cudaStreamSynchronize(st));
+  D.src = P; D.srcSlots = P->nSlots; D.ordering = s->iluOrdering; D.nBlocks = nBlocks;
+  if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
+  return PHB_OK;
+}
+
+int ilu_factor(phb_solver *s, const double *vals) {
+  IluData &D = s->ilu;
+  phb_ctx *c = s->ctx;
+  const long long nSlots = D.pat.nSlots;
+  const int g = (int)std::max<long long>(1, std::min<long long>((nSlots + kThreads - 1) / kThreads, (long long)c->numSMs * 8));
+  PHB_LAUNCH(c, k_permute_vals, g, kThreads, 0, nSlots, D.slotMap.p, vals, D.vals.p, D.lu.p);
+  const IluView V = view_of(D);
+  for (int b = 0; b < D.nBlocks; ++b) {
+    if (!D.hasLower[b]) continue;
+    const int r0 = D.blockPtr[b], r1 = D.blockPtr[b + 1];
+    if (r1 > r0) PHB_LAUNCH(c, k_ilu_factor, (r1 - r0 + kThreads - 1) / kThreads, kThreads, 0, V, D.lu.p, r0, r1);
+  }
+  return PHB_OK;
+}
+
+// z = U^-1 L^-1 r  (vectors in the permuted numbering, leading dimension ld)
+int ilu_apply(phb_solver *s, const double *r, double *z) {
+  IluData &D = s->ilu;
+  phb_ctx *c = s->ctx;
+  const IluView V = view_of(D);
+  const int ld = s->ld;
+#define ILU_LAUNCH(K, NCV, FLAG, ...)                                                          \
+  do {                                                                                         \
+    if (FLAG) PHB_LAUNCH(c, (K<NCV, true>), grid, kThreads, 0, __VA_ARGS__);                   \
+    else PHB_LAUNCH(c, (K<NCV, false>), grid, kThreads, 0, __VA_ARGS__);                       \
+  } while (0)
+  for (int b = 0; b < D.nBlocks; ++b) {
+    const int r0 = D.blockPtr[b], r1 = D.blockPtr[b + 1];
+    if (r1 <= r0) continue;
+    const int grid = (r1 - r0 + kThreads - 1) / kThreads;
+    if (s->nComp == 1) ILU_LAUNCH(k_ilu_fwd, 1, D.hasLower[b], V, D.lu.p, r, z, ld, r0, r1);
+    else ILU_LAUNCH(k_ilu_fwd, 2, D.hasLower[b], V, D.lu.p, r, z, ld, r0, r1);
+  }
+  for (int b = D.nBlocks - 1; b >= 0; --b) {
+    const int r0 = D.blockPtr[b], r1 = D.blockPtr[b + 1];
+    if (r1 <= r0) continue;
+    const int grid = (r1 - r0 + kThreads - 1) / kThreads;
+    if (s->nComp == 1) ILU_LAUNCH(k_ilu_bwd, 1, D.hasUpper[b], V, D.lu.p, z, ld, r0, r1);
+    else ILU_LAUNCH(k_ilu_bwd, 2, D.hasUpper[b], V, D.lu.p, z, ld, r0, r1);
+  }
+#undef ILU_LAUNCH
+  return PHB_OK;
+}
+
+int ilu_permute(phb_solver *s, const double *x, double *y, int dir) {
+  phb_ctx *c = s->ctx;
+  const int n = s->ilu.pat.nRows;
+  const long long work = (long long)n * s->nComp;
+  const int g = (int)std::max<long long>(1, std::min<long long>((work + kThreads - 1) / kThreads, (long long)c->numSMs * 8));
+  PHB_LAUNCH(c, k_permute_vec, g, kThreads, 0, n, s->nComp, s->ld, s->ilu.new2old.p, x, y, dir);
+  return PHB_OK;
+}
+
+int ilu_launches_per_apply(const phb_solver *s) {
+  int k = 0;
+  for (int b = 0; b < s->ilu.nBlocks; ++b) k += (s->ilu.blockPtr[b + 1] > s->ilu.blockPtr[b]) ? 2 : 0;
+  return k;
+}
+
+}  // namespace phb

@@ -649,26 +649,33 @@ int phb_mesh_create_local(phb_ctx *ctx, const phb_mesh *g, const int *part, phb_
   PHB_TRY_END
 }
 
-// Local mesh of a y-strip partition of an nx x ny rectilinear grid, built WITHOUT
-// materialising the global mesh (weak-scaling runs): rank r owns rows
-// [r ny/P, (r+1) ny/P); the result is identical (numbering, patches, halo maps) to
-// phb_mesh_create_rectilinear + that partition vector + phb_mesh_create_local.
-int phb_mesh_create_rect_strip(phb_ctx *ctx, int nx, int ny, double w, double h, phb_mesh **out) {
+// Local mesh of a px x py block partition of an nx x ny rectilinear grid, built
+// WITHOUT materialising the global mesh (weak-scaling runs): rank q = bj px + bi owns
+// columns [bi nx/px, (bi+1) nx/px) x rows [bj ny/py, (bj+1) ny/py); the result is
+// identical (numbering, patches, halo maps) to phb_mesh_create_rectilinear + that
+// partition vector + phb_mesh_create_local.
+int phb_mesh_create_rect_block(phb_ctx *ctx, int nx, int ny, double w, double h, int px, int py,
+                               phb_mesh **out) {
   PHB_TRY_BEGIN
-  PHB_REQUIRE(ctx && out && nx > 0 && ny > 0 && w > 0 && h > 0, "phb_mesh_create_rect_strip: bad argument");
+  PHB_REQUIRE(ctx && out && nx > 0 && ny > 0 && w > 0 && h > 0, "phb_mesh_create_rect_block: bad argument");
   const int rank = ctx->rank, P = ctx->nProcs;
-  PHB_REQUIRE(ny >= P, "phb_mesh_create_rect_strip: fewer rows than ranks");
-  auto rowOwner = [&](int j) { return (int)(((long long)j * P) / ny); };
-  auto firstRow = [&](int q) { return (int)(((long long)q * ny + P - 1) / P); };
-  const int j0 = firstRow(rank), j1 = (rank + 1 < P) ? firstRow(rank + 1) : ny;
-  const int jlo = std::max(0, j0 - 1), jhi = std::min(ny, j1 + 1);  // kept rows: face/node neighbours
+  PHB_REQUIRE(px >= 1 && py >= 1 && px * py == P, "phb_mesh_create_rect_block: px*py (%d*%d) != nProcs %d", px, py, P);
+  PHB_REQUIRE(ny >= py && nx >= px, "phb_mesh_create_rect_block: fewer rows/columns than blocks");
+  auto rowBlock = [&](int j) { return (int)(((long long)j * py) / ny); };
+  auto colBlock = [&](int i) { return (int)(((long long)i * px) / nx); };
+  auto firstRow = [&](int b) { return b >= py ? ny : (int)(((long long)b * ny + py - 1) / py); };
+  auto firstCol = [&](int b) { return b >= px ? nx : (int)(((long long)b * nx + px - 1) / px); };
+  const int bi = rank % px, bj = rank / px;
+  const int i0 = firstCol(bi), i1 = firstCol(bi + 1), j0 = firstRow(bj), j1 = firstRow(bj + 1);
+  // kept cells: the block plus its face/node neighbours (one ring)
+  const int ilo = std::max(0, i0 - 1), ihi = std::min(nx, i1 + 1), jlo = std::max(0, j0 - 1), jhi = std::min(ny, j1 + 1);
   const double hx0 = w / nx, hy0 = h / ny;
-  const int nnx = nx + 1;
-  std::vector<int> keep, cptr(1, 0), cind, localNode((size_t)(jhi - jlo + 1) * nnx, -1);
+  const int lnx = ihi - ilo + 1;  // local node columns
+  std::vector<int> keep, cptr(1, 0), cind, localNode((size_t)(jhi - jlo + 1) * lnx, -1);
   std::vector<double> xy;
-  keep.reserve((size_t)(jhi - jlo) * nx);
+  keep.reserve((size_t)(jhi - jlo) * (ihi - ilo));
   auto nodeId = [&](int i, int j) -> int {
-    int &ln = localNode[(size_t)(j - jlo) * nnx + i];
+    int &ln = localNode[(size_t)(j - jlo) * lnx + (i - ilo)];
     if (ln < 0) {
       ln = (int)(xy.size() / 2);
       xy.push_back(i * hx0); xy.push_back(j * hy0);
@@ -676,7 +683,7 @@ int phb_mesh_create_rect_strip(phb_ctx *ctx, int nx, int ny, double w, double h,
     return ln;
   };
   for (int j = jlo; j < jhi; ++j)
-    for (int i = 0; i < nx; ++i) {
+    for (int i = ilo; i < ihi; ++i) {
       keep.push_back(j * nx + i);
       cind.push_back(nodeId(i, j)); cind.push_back(nodeId(i + 1, j));
       cind.push_back(nodeId(i + 1, j + 1)); cind.push_back(nodeId(i, j + 1));
@@ -685,35 +692,51 @@ int phb_mesh_create_rect_strip(phb_ctx *ctx, int nx, int ny, double w, double h,
   phb_mesh *m = nullptr;
   PHB_CHECK(mesh_from_arrays(ctx, (int)(xy.size() / 2), xy.data(), (int)keep.size(), cptr.data(), cind.data(), &m));
   std::unique_ptr<phb_mesh> guard(m);
-  auto ln = [&](int i, int j) { return localNode[(size_t)(j - jlo) * nnx + i]; };
+  auto ln = [&](int i, int j) { return localNode[(size_t)(j - jlo) * lnx + (i - ilo)]; };
   std::vector<int> pr;
-  // same creation order as the global grid: x-, x+, y-, y+ (a patch absent locally keeps its id)
-  for (int side = 0; side < 2; ++side) {
-    pr.clear();
-    const int i = side ? nx : 0;
-    for (int j = jlo; j < jhi; ++j) { pr.push_back(ln(i, j)); pr.push_back(ln(i, j + 1)); }
-    if (!pr.empty() && phb_mesh_add_patch_by_nodes(m, side ? "x+" : "x-", (int)pr.size() / 2, pr.data()) < 0)
-      return PHB_ERR_ARG;
-  }
+  // same creation order as the global grid: x-, x+, y-, y+ (a patch absent locally is not created)
   pr.clear();
-  if (jlo == 0) for (int i = 0; i < nx; ++i) { pr.push_back(ln(i, 0)); pr.push_back(ln(i + 1, 0)); }
+  if (ilo == 0) for (int j = jlo; j < jhi; ++j) { pr.push_back(ln(0, j)); pr.push_back(ln(0, j + 1)); }
+  if (!pr.empty() && phb_mesh_add_patch_by_nodes(m, "x-", (int)pr.size() / 2, pr.data()) < 0) return PHB_ERR_ARG;
+  pr.clear();
+  if (ihi == nx) for (int j = jlo; j < jhi; ++j) { pr.push_back(ln(nx, j)); pr.push_back(ln(nx, j + 1)); }
+  if (!pr.empty() && phb_mesh_add_patch_by_nodes(m, "x+", (int)pr.size() / 2, pr.data()) < 0) return PHB_ERR_ARG;
+  pr.clear();
+  if (jlo == 0) for (int i = ilo; i < ihi; ++i) { pr.push_back(ln(i, 0)); pr.push_back(ln(i + 1, 0)); }
   if (!pr.empty() && phb_mesh_add_patch_by_nodes(m, "y-", (int)pr.size() / 2, pr.data()) < 0) return PHB_ERR_ARG;
   pr.clear();
-  if (jhi == ny) for (int i = 0; i < nx; ++i) { pr.push_back(ln(i, ny)); pr.push_back(ln(i + 1, ny)); }
+  if (jhi == ny) for (int i = ilo; i < ihi; ++i) { pr.push_back(ln(i, ny)); pr.push_back(ln(i + 1, ny)); }
   if (!pr.empty() && phb_mesh_add_patch_by_nodes(m, "y+", (int)pr.size() / 2, pr.data()) < 0) return PHB_ERR_ARG;
+  // IndexMap offsets: owned rows contiguous per rank, in rank order
   std::vector<int> offs(P + 1, 0);
-  for (int q = 0; q < P; ++q) offs[q + 1] = ((q + 1 < P) ? firstRow(q + 1) : ny) * nx;
-  auto partOf = [&](int c) { return rowOwner(c / nx); };
+  for (int q = 0; q < P; ++q) {
+    const int qi = q % px, qj = q / px;
+    offs[q + 1] = offs[q] + (firstCol(qi + 1) - firstCol(qi)) * (firstRow(qj + 1) - firstRow(qj));
+  }
+  auto partOf = [&](int c) { return rowBlock(c / nx) * px + colBlock(c % nx); };
   auto touches = [&](int c, int q) {
-    const int j = c / nx;
-    for (int jj = std::max(0, j - 1); jj <= std::min(ny - 1, j + 1); ++jj) if (rowOwner(jj) == q) return true;
+    const int i = c % nx, j = c / nx;
+    for (int jj = std::max(0, j - 1); jj <= std::min(ny - 1, j + 1); ++jj)
+      for (int ii = std::max(0, i - 1); ii <= std::min(nx - 1, i + 1); ++ii)
+        if (rowBlock(jj) * px + colBlock(ii) == q) return true;
     return false;
   };
-  finish_local(m, rank, P, keep, partOf, touches, offs, [](int c) { return c; });
+  // global row = owner offset + rank of the cell among the owner's cells in ascending global id
+  auto gRowOf = [&](int c) {
+    const int i = c % nx, j = c / nx, qi = colBlock(i), qj = rowBlock(j);
+    const int bw = firstCol(qi + 1) - firstCol(qi);
+    return offs[qj * px + qi] + (j - firstRow(qj)) * bw + (i - firstCol(qi));
+  };
+  finish_local(m, rank, P, keep, partOf, touches, offs, gRowOf);
   PHB_CHECK(phb_mesh_finalize(m));
   *out = guard.release();
   return PHB_OK;
   PHB_TRY_END
+}
+
+int phb_mesh_create_rect_strip(phb_ctx *ctx, int nx, int ny, double w, double h, phb_mesh **out) {
+  PHB_REQUIRE(ctx, "phb_mesh_create_rect_strip: ctx is NULL");
+  return phb_mesh_create_rect_block(ctx, nx, ny, w, h, 1, ctx->nProcs, out);
 }
 
 }  // extern "C"

@@ -70,7 +70,7 @@ __device__ __forceinline__ void slice_dot_any(const int *__restrict__ col, const
 
 // EPI 0: y = A x
 // EPI 1: y = A x, sigma = (w . y)                       [v = A p, (rhat . v)]
-// EPI 2: y = A x, ts = (y . x_row), tt = (y . y)         [t = A s, (t.s), (t.t)]
+// EPI 2: y = A x, ts = (y . w), tt = (y . y)             [t = A M^-1 s, (t.s), (t.t); w = s]
 // EPI 3: y = b - A x, w2 = y, rr = rho0 = (y . y), bb = (b . b)   [initial residual]
 template <int NC, int EPI>
 __global__ void __launch_bounds__(kThreads)
@@ -108,7 +108,7 @@ k_spmv(SellView A, const double *__restrict__ vals, const double *__restrict__ x
           y[idx] = acc[i];
           if (EPI == 1) s0 = fma(w[idx], acc[i], s0);
           if (EPI == 2) {
-            s0 = fma(acc[i], x[idx], s0);
+            s0 = fma(acc[i], w[idx], s0);
             s1 = fma(acc[i], acc[i], s1);
           }
         }
@@ -176,8 +176,9 @@ k_update_s(int n, int ld, const double *__restrict__ r, const double *__restrict
 // x += alpha p + omega s ; r = s - omega t ; rho' = (rhat . r), rr = (r . r)
 template <int NC>
 __global__ void __launch_bounds__(kThreads)
-k_update_xr(int n, int ld, double *__restrict__ x, const double *__restrict__ p,
-            const double *__restrict__ s, const double *__restrict__ t, double *__restrict__ r,
+k_update_xr(int n, int ld, double *__restrict__ x, const double *__restrict__ ph,
+            const double *__restrict__ sh, const double *__restrict__ s, const double *__restrict__ t,
+            double *__restrict__ r,
             const double *__restrict__ rhat, KrylovSums *S, int cur, int maxIters, double *partials,
             unsigned *ticket) {
   if (krylov_done(S, maxIters)) return;
@@ -188,7 +189,7 @@ k_update_xr(int n, int ld, double *__restrict__ x, const double *__restrict__ p,
     for (int c = 0; c < NC; ++c) {
       const size_t k = (size_t)c * ld + i;
       const double sk = s[k];
-      x[k] += alpha * p[k] + omega * sk;
+      x[k] += alpha * ph[k] + omega * sh[k];
       const double rk = sk - omega * t[k];
       r[k] = rk;
       s0 = fma(rhat[k], rk, s0);
@@ -288,8 +289,9 @@ int spmv_grid(const phb_ctx *c, const SellPattern *P) {
 
 template <int EPI>
 void launch_spmv(phb_solver *s, const double *vals, const double *x, double *y, const double *w, double *w2) {
-  const SellView A = view_of(s->pat);
-  const int grid = spmv_grid(s->ctx, s->pat);
+  const SellPattern *P = s->runPat ? s->runPat : s->pat;
+  const SellView A = view_of(P);
+  const int grid = spmv_grid(s->ctx, P);
   if (s->nComp == 1)
     PHB_LAUNCH(s->ctx, (k_spmv<1, EPI>), grid, kThreads, 0, A, vals, x, y, s->ld, w, w2, s->sums.p, s->maxIters,
                s->partials.p, s->ticket.p);
@@ -306,8 +308,8 @@ int halo_exchange(phb_solver *s, double *x) {
   const int nSend = (int)m->hSendDev.size();
   phb_mesh *mm = const_cast<phb_mesh *>(m);
   if (nSend)
-    PHB_LAUNCH(s->ctx, k_pack, (nSend * s->nComp + 255) / 256, 256, 0, nSend, s->nComp, s->ld, m->dSendDev.p, x,
-               mm->dSendBuf.p);
+    PHB_LAUNCH(s->ctx, k_pack, (nSend * s->nComp + 255) / 256, 256, 0, nSend, s->nComp, s->ld,
+               s->runSendDev ? s->runSendDev : m->dSendDev.p, x, mm->dSendBuf.p);
   for (int c = 0; c < s->nComp; ++c)
     PHB_CHECK(comm_exchange(s->ctx, mm->dSendBuf.p + (size_t)c * nSend, m->hSendOff.data(), m->hSendCnt.data(),
                             x + (size_t)c * s->ld, m->hRecvOff.data(), m->hRecvCnt.data()));
@@ -318,25 +320,29 @@ int enqueue_iteration(phb_solver *s, const double *A, int cur) {
   phb_ctx *c = s->ctx;
   const int n = s->pat->nRows, ld = s->ld;
   const int gv = grid_for(c, n);
+  const bool ilu = s->precond == PHB_PC_ILU0;
+  double *ph = ilu ? s->ph.p : s->p.p, *sh = ilu ? s->sh.p : s->s.p;
   if (s->nComp == 1)
     PHB_LAUNCH(c, k_update_p<1>, gv, kThreads, 0, n, ld, s->r.p, s->p.p, s->v.p, s->sums.p, cur, s->maxIters);
   else
     PHB_LAUNCH(c, k_update_p<2>, gv, kThreads, 0, n, ld, s->r.p, s->p.p, s->v.p, s->sums.p, cur, s->maxIters);
-  PHB_CHECK(halo_exchange(s, s->p.p));
-  launch_spmv<1>(s, A, s->p.p, s->v.p, s->rhat.p, nullptr);
+  if (ilu) PHB_CHECK(ilu_apply(s, s->p.p, ph));          // ph = M^-1 p
+  PHB_CHECK(halo_exchange(s, ph));
+  launch_spmv<1>(s, A, ph, s->v.p, s->rhat.p, nullptr);   // v = A ph, sigma = (rhat . v)
   PHB_CHECK(comm_allreduce_sum(c, &s->sums.p->sigma, 1));
   if (s->nComp == 1)
     PHB_LAUNCH(c, k_update_s<1>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->sums.p, cur, s->maxIters);
   else
     PHB_LAUNCH(c, k_update_s<2>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->sums.p, cur, s->maxIters);
-  PHB_CHECK(halo_exchange(s, s->s.p));
-  launch_spmv<2>(s, A, s->s.p, s->t.p, nullptr, nullptr);
+  if (ilu) PHB_CHECK(ilu_apply(s, s->s.p, sh));          // sh = M^-1 s
+  PHB_CHECK(halo_exchange(s, sh));
+  launch_spmv<2>(s, A, sh, s->t.p, s->s.p, nullptr);      // t = A sh, (t . s), (t . t)
   PHB_CHECK(comm_allreduce_sum(c, &s->sums.p->ts, 2));
   if (s->nComp == 1)
-    PHB_LAUNCH(c, k_update_xr<1>, gv, kThreads, 0, n, ld, s->x.p, s->p.p, s->s.p, s->t.p, s->r.p, s->rhat.p,
+    PHB_LAUNCH(c, k_update_xr<1>, gv, kThreads, 0, n, ld, s->x.p, ph, sh, s->s.p, s->t.p, s->r.p, s->rhat.p,
                s->sums.p, cur, s->maxIters, s->partials.p, s->ticket.p);
   else
-    PHB_LAUNCH(c, k_update_xr<2>, gv, kThreads, 0, n, ld, s->x.p, s->p.p, s->s.p, s->t.p, s->r.p, s->rhat.p,
+    PHB_LAUNCH(c, k_update_xr<2>, gv, kThreads, 0, n, ld, s->x.p, ph, sh, s->s.p, s->t.p, s->r.p, s->rhat.p,
                s->sums.p, cur, s->maxIters, s->partials.p, s->ticket.p);
   PHB_CHECK(comm_allreduce_sum(c, &s->sums.p->pad[0], 2));
   PHB_LAUNCH(c, k_iter_scalars, 1, 1, 0, s->sums.p, cur, s->maxIters);
@@ -385,13 +391,30 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
   phb_ctx *c = s->ctx;
   PHB_REQUIRE(s->pat && s->dVals, "solver: no matrix set");
   PHB_REQUIRE(s->method == "BICGSTAB", "solver \"%s\" is not available (BICGSTAB only)", s->method.c_str());
-  PHB_REQUIRE(s->precond == PHB_PC_NONE || s->precond == PHB_PC_JACOBI,
-              "preconditioner %d not available in this build", s->precond);
   const SellPattern *P = s->pat;
   const int n = P->nRows, ld = s->ld;
   const SellView A = view_of(P);
   const int gv = grid_for(c, n);
   const double *Aw = s->dVals;
+  s->runPat = P;
+  s->runSendDev = nullptr;
+  // ---- ILU(0): iterate on the symmetrically permuted system (rows grouped by independent set)
+  if (s->precond == PHB_PC_ILU0) {
+    PHB_CHECK(ilu_prepare(s, P, (s->halo && c->nProcs > 1) ? s->halo : nullptr));
+    PHB_CHECK(ilu_factor(s, s->dVals));
+    const size_t len = (size_t)ld * s->nComp;
+    PHB_CHECK(s->ph.alloc(len)); PHB_CHECK(s->sh.alloc(len));
+    PHB_CUDA(cudaMemsetAsync(s->ph.p, 0, len * sizeof(double), c->stream));
+    PHB_CUDA(cudaMemsetAsync(s->sh.p, 0, len * sizeof(double), c->stream));
+    // b, x0 -> permuted numbering (t and v are free before the first iteration)
+    PHB_CHECK(ilu_permute(s, s->b.p, s->t.p, 0));
+    PHB_CHECK(ilu_permute(s, s->x.p, s->v.p, 0));
+    PHB_CUDA(cudaMemcpyAsync(s->b.p, s->t.p, len * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    PHB_CUDA(cudaMemcpyAsync(s->x.p, s->v.p, len * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    Aw = s->ilu.vals.p;
+    s->runPat = &s->ilu.pat;
+    s->runSendDev = s->ilu.sendDev.p;
+  }
   // ---- Jacobi fold: iterate on y = D x with A D^-1
   if (s->precond == PHB_PC_JACOBI) {
     PHB_CHECK(s->dinv.alloc((size_t)ld));
@@ -433,7 +456,8 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
     // ---- iterations: graphs of K iterations, polled every `burst` graphs
     const int K = std::max(2, s->itersPerGraph & ~1);
     bool graphOk = s->useGraph;
-    const void *key[4] = {P, Aw, (const void *)(intptr_t)(s->nComp * 1000003 + s->maxIters), s->halo};
+    const void *key[4] = {s->runPat, Aw,
+                          (const void *)(intptr_t)(s->nComp * 1000003 + s->maxIters + 7919 * s->precond), s->halo};
     if (graphOk && (!s->graphExec || memcmp(key, s->graphKey, sizeof(key)) != 0)) {
       if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
       cudaGraph_t g = nullptr;
@@ -452,7 +476,8 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
       if (g) cudaGraphDestroy(g);
       memcpy(s->graphKey, key, sizeof(key));
     }
-    const int launchesPerIter = 6 + ((s->halo && c->nProcs > 1) ? 2 : 0);
+    const int launchesPerIter = 6 + ((s->halo && c->nProcs > 1) ? 2 : 0) +
+                                (s->precond == PHB_PC_ILU0 ? 2 * ilu_launches_per_apply(s) : 0);
     int launched = 0, burst = 1;
     bool done = false;
     while (!done && launched < budget) {
@@ -495,6 +520,13 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
     else
       PHB_LAUNCH(c, k_diag_apply<2>, gv, kThreads, 0, n, ld, s->x.p, s->dinv.p, s->x.p, 0);
   }
+  if (s->precond == PHB_PC_ILU0) {  // back to the caller's numbering
+    PHB_CHECK(ilu_permute(s, s->x.p, s->v.p, 1));
+    PHB_CUDA(cudaMemcpyAsync(s->x.p, s->v.p, (size_t)ld * s->nComp * sizeof(double), cudaMemcpyDeviceToDevice,
+                             c->stream));
+  }
+  s->runPat = P;
+  s->runSendDev = nullptr;
   s->lastIters = totalIters;
   s->lastRelres = rel;
   if (iters) *iters = totalIters;
@@ -545,6 +577,10 @@ int phb_solver_setup(phb_solver *s, const char *key, const char *value) {
     else if (lv == "jacobi" || lv == "diagonal") s->precond = PHB_PC_JACOBI;
     else if (lv == "ilu0" || lv == "riluk" || lv == "schwarz" || lv == "ilu") s->precond = PHB_PC_ILU0;
     else PHB_REQUIRE(false, "unknown preconditioner \"%s\"", value);
+  } else if (k == "ordering" || k == "iluOrdering") {
+    if (lv == "multicolor" || lv == "multicolour" || lv == "colour" || lv == "color") s->iluOrdering = 0;
+    else if (lv == "levels" || lv == "natural" || lv == "wavefront") s->iluOrdering = 1;
+    else PHB_REQUIRE(false, "unknown ILU ordering \"%s\" (multicolor | levels)", value);
   } else if (k == "iluFill") {
     PHB_REQUIRE(std::stod(v) == 0., "only iluFill 0 is supported");
   } else if (k == "itersPerGraph") {
@@ -776,7 +812,9 @@ int phb_solver_bytes(const phb_solver *s, double out[2]) {
   PHB_REQUIRE(s && out && s->pat, "phb_solver_bytes: no matrix bound");
   const double nnz = (double)s->pat->nnz, n = (double)s->pat->nRows, nc = s->nComp;
   out[0] = 12. * nnz + 4. * (n + 1.) + 16. * n * nc;
-  out[1] = 2. * out[0] + 112. * n * nc;
+  // ILU(0) apply: L and U sweeps over the pattern once, 12 nnz + 8 (n+1) + 8 n + 32 n nc
+  const double prec = s->precond == PHB_PC_ILU0 ? 12. * nnz + 8. * (n + 1.) + 8. * n + 32. * n * nc : 0.;
+  out[1] = 2. * out[0] + 2. * prec + 112. * n * nc;
   return PHB_OK;
 }
 

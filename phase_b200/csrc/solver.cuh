@@ -14,6 +14,19 @@ struct KrylovSums {
   double pad[7];
 };
 
+// ILU(0): permuted pattern + factors (ilu.cu)
+struct IluData {
+  const SellPattern *src = nullptr;
+  long long srcSlots = 0;
+  int ordering = -1, nBlocks = 0;
+  SellPattern pat;                 // rows grouped by independent set
+  std::vector<int> blockPtr;       // nBlocks + 1 row offsets
+  std::vector<char> hasLower, hasUpper;
+  phb::DevBuf<int> slotMap, diagK, blockOf, new2old, sendDev;
+  phb::DevBuf<signed char> kind;   // per slot: 0 pad/ghost, 1 lower, 2 diagonal, 3 upper
+  phb::DevBuf<double> vals, lu;
+};
+
 struct phb_solver {
   phb_ctx *ctx = nullptr;
   // configuration (keys of LinearAlgebra.<eqn>, M/TrilinosBelosSparseMatrixSolver.cpp:44-86)
@@ -37,6 +50,13 @@ struct phb_solver {
   int ld = 0;  // vector leading dimension (= pat->nCols)
   const phb_mesh *halo = nullptr;  // halo lists (nProcs > 1)
   phb::DevBuf<double> scaled, dinv;
+  IluData ilu;
+  int iluOrdering = 0;             // 0 multicolour, 1 wavefront levels of the given ordering
+  phb::DevBuf<double> ph, sh;      // M^-1 p, M^-1 s (ILU only; alias p, s otherwise)
+  // run-time view of the system being iterated on (permuted when ILU is active)
+  const SellPattern *runPat = nullptr;
+  const int *runSendDev = nullptr;
+  double *runPh = nullptr, *runSh = nullptr;
   phb::DevBuf<double> b, x, r, rhat, p, v, s, t;
   phb::DevBuf<double> partials;
   phb::DevBuf<unsigned> ticket;
@@ -57,4 +77,9 @@ namespace phb {
 int solver_run(phb_solver *s, int *iters, double *relres);
 int solver_bind(phb_solver *s, const SellPattern *pat, const double *dVals, int nComp,
                 const phb_mesh *halo);
+int ilu_prepare(phb_solver *s, const SellPattern *P, const phb_mesh *halo);
+int ilu_factor(phb_solver *s, const double *vals);
+int ilu_apply(phb_solver *s, const double *r, double *z);
+int ilu_permute(phb_solver *s, const double *x, double *y, int dir);
+int ilu_launches_per_apply(const phb_solver *s);
 }  // namespace phb

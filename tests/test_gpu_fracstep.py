@@ -56,3 +56,21 @@ def test_time_step_control(comm):
     want = min(0.5 / co * dt, (1 + 0.1 * 0.5 / co) * dt, 1.2 * dt, 1.0)   # US/FractionalStep.cpp:68-77
     assert np.isclose(new, want, rtol=1e-6)
     gfs.close(); g.close()
+
+
+@pytest.mark.parametrize("kind,nx,ny", [("rect", 40, 32), ("tri", 16, 18)])
+def test_cavity_with_ilu0(comm, kind, nx, ny):
+    """Same parity bar with the ILU(0) preconditioner (2-component uEqn_ and scalar pEqn_)."""
+    from phase_b200.api import FiniteVolumeGrid2D as G, lid_driven_cavity
+    om, ofs = oracle_cavity(kind, nx, ny, 1.0, 1.0, 1.0, 0.1)
+    ofs.use_direct_solver()
+    g = (G.rectilinear if kind == "rect" else G.triangulated)(comm, nx, ny, 1.0, 1.0)
+    gfs = lid_driven_cavity(g, 1.0, 0.1, solver=dict(tolerance=1e-11, maxIters=20000, preconditioner="ilu0"))
+    dt = 0.5 / nx
+    for _ in range(5):
+        ofs.step(dt)
+        st = gfs.solve(dt)
+    u, p, po = gfs.u.get("cells"), gfs.p.get("cells"), ofs.view("p").copy()
+    assert rel_l2(u[0], ofs.view("ux")) < TOL and rel_l2(u[1], ofs.view("uy")) < TOL
+    assert rel_l2(p - p.mean(), po - po.mean()) < TOL
+    gfs.close(); g.close()

@@ -44,7 +44,7 @@ def test_spmv_padded_csr(comm, kind, nx, ny):
     s.close()
 
 
-@pytest.mark.parametrize("pc", ["none", "jacobi"])
+@pytest.mark.parametrize("pc", ["none", "jacobi", "ilu0"])
 @pytest.mark.parametrize("kind,nx,ny", [("rect", 40, 40), ("tri", 24, 20)])
 def test_bicgstab_vs_direct(comm, kind, nx, ny, pc):
     from phase_b200.api import SparseMatrixSolver
@@ -114,3 +114,35 @@ def test_matches_oracle_bicgstab_iteration_count(comm):
     assert abs(s.nIters() - ito) <= max(8, ito // 4)
     assert rel_l2(s.x(), xo) < 1e-6
     s.close()
+
+
+def test_ilu0_levels_is_exact_on_a_chain(comm):
+    """On a 1-D chain the pattern has no fill, so ILU(0) in the natural (wavefront-level) ordering is the
+    exact LU: BiCGStab must converge in one iteration."""
+    from phase_b200.api import SparseMatrixSolver
+    rp, ci, va, b = poisson_system("rect", 70, 1)
+    xd = O.direct_solve(rp, ci, va, b)
+    s = SparseMatrixSolver(comm).setup(dict(maxIters=50, tolerance=1e-12, preconditioner="ilu0", ordering="levels"))
+    s.set(rp, ci, va); s.setRhs(b); s.solve()
+    assert s.nIters() <= 2 and rel_l2(s.x(), xd) < 1e-10
+    s.close()
+
+
+@pytest.mark.parametrize("kind,nx,ny", [("rect", 64, 64), ("tri", 40, 40)])
+def test_ilu0_reduces_iterations(comm, kind, nx, ny):
+    from phase_b200.api import SparseMatrixSolver
+    rp, ci, va, b = poisson_system(kind, nx, ny)
+    xd = O.direct_solve(rp, ci, va, b)
+    its = {}
+    for name, cfg in (("jacobi", dict(preconditioner="jacobi")), ("ilu0_mc", dict(preconditioner="ilu0")),
+                      ("ilu0_lv", dict(preconditioner="ilu0", ordering="levels"))):
+        s = SparseMatrixSolver(comm).setup(dict(maxIters=5000, tolerance=1e-10, **cfg))
+        s.set(rp, ci, va); s.setRhs(b); s.solve()
+        assert s.error() <= 1e-10 and rel_l2(s.x(), xd) < 1e-7, name
+        its[name] = s.nIters()
+        s.close()
+    # same algorithm on the CPU oracle (natural-order ILU(0)) for the iteration count
+    xo, ito, rro = O.bicgstab(rp, ci, va, b, tol=1e-10, max_iters=5000, precond=2)
+    assert its["ilu0_mc"] < its["jacobi"]
+    assert its["ilu0_lv"] <= its["ilu0_mc"]
+    assert abs(its["ilu0_lv"] - ito) <= max(6, ito // 3), (its, ito)

@@ -149,3 +149,25 @@ def test_gloo_world2_halo_exchange_and_spmv():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+@pytest.mark.parametrize("nx,ny,px,py", [(8, 6, 2, 2), (9, 10, 2, 4), (7, 5, 3, 1), (6, 6, 1, 3)])
+def test_block_mesh_equals_generic_path_and_oracle(nx, ny, px, py):
+    from phase_b200.api import FiniteVolumeGrid2D as G
+    P = px * py
+    g = G.rectilinear(host_comm(), nx, ny, 2.0, 1.0)
+    om = O.Mesh.rectilinear(nx, ny, 2.0, 1.0)
+    cells = np.arange(nx * ny)
+    part = (((cells // nx) * py // ny) * px + ((cells % nx) * px // nx)).astype(np.int32)
+    locs = om.partition(part, P)
+    for r in range(P):
+        gb = G.rectilinear_block(host_comm(r, P), nx, ny, 2.0, 1.0, px, py)
+        gl = g.local(part, host_comm(r, P))
+        for nm in INT_ARRAYS + ["rowPtr", "colInd", "slotL", "slotR", "cell2dev"]:
+            assert np.array_equal(gb.i32(nm), gl.i32(nm)), (r, nm)
+        for nm in INT_ARRAYS:
+            assert np.array_equal(gb.i32(nm), locs[r].array(nm)), (r, nm)
+        for nm in ("vol", "cellCx", "cellCy", "faceSx", "faceSy", "faceG", "faceW"):
+            assert np.allclose(gb.f64(nm), gl.f64(nm), rtol=1e-13, atol=1e-15), nm
+        gb.close(); gl.close()
+    g.close()

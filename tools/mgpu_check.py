@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--ny", type=int, default=40)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--strip", action="store_true")
+    ap.add_argument("--precond", default="jacobi")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -43,7 +44,7 @@ def main():
         host = Communicator(Communicator.HOST_ONLY)
         g = (G.rectilinear if a.kind == "rect" else G.triangulated)(host, a.nx, a.ny, 1.0, 1.0)
         gl = g.local(g.partition_rcb(world), comm)
-    fs = lid_driven_cavity(gl, 1.0, 0.1, solver=dict(tolerance=1e-11, maxIters=50000))
+    fs = lid_driven_cavity(gl, 1.0, 0.1, solver=dict(tolerance=1e-11, maxIters=50000, preconditioner=a.precond))
     om = (O.Mesh.rectilinear if a.kind == "rect" else O.Mesh.triangulated)(a.nx, a.ny, 1.0, 1.0)
     ofs = O.cavity(om, 1.0, 0.1)
     ofs.use_direct_solver()
