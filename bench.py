@@ -169,13 +169,16 @@ def block_layout(nprocs):
 def workload_config(args, nprocs):
     return {"workload": "lid-driven cavity (rho=1, mu=0.1, lid u=1), %dx%d quads = %d cells per GPU, "
                         "FractionalStep time step (the snapshot's PISO successor), dt = 0.5 h (maxCo 0.5), "
-                        "BiCGStab + Jacobi, tolerance %g on ||r||/||b||, warm start from the previous step"
-                        % (args.n, args.n, args.n * args.n, args.tol),
+                        "BiCGStab + %s, tolerance %g on ||r||/||b||, warm start from the previous step"
+                        % (args.n, args.n, args.n * args.n, args.precond, args.tol),
             "cells_per_gpu": args.n * args.n, "global_cells": args.n * args.n * nprocs,
             "partition": "none" if nprocs == 1 else "%dx%d blocks of %dx%d cells, one per GPU (global grid %dx%d)" % (
                 block_layout(nprocs) + (args.n, args.n, args.n * block_layout(nprocs)[0], args.n * block_layout(nprocs)[1])),
             "l2": "inputs larger than L2 (matrix + vectors ~0.6 GB per solve vs 126 MB L2); no flush needed",
-            "tolerance": args.tol, "max_iters": args.max_iters}
+            "tolerance": args.tol, "max_iters": args.max_iters, "preconditioner": args.precond,
+            "comm": "single GPU" if nprocs == 1 else (
+                "NVLink peer-memory kernels (halo + all-reduce fused into the Krylov loop), NCCL outside the loop"
+                if args.comm == "peer" else "NCCL send/recv + all-reduce")}
 
 
 def main():
@@ -189,6 +192,8 @@ def main():
     ap.add_argument("--max-iters", type=int, default=20000)
     ap.add_argument("--precond", default="jacobi")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
+                    help="in-loop halo/all-reduce: NVLink peer-memory kernels (default) or NCCL calls")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -215,6 +220,12 @@ def main():
         grid = FiniteVolumeGrid2D.rectilinear(comm, nx, ny, 1.0, 1.0)
     else:
         grid = FiniteVolumeGrid2D.rectilinear_block(comm, nx, ny, float(px), float(py), px, py)
+    if world > 1 and args.comm == "peer":
+        def all_gather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        comm.enable_peer_memory(grid, all_gather)
     cfg = dict(solver="BICGSTAB", maxIters=args.max_iters, tolerance=args.tol, preconditioner=args.precond)
     fs = lid_driven_cavity(grid, 1.0, 0.1, solver=cfg)
     dt = 0.5 / nx

@@ -63,6 +63,16 @@ int phb_ctx_destroy(phb_ctx *ctx);
 /* 128-byte NCCL unique id made on rank 0, shipped by the host launcher */
 int phb_comm_unique_id(void *out128);
 int phb_ctx_init_comm(phb_ctx *ctx, int rank, int nProcs, const void *id128);
+/* Peer-memory communication (NVLink, CUDA IPC) for the exchanges INSIDE the
+ * Krylov loop: every rank allocates one arena (sized for `maxSolvers` solvers with
+ * vectors of up to 2 x maxCols doubles; maxCols = max over ranks of owned+ghost
+ * cells), the launcher all-gathers the 64-byte handles, and every rank opens the
+ * others'.  After that halos and dot-product reductions of a distributed solve are
+ * single small kernels storing into the peers' arenas; NCCL remains the path for
+ * everything outside the loop.  Optional: without it every exchange uses NCCL. */
+int phb_ctx_peer_arena_create(phb_ctx *ctx, long long maxCols, int maxSolvers,
+                              void *handleOut64);
+int phb_ctx_peer_arena_open(phb_ctx *ctx, const void *handles /* nProcs x 64 B */);
 int phb_ctx_rank(const phb_ctx *ctx);
 int phb_ctx_nprocs(const phb_ctx *ctx);
 int phb_ctx_sync(phb_ctx *ctx);
@@ -116,6 +126,10 @@ int phb_partition_rcb(const phb_mesh *global, int nParts, int *cellPartition);
  * lists as in initCommBuffers (:460-511).  `global` must be finalized. */
 int phb_mesh_create_local(phb_ctx *ctx, const phb_mesh *global,
                           const int *cellPartition, phb_mesh **out);
+
+/* peer-memory halo layout: for every peer q, the offset at which this rank's
+ * values land in q's vectors (q's "recvOff"[this rank]) and q's owned+ghost count */
+int phb_mesh_set_peer_layout(phb_mesh *m, const int *peerRecvOff, const int *peerLd);
 
 /* local mesh of ctx's rank for a y-strip partition of an nx x ny rectilinear
  * grid (rank r owns rows [r ny/P, (r+1) ny/P)) built without the global mesh;

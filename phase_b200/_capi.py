@@ -21,6 +21,9 @@ SIGNATURES = {
     "phb_ctx_destroy": (ci, [vp]),
     "phb_comm_unique_id": (ci, [vp]),
     "phb_ctx_init_comm": (ci, [vp, ci, ci, vp]),
+    "phb_ctx_peer_arena_create": (ci, [vp, cll, ci, vp]),
+    "phb_ctx_peer_arena_open": (ci, [vp, vp]),
+    "phb_mesh_set_peer_layout": (ci, [vp, pi, pi]),
     "phb_ctx_rank": (ci, [vp]),
     "phb_ctx_nprocs": (ci, [vp]),
     "phb_ctx_sync": (ci, [vp]),

@@ -44,6 +44,22 @@ class Communicator:
         check(_capi.lib().phb_comm_unique_id(buf))
         return bytes(buf.raw)
 
+    def enable_peer_memory(self, grid, all_gather, max_solvers=4):
+        """Switch the in-loop halo / all-reduce traffic of distributed solves to NVLink peer
+        memory.  `all_gather(obj) -> list` is the launcher's object all-gather (e.g. a wrapper
+        around torch.distributed.all_gather_object)."""
+        n = self.nProcs()
+        me = self.rank()
+        info = all_gather((grid.sizes()["nCells"], [int(v) for v in grid.i32("recvOff")]))
+        peer_ld = np.array([info[q][0] for q in range(n)], np.int32)
+        peer_off = np.array([info[q][1][me] for q in range(n)], np.int32)
+        check(self.L.phb_mesh_set_peer_layout(grid.h, _ip(peer_off), _ip(peer_ld)))
+        buf = C.create_string_buffer(64)
+        check(self.L.phb_ctx_peer_arena_create(self.h, int(peer_ld.max()), max_solvers, buf))
+        handles = all_gather(bytes(buf.raw))
+        allh = C.create_string_buffer(b"".join(handles), 64 * n)
+        check(self.L.phb_ctx_peer_arena_open(self.h, allh))
+
     def rank(self):
         return self.L.phb_ctx_rank(self.h)
 

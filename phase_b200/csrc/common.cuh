@@ -54,14 +54,22 @@ void set_error(const char *fmt, ...);
 template <class T> struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
+  bool owned = true;  // false: points into storage owned by someone else (peer arena)
   DevBuf() = default;
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr;
     n = 0;
+    owned = true;
+  }
+  void attach(T *ext, size_t count) {
+    release();
+    p = ext;
+    n = count;
+    owned = false;
   }
   int alloc(size_t count) {
     if (count == n && p) return PHB_OK;
@@ -89,6 +97,23 @@ constexpr int kSliceRows = 32;  // SELL slice height = one warp, lane <-> row
 
 struct ncclComm;
 
+// Peer-memory communication over NVLink (CUDA IPC, one arena per rank, identical
+// layout on every rank): reductions and halos inside the Krylov loop are done by
+// small kernels that store straight into the peers' arenas and spin on epoch flags
+// -- no NCCL call, no host involvement (peer.cu).
+constexpr int kMaxPeers = 8;
+constexpr int kPeerRedChannels = 16, kPeerHaloChannels = 16;
+constexpr size_t kPeerHeaderBytes = 16384;  // red slots | halo flags | local epochs
+struct PeerComm {
+  bool enabled = false;
+  char *arena = nullptr;
+  size_t arenaBytes = 0, regionBytes = 0, vecBytes = 0;
+  long long maxCols = 0;
+  int maxRegions = 0, nextRegion = 0;
+  char *peerArena[kMaxPeers] = {nullptr};
+  bool opened[kMaxPeers] = {false};
+};
+
 struct phb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;       // compute stream (all kernels)
@@ -99,6 +124,7 @@ struct phb_ctx {
   long long launches = 0;
   // pinned scratch for small device->host reads
   double *pinned = nullptr;
+  PeerComm peer;
 };
 
 #define PHB_LAUNCH(ctx, kernel, grid, block, smem, ...)                        \

@@ -55,6 +55,7 @@ int phb_ctx_destroy(phb_ctx *c) {
     return PHB_OK;
   }
   cudaSetDevice(c->device);
+  phb::peer_destroy(c);
   phb::comm_destroy(c);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->commStream) cudaStreamDestroy(c->commStream);
@@ -87,5 +88,10 @@ int phb_ctx_init_comm(phb_ctx *c, int rank, int nProcs, const void *id128) {
   }
   return phb::comm_init(c, rank, nProcs, id128);
 }
+
+int phb_ctx_peer_arena_create(phb_ctx *c, long long maxCols, int maxSolvers, void *handle64) {
+  return phb::peer_arena_create(c, maxCols, maxSolvers, handle64);
+}
+int phb_ctx_peer_arena_open(phb_ctx *c, const void *handles) { return phb::peer_arena_open(c, handles); }
 
 }  // extern "C"

@@ -510,6 +510,13 @@ int phb_mesh_finalize(phb_mesh *m) {
   PHB_TRY_END
 }
 
+int phb_mesh_set_peer_layout(phb_mesh *m, const int *peerRecvOff, const int *peerLd) {
+  PHB_REQUIRE(m && peerRecvOff && peerLd, "phb_mesh_set_peer_layout: NULL argument");
+  m->peerRecvOff.assign(peerRecvOff, peerRecvOff + m->nProcs);
+  m->peerLd.assign(peerLd, peerLd + m->nProcs);
+  return PHB_OK;
+}
+
 int phb_mesh_destroy(phb_mesh *m) {
   delete m;
   return PHB_OK;
@@ -542,7 +549,7 @@ long long phb_mesh_get_i32(const phb_mesh *m, const char *name, int *out, long l
   GET("slotDiag", m->slotDiag) GET("owner", m->owner) GET("globalId", m->globalId)
   GET("localRow", m->localRow) GET("globalRow", m->globalRow) GET("bufPtr", m->bufPtr)
   GET("bufCell", m->bufCell) GET("sendPtr", m->sendPtr) GET("sendCell", m->sendCell)
-  GET("cell2dev", m->cell2dev) GET("sellSliceOff", m->sell.hSliceOff) GET("sellCol", m->sell.hCol)
+  GET("cell2dev", m->cell2dev) GET("recvOff", m->hRecvOff) GET("recvCnt", m->hRecvCnt) GET("sellSliceOff", m->sell.hSliceOff) GET("sellCol", m->sell.hCol)
   GET("sellRowLen", m->sell.hRowLen)
   phb::set_error("phb_mesh_get_i32: unknown array \"%s\"", name);
   return PHB_ERR_ARG;

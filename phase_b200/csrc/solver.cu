@@ -302,10 +302,28 @@ void launch_spmv(phb_solver *s, const double *vals, const double *x, double *y, 
 
 // ghost refresh of a gathered vector before an SpMV (grid_->sendMessages analogue
 // inside the Krylov loop; UG/FiniteVolumeGrid2D.tpp:3-49)
-int halo_exchange(phb_solver *s, double *x) {
+bool use_peer(const phb_solver *s) {
+  return s->ctx->peer.enabled && s->ctx->nProcs > 1 && s->peerRegion >= 0 && s->halo &&
+         (int)s->halo->peerLd.size() == s->ctx->nProcs;
+}
+
+int halo_exchange(phb_solver *s, double *x, bool inLoop = false) {
   const phb_mesh *m = s->halo;
   if (!m || s->ctx->nProcs == 1) return PHB_OK;
   const int nSend = (int)m->hSendDev.size();
+  if (use_peer(s) && peer_owns(s->ctx, x)) {
+    int vec = x == s->p.p ? 0 : x == s->s.p ? 1 : x == s->ph.p ? 2 : 3;
+    PeerHalo h;
+    h.sendDev = s->runSendDev ? s->runSendDev : m->dSendDev.p;
+    for (int q = 0; q < kMaxPeers; ++q) {
+      const bool in = q < s->ctx->nProcs;
+      h.sendOff[q] = in ? m->hSendOff[q] : 0; h.sendCnt[q] = in ? m->hSendCnt[q] : 0;
+      h.recvCnt[q] = in ? m->hRecvCnt[q] : 0;
+      h.peerRecvOff[q] = in ? m->peerRecvOff[q] : 0; h.peerLd[q] = in ? m->peerLd[q] : 0;
+    }
+    return peer_halo(s->ctx, s->peerRegion * 4 + vec, h, x, s->nComp, s->ld, inLoop ? s->sums.p : nullptr,
+                     s->maxIters);
+  }
   phb_mesh *mm = const_cast<phb_mesh *>(m);
   if (nSend)
     PHB_LAUNCH(s->ctx, k_pack, (nSend * s->nComp + 255) / 256, 256, 0, nSend, s->nComp, s->ld,
@@ -314,6 +332,15 @@ int halo_exchange(phb_solver *s, double *x) {
     PHB_CHECK(comm_exchange(s->ctx, mm->dSendBuf.p + (size_t)c * nSend, m->hSendOff.data(), m->hSendCnt.data(),
                             x + (size_t)c * s->ld, m->hRecvOff.data(), m->hRecvCnt.data()));
   return PHB_OK;
+}
+
+// sum-all-reduce of the Krylov sums: peer kernel (one launch, bitwise identical on all ranks) or NCCL
+int reduce_sums(phb_solver *s, int which, double *vals, int n, bool inLoop, int finishIter, int cur) {
+  if (s->ctx->nProcs == 1) return PHB_OK;
+  if (use_peer(s))
+    return peer_allreduce(s->ctx, s->peerRegion * 4 + which, vals, n, inLoop ? s->sums.p : nullptr, s->maxIters,
+                          finishIter, cur);
+  return comm_allreduce_sum(s->ctx, vals, n);
 }
 
 int enqueue_iteration(phb_solver *s, const double *A, int cur) {
@@ -327,33 +354,49 @@ int enqueue_iteration(phb_solver *s, const double *A, int cur) {
   else
     PHB_LAUNCH(c, k_update_p<2>, gv, kThreads, 0, n, ld, s->r.p, s->p.p, s->v.p, s->sums.p, cur, s->maxIters);
   if (ilu) PHB_CHECK(ilu_apply(s, s->p.p, ph));          // ph = M^-1 p
-  PHB_CHECK(halo_exchange(s, ph));
+  PHB_CHECK(halo_exchange(s, ph, true));
   launch_spmv<1>(s, A, ph, s->v.p, s->rhat.p, nullptr);   // v = A ph, sigma = (rhat . v)
-  PHB_CHECK(comm_allreduce_sum(c, &s->sums.p->sigma, 1));
+  PHB_CHECK(reduce_sums(s, 0, &s->sums.p->sigma, 1, true, 0, cur));
   if (s->nComp == 1)
     PHB_LAUNCH(c, k_update_s<1>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->sums.p, cur, s->maxIters);
   else
     PHB_LAUNCH(c, k_update_s<2>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->sums.p, cur, s->maxIters);
   if (ilu) PHB_CHECK(ilu_apply(s, s->s.p, sh));          // sh = M^-1 s
-  PHB_CHECK(halo_exchange(s, sh));
+  PHB_CHECK(halo_exchange(s, sh, true));
   launch_spmv<2>(s, A, sh, s->t.p, s->s.p, nullptr);      // t = A sh, (t . s), (t . t)
-  PHB_CHECK(comm_allreduce_sum(c, &s->sums.p->ts, 2));
+  PHB_CHECK(reduce_sums(s, 1, &s->sums.p->ts, 2, true, 0, cur));
   if (s->nComp == 1)
     PHB_LAUNCH(c, k_update_xr<1>, gv, kThreads, 0, n, ld, s->x.p, ph, sh, s->s.p, s->t.p, s->r.p, s->rhat.p,
                s->sums.p, cur, s->maxIters, s->partials.p, s->ticket.p);
   else
     PHB_LAUNCH(c, k_update_xr<2>, gv, kThreads, 0, n, ld, s->x.p, ph, sh, s->s.p, s->t.p, s->r.p, s->rhat.p,
                s->sums.p, cur, s->maxIters, s->partials.p, s->ticket.p);
-  PHB_CHECK(comm_allreduce_sum(c, &s->sums.p->pad[0], 2));
-  PHB_LAUNCH(c, k_iter_scalars, 1, 1, 0, s->sums.p, cur, s->maxIters);
+  if (use_peer(s)) {  // the all-reduce kernel also publishes the iteration's scalars
+    PHB_CHECK(reduce_sums(s, 2, &s->sums.p->pad[0], 2, true, 1, cur));
+  } else {
+    PHB_CHECK(comm_allreduce_sum(c, &s->sums.p->pad[0], 2));
+    PHB_LAUNCH(c, k_iter_scalars, 1, 1, 0, s->sums.p, cur, s->maxIters);
+  }
   return PHB_OK;
 }
 
 int ensure_vectors(phb_solver *s) {
   const size_t len = (size_t)s->ld * s->nComp;
+  phb_ctx *c = s->ctx;
   PHB_CHECK(s->b.alloc(len)); PHB_CHECK(s->x.alloc(len)); PHB_CHECK(s->r.alloc(len));
-  PHB_CHECK(s->rhat.alloc(len)); PHB_CHECK(s->p.alloc(len)); PHB_CHECK(s->v.alloc(len));
-  PHB_CHECK(s->s.alloc(len)); PHB_CHECK(s->t.alloc(len));
+  PHB_CHECK(s->rhat.alloc(len)); PHB_CHECK(s->v.alloc(len)); PHB_CHECK(s->t.alloc(len));
+  // the gathered vectors (p, s and their preconditioned images) live in the peer arena when
+  // there is one, so that peers can store their halo values straight into the ghost segments
+  if (c->peer.enabled && c->nProcs > 1 && s->peerRegion == -1)
+    s->peerRegion = (c->peer.nextRegion < c->peer.maxRegions && c->peer.maxRegions * 4 <= kPeerHaloChannels)
+                        ? c->peer.nextRegion++ : -2;
+  if (s->peerRegion >= 0 && len * sizeof(double) <= c->peer.vecBytes) {
+    s->p.attach(peer_vector(c, s->peerRegion, 0), len); s->s.attach(peer_vector(c, s->peerRegion, 1), len);
+    s->ph.attach(peer_vector(c, s->peerRegion, 2), len); s->sh.attach(peer_vector(c, s->peerRegion, 3), len);
+  } else {
+    if (s->peerRegion >= 0) s->peerRegion = -2;
+    PHB_CHECK(s->p.alloc(len)); PHB_CHECK(s->s.alloc(len));
+  }
   const size_t nb = (size_t)s->ctx->numSMs * kBlocksPerSM;
   if (s->partials.n != nb * 4) {
     PHB_CHECK(s->partials.alloc(nb * 4));
@@ -403,7 +446,7 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
     PHB_CHECK(ilu_prepare(s, P, (s->halo && c->nProcs > 1) ? s->halo : nullptr));
     PHB_CHECK(ilu_factor(s, s->dVals));
     const size_t len = (size_t)ld * s->nComp;
-    PHB_CHECK(s->ph.alloc(len)); PHB_CHECK(s->sh.alloc(len));
+    if (s->ph.owned) { PHB_CHECK(s->ph.alloc(len)); PHB_CHECK(s->sh.alloc(len)); }
     PHB_CUDA(cudaMemsetAsync(s->ph.p, 0, len * sizeof(double), c->stream));
     PHB_CUDA(cudaMemsetAsync(s->sh.p, 0, len * sizeof(double), c->stream));
     // b, x0 -> permuted numbering (t and v are free before the first iteration)
@@ -447,7 +490,7 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
     PHB_CUDA(cudaMemsetAsync(s->v.p, 0, (size_t)ld * s->nComp * sizeof(double), c->stream));
     PHB_CHECK(halo_exchange(s, s->x.p));
     launch_spmv<3>(s, Aw, s->x.p, s->r.p, s->b.p, s->rhat.p);
-    PHB_CHECK(comm_allreduce_sum(c, &s->sums.p->rr, 2));
+    PHB_CHECK(reduce_sums(s, 3, &s->sums.p->rr, 2, false, 0, 0));
     PHB_LAUNCH(c, k_init_scalars, 1, 1, 0, s->sums.p, s->tol);
     const int budget = s->maxIters - totalIters;
     if (budget <= 0) break;
@@ -500,7 +543,7 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
     // ---- true residual (the recursive one can drift); restart if it disagrees
     PHB_CHECK(halo_exchange(s, s->x.p));
     launch_spmv<3>(s, Aw, s->x.p, s->r.p, s->b.p, s->rhat.p);
-    PHB_CHECK(comm_allreduce_sum(c, &s->sums.p->rr, 2));
+    PHB_CHECK(reduce_sums(s, 3, &s->sums.p->rr, 2, false, 0, 0));
     PHB_CUDA(cudaMemcpyAsync(hs, s->sums.p, sizeof(KrylovSums), cudaMemcpyDeviceToHost, c->stream));
     PHB_CUDA(cudaStreamSynchronize(c->stream));
     rel = hs->bb > 0. ? std::sqrt(hs->rr / hs->bb) : std::sqrt(hs->rr);

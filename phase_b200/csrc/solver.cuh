@@ -56,6 +56,7 @@ struct phb_solver {
   // run-time view of the system being iterated on (permuted when ILU is active)
   const SellPattern *runPat = nullptr;
   const int *runSendDev = nullptr;
+  int peerRegion = -1;             // slot of this solver in the peer arena (-1 unassigned, -2 not usable)
   double *runPh = nullptr, *runSh = nullptr;
   phb::DevBuf<double> b, x, r, rhat, p, v, s, t;
   phb::DevBuf<double> partials;

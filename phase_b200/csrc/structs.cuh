@@ -63,6 +63,8 @@ struct phb_mesh {
   phb::DevBuf<double> dSendBuf;
   // host<->device field permutation
   phb::DevBuf<int> dCell2Dev;
+  // peer-memory halo: where my values land in each peer's vectors (set by the launcher)
+  std::vector<int> peerRecvOff, peerLd;
 };
 
 struct BcEntry {

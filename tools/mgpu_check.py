@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--strip", action="store_true")
     ap.add_argument("--precond", default="jacobi")
+    ap.add_argument("--peer", action="store_true", help="NVLink peer-memory exchanges inside the Krylov loop")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -44,6 +45,12 @@ def main():
         host = Communicator(Communicator.HOST_ONLY)
         g = (G.rectilinear if a.kind == "rect" else G.triangulated)(host, a.nx, a.ny, 1.0, 1.0)
         gl = g.local(g.partition_rcb(world), comm)
+    if a.peer:
+        def all_gather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        comm.enable_peer_memory(gl, all_gather)
     fs = lid_driven_cavity(gl, 1.0, 0.1, solver=dict(tolerance=1e-11, maxIters=50000, preconditioner=a.precond))
     om = (O.Mesh.rectilinear if a.kind == "rect" else O.Mesh.triangulated)(a.nx, a.ny, 1.0, 1.0)
     ofs = O.cavity(om, 1.0, 0.1)
