@@ -127,6 +127,15 @@ int phb_partition_rcb(const phb_mesh *global, int nParts, int *cellPartition);
 int phb_mesh_create_local(phb_ctx *ctx, const phb_mesh *global,
                           const int *cellPartition, phb_mesh **out);
 
+/* ingest.  ADF-format CGNS file with the semantics of
+ * CgnsUnstructuredGrid::load (UG/CgnsUnstructuredGrid.cpp:13-105): element sections
+ * merged by element id, BC point lists = BAR_2 element ids -> patches by node pair,
+ * cells = elements with > 2 nodes in element-id order.  The mesh is NOT finalized. */
+int phb_mesh_read_cgns(phb_ctx *ctx, const char *filename, phb_mesh **out);
+/* uniform refinement (tri -> 4 tri, quad -> 4 quad), `levels` rounds; patches follow */
+int phb_mesh_refine(phb_ctx *ctx, const phb_mesh *in, int levels, phb_mesh **out);
+int phb_mesh_patch_name(const phb_mesh *m, int id, char *out, int cap);
+
 /* peer-memory halo layout: for every peer q, the offset at which this rank's
  * values land in q's vectors (q's "recvOff"[this rank]) and q's owned+ghost count */
 int phb_mesh_set_peer_layout(phb_mesh *m, const int *peerRecvOff, const int *peerLd);
@@ -259,6 +268,22 @@ int phb_fs_step(phb_fracstep *fs, double dt, double stats[6]);
 /* computeMaxTimeStep: US/FractionalStep.cpp:68-77 */
 int phb_fs_max_time_step(phb_fracstep *fs, double maxCo, double prevDt,
                          double maxDt, double *out);
+
+/* ------------------------------------------------------------ PISO time step
+ * "phasePiso" of the north star.  The mounted snapshot has no PISO module any more
+ * (SURVEY.md section 0); this driver is rebuilt from README.md:26-37, the commented
+ * relax() body (UE/ScalarFiniteVolumeEquation.cpp:45-55) and the legacy case keys
+ * (Examples/LidDrivenCavity/case/case.info:12-15).  Parity: self-consistency only. */
+typedef struct phb_piso phb_piso;
+int phb_piso_create(phb_mesh *m, double rho, double mu, phb_piso **out);
+int phb_piso_destroy(phb_piso *s);
+phb_field *phb_piso_field(phb_piso *s, const char *name);   /* u p pCorr gradP d */
+phb_solver *phb_piso_solver(phb_piso *s, const char *name); /* uEqn pCorrEqn */
+/* numInnerIterations numPressureCorrections momentumRelaxation pressureCorrectionRelaxation */
+int phb_piso_setup(phb_piso *s, const char *key, double value);
+int phb_piso_initialize(phb_piso *s);
+/* stats: [itersU, itersPCorr, relresU, relresPCorr, maxMassImbalance, maxCourant] */
+int phb_piso_step(phb_piso *s, double dt, double stats[6]);
 
 #ifdef __cplusplus
 }

@@ -103,6 +103,11 @@ def lib():
                                   C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int,
                                   C.POINTER(C.c_double)]
+        L.or_multicolor_order.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_int), C.c_int]
+        L.or_bicgstab_blocks.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int,
+                                         C.POINTER(C.c_int), C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -420,3 +425,41 @@ def cavity(mesh, rho=1.0, mu=0.1, lid=1.0):
         fs.set_bc("p", pt, NORMAL_GRADIENT, 0.0)
     fs.initialize()
     return fs
+
+
+def multicolor_permute(rp, ci, va):
+    """Compact the CSR (drop -1 padding) and permute it symmetrically into the multicolour ordering the
+    CUDA path uses for ILU(0).  Returns (rp, ci, va, new2old, blockPtr)."""
+    rp = np.ascontiguousarray(rp, np.int32)
+    ci = np.ascontiguousarray(ci, np.int32)
+    va = np.ascontiguousarray(va, np.float64)
+    n = len(rp) - 1
+    new2old = np.zeros(n, np.int32)
+    bp = np.zeros(66, np.int32)
+    nc = lib().or_multicolor_order(n, _ip(rp), _ip(ci), _ip(new2old), _ip(bp), 64)
+    if nc < 0:
+        raise RuntimeError("more than 64 colours")
+    old2new = np.empty(n, np.int32)
+    old2new[new2old] = np.arange(n, dtype=np.int32)
+    rows = np.repeat(np.arange(n, dtype=np.int32), np.diff(rp))
+    keep = ci >= 0
+    r2, c2, v2 = old2new[rows[keep]], old2new[ci[keep]], va[keep]
+    order = np.argsort(r2, kind="stable")
+    r2, c2, v2 = r2[order], c2[order], v2[order]
+    rp2 = np.zeros(n + 1, np.int32)
+    np.add.at(rp2, r2 + 1, 1)
+    rp2 = np.cumsum(rp2).astype(np.int32)
+    return rp2, np.ascontiguousarray(c2), np.ascontiguousarray(v2), new2old, np.ascontiguousarray(bp[:nc + 1])
+
+
+def bicgstab_ilu0_multicolor(rp, ci, va, b, tol=1e-8, max_iters=10000):
+    """BiCGStab + ILU(0) in the multicolour ordering (the CUDA path's default algorithm) on the CPU."""
+    rp2, ci2, va2, new2old, bp = multicolor_permute(rp, ci, va)
+    b2 = np.ascontiguousarray(np.asarray(b, np.float64)[new2old])
+    x2 = np.zeros_like(b2)
+    rr = C.c_double()
+    it = lib().or_bicgstab_blocks(len(b2), _ip(rp2), _ip(ci2), _dp(va2), _dp(b2), _dp(x2), tol, max_iters,
+                                  len(bp) - 1, _ip(bp), C.byref(rr))
+    x = np.empty_like(x2)
+    x[new2old] = x2
+    return x, it, rr.value

@@ -1500,11 +1500,14 @@ typedef struct {
   int *diag;    /* slot of the diagonal per row */
   double *dinv; /* Jacobi */
   int kind;
+  int nBlocks;        /* > 0: rows are grouped in independent sets (multicolour ordering): */
+  const int *blockPtr; /* the sweeps run set by set, OpenMP-parallel inside a set */
 } Precond;
 
 static void precond_setup(Precond *P, int n, const int *rp, const int *ci,
                           const double *v, int kind) {
   P->n = n; P->rp = rp; P->ci = ci; P->kind = kind;
+  P->nBlocks = 0; P->blockPtr = NULL;
   P->lu = NULL; P->diag = NULL; P->dinv = NULL;
   if (kind == 1) {
     P->dinv = (double *)xcalloc(n, sizeof(double));
@@ -1566,6 +1569,26 @@ static void precond_apply(const Precond *P, const double *r, double *z) {
   } else if (P->kind == 1) {
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < n; ++i) z[i] = r[i] * P->dinv[i];
+  } else if (P->nBlocks > 0) {
+    /* multicolour ordering: rows of a set are independent -> parallel sweeps */
+    for (int b = 0; b < P->nBlocks; ++b) {
+#pragma omp parallel for schedule(static)
+      for (int i = P->blockPtr[b]; i < P->blockPtr[b + 1]; ++i) {
+        double a = r[i];
+        for (int j = P->rp[i]; j < P->rp[i + 1]; ++j)
+          if (P->ci[j] >= 0 && P->ci[j] < i) a -= P->lu[j] * z[P->ci[j]];
+        z[i] = a;
+      }
+    }
+    for (int b = P->nBlocks - 1; b >= 0; --b) {
+#pragma omp parallel for schedule(static)
+      for (int i = P->blockPtr[b]; i < P->blockPtr[b + 1]; ++i) {
+        double a = z[i];
+        for (int j = P->rp[i]; j < P->rp[i + 1]; ++j)
+          if (P->ci[j] > i) a -= P->lu[j] * z[P->ci[j]];
+        z[i] = a / P->lu[P->diag[i]];
+      }
+    }
   } else {
     for (int i = 0; i < n; ++i) {
       double a = r[i];
@@ -1587,9 +1610,51 @@ static void precond_free(Precond *P) {
   free(P->dinv);
 }
 
+/* greedy multicolouring in the given order (same rule as the CUDA path's symbolic
+ * phase): colour of row i = smallest colour not used by its neighbours j < i.
+ * new2old = rows sorted by colour (stable), blockPtr[nColours+1]; returns nColours. */
+int or_multicolor_order(int n, const int *rp, const int *ci, int *new2old, int *blockPtr, int maxColours) {
+  int *col = (int *)xcalloc(n, sizeof(int));
+  int nc = 1;
+  for (int i = 0; i < n; ++i) {
+    unsigned long long used = 0ull;
+    for (int j = rp[i]; j < rp[i + 1]; ++j)
+      if (ci[j] >= 0 && ci[j] < i && col[ci[j]] < 64) used |= 1ull << col[ci[j]];
+    int c = 0;
+    while ((used >> c) & 1ull) ++c;
+    col[i] = c;
+    if (c + 1 > nc) nc = c + 1;
+  }
+  if (nc > maxColours) { free(col); return -nc; }
+  for (int c = 0; c <= nc; ++c) blockPtr[c] = 0;
+  for (int i = 0; i < n; ++i) blockPtr[col[i] + 1]++;
+  for (int c = 0; c < nc; ++c) blockPtr[c + 1] += blockPtr[c];
+  int *fill = (int *)xcalloc(nc, sizeof(int));
+  for (int i = 0; i < n; ++i) new2old[blockPtr[col[i]] + fill[col[i]]++] = i;
+  free(fill);
+  free(col);
+  return nc;
+}
+
+static int bicgstab_impl(int n, const int *rp, const int *ci, const double *v,
+                const double *b, double *x, double tol, int maxIters,
+                int precond, double *relres, int nBlocks, const int *blockPtr);
+
 int or_bicgstab(int n, const int *rp, const int *ci, const double *v,
                 const double *b, double *x, double tol, int maxIters,
                 int precond, double *relres) {
+  return bicgstab_impl(n, rp, ci, v, b, x, tol, maxIters, precond, relres, 0, NULL);
+}
+/* ILU(0) on a system whose rows are already grouped in independent sets (blockPtr) */
+int or_bicgstab_blocks(int n, const int *rp, const int *ci, const double *v,
+                       const double *b, double *x, double tol, int maxIters,
+                       int nBlocks, const int *blockPtr, double *relres) {
+  return bicgstab_impl(n, rp, ci, v, b, x, tol, maxIters, 2, relres, nBlocks, blockPtr);
+}
+
+static int bicgstab_impl(int n, const int *rp, const int *ci, const double *v,
+                const double *b, double *x, double tol, int maxIters,
+                int precond, double *relres, int nBlocks, const int *blockPtr) {
   double *r = (double *)xcalloc(n, sizeof(double));
   double *r0 = (double *)xcalloc(n, sizeof(double));
   double *p = (double *)xcalloc(n, sizeof(double));
@@ -1600,6 +1665,8 @@ int or_bicgstab(int n, const int *rp, const int *ci, const double *v,
   double *sh = (double *)xcalloc(n, sizeof(double));
   Precond P;
   precond_setup(&P, n, rp, ci, v, precond);
+  P.nBlocks = nBlocks;
+  P.blockPtr = blockPtr;
   spmv(n, rp, ci, v, x, r);
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < n; ++i) {

@@ -121,6 +121,13 @@ OrCrs *or_op_scalar_transport(OrFracStep *s, double dt, double theta, const doub
 int or_bicgstab(int n, const int *rowPtr, const int *colInd,
                 const double *vals, const double *b, double *x, double tol,
                 int maxIters, int precond, double *relres);
+/* multicolour ordering (the CUDA path's rule) and BiCGStab + ILU(0) on a system
+ * grouped in independent sets: triangular sweeps OpenMP-parallel inside a set */
+int or_multicolor_order(int n, const int *rowPtr, const int *colInd, int *new2old,
+                        int *blockPtr, int maxColours);
+int or_bicgstab_blocks(int n, const int *rowPtr, const int *colInd, const double *vals,
+                       const double *b, double *x, double tol, int maxIters,
+                       int nBlocks, const int *blockPtr, double *relres);
 int or_num_threads(void);
 
 #ifdef __cplusplus

@@ -24,6 +24,9 @@ SIGNATURES = {
     "phb_ctx_peer_arena_create": (ci, [vp, cll, ci, vp]),
     "phb_ctx_peer_arena_open": (ci, [vp, vp]),
     "phb_mesh_set_peer_layout": (ci, [vp, pi, pi]),
+    "phb_mesh_read_cgns": (ci, [vp, cs, pvp]),
+    "phb_mesh_refine": (ci, [vp, vp, ci, pvp]),
+    "phb_mesh_patch_name": (ci, [vp, ci, cs, ci]),
     "phb_ctx_rank": (ci, [vp]),
     "phb_ctx_nprocs": (ci, [vp]),
     "phb_ctx_sync": (ci, [vp]),
@@ -91,6 +94,13 @@ SIGNATURES = {
     "phb_fs_assemble_p": (ci, [vp, cd]),
     "phb_fs_step": (ci, [vp, cd, pd]),
     "phb_fs_max_time_step": (ci, [vp, cd, cd, cd, pd]),
+    "phb_piso_create": (ci, [vp, cd, cd, pvp]),
+    "phb_piso_destroy": (ci, [vp]),
+    "phb_piso_field": (vp, [vp, cs]),
+    "phb_piso_solver": (vp, [vp, cs]),
+    "phb_piso_setup": (ci, [vp, cs, cd]),
+    "phb_piso_initialize": (ci, [vp]),
+    "phb_piso_step": (ci, [vp, cd, pd]),
 }
 
 _lib = None

@@ -124,6 +124,33 @@ class FiniteVolumeGrid2D:
         check(comm.L.phb_mesh_create_rect_block(comm.h, nx, ny, width, height, px, py, C.byref(h)))
         return cls(comm, h)
 
+    @classmethod
+    def from_cgns(cls, comm, filename, refine=0, finalize=True):
+        """CgnsUnstructuredGrid: ADF-format CGNS mesh (+ optional uniform refinement rounds)."""
+        h = C.c_void_p()
+        check(comm.L.phb_mesh_read_cgns(comm.h, str(filename).encode(), C.byref(h)))
+        g = cls(comm, h)
+        if refine > 0:
+            h2 = C.c_void_p()
+            check(comm.L.phb_mesh_refine(comm.h, g.h, refine, C.byref(h2)))
+            g.close()
+            g = cls(comm, h2)
+        return g.finalize() if finalize else g
+
+    def refined(self, levels=1, finalize=True):
+        h2 = C.c_void_p()
+        check(self.L.phb_mesh_refine(self.comm.h, self.h, levels, C.byref(h2)))
+        g = FiniteVolumeGrid2D(self.comm, h2)
+        return g.finalize() if finalize else g
+
+    def patch_names(self):
+        out = []
+        for i in range(self.sizes()["nPatches"]):
+            buf = C.create_string_buffer(64)
+            check(self.L.phb_mesh_patch_name(self.h, i, buf, 64))
+            out.append(buf.value.decode())
+        return out
+
     def createPatchByNodes(self, name, pairs):
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1)
         return check(self.L.phb_mesh_add_patch_by_nodes(self.h, name.encode(), len(pairs) // 2, _ip(pairs)))
@@ -449,6 +476,36 @@ class FractionalStep:
             self.h = None
 
 
+class Piso:
+    """phasePiso: device-resident PISO/SIMPLE-type time step (README.md:26-37; self-consistent parity)."""
+
+    def __init__(self, grid, rho=1.0, mu=1.0, **keys):
+        self.grid, self.L = grid, grid.L
+        h = C.c_void_p()
+        check(self.L.phb_piso_create(grid.h, rho, mu, C.byref(h)))
+        self.h = h
+        f = lambda n, nc: FiniteVolumeField(grid, nc, n, handle=C.c_void_p(self.L.phb_piso_field(h, n.encode())))
+        self.u, self.p, self.pCorr, self.gradP, self.d = f("u", 2), f("p", 1), f("pCorr", 1), f("gradP", 2), f("d", 1)
+        self.uSolver = SparseMatrixSolver(grid.comm, handle=C.c_void_p(self.L.phb_piso_solver(h, b"uEqn")))
+        self.pCorrSolver = SparseMatrixSolver(grid.comm, handle=C.c_void_p(self.L.phb_piso_solver(h, b"pCorrEqn")))
+        for k, v in keys.items():
+            check(self.L.phb_piso_setup(h, k.encode(), float(v)))
+
+    def initialize(self):
+        check(self.L.phb_piso_initialize(self.h))
+
+    def solve(self, dt):
+        st = (C.c_double * 6)()
+        check(self.L.phb_piso_step(self.h, dt, st))
+        return dict(itersU=int(st[0]), itersPCorr=int(st[1]), errorU=st[2], errorPCorr=st[3],
+                    maxMassImbalance=st[4], maxCourant=st[5])
+
+    def close(self):
+        if self.h:
+            self.L.phb_piso_destroy(self.h)
+            self.h = None
+
+
 def lid_driven_cavity(grid, rho=1.0, mu=0.1, lid=1.0, solver=None):
     """Examples/LidDrivenCavity/case/boundaries.info on any grid with x-/x+/y-/y+ patches."""
     fs = FractionalStep(grid, rho, mu)
@@ -457,7 +514,7 @@ def lid_driven_cavity(grid, rho=1.0, mu=0.1, lid=1.0, solver=None):
     fs.u.setBoundary("y+", FIXED, (lid, 0.0))
     for pt in ("x-", "x+", "y-", "y+"):
         fs.p.setBoundary(pt, NORMAL_GRADIENT, 0.0)
-    cfg = dict(solver="BICGSTAB", maxIters=20000, tolerance=1e-10, preconditioner="jacobi")
+    cfg = dict(solver="BICGSTAB", maxIters=20000, tolerance=1e-10, preconditioner="ilu0")
     cfg.update(solver or {})
     fs.uEqn.solver.setup(cfg)
     fs.pEqn.solver.setup(cfg)

@@ -28,7 +28,7 @@ void peer_destroy(phb_ctx *c);
 // carve vector `vec` (0..3) of solver region `region` out of the arena
 double *peer_vector(phb_ctx *c, int region, int vec);
 bool peer_owns(const phb_ctx *c, const void *p);
-// all-reduce (sum) of nvals <= 2 doubles at `vals` through channel ch; when S != NULL the kernel
+// all-reduce (sum) of nvals <= 6 doubles at `vals` through channel ch; when S != NULL the kernel
 // exits early once the Krylov loop is done; finishIter publishes the iteration's scalars
 int peer_allreduce(phb_ctx *c, int ch, double *vals, int nvals, void *S, int maxIters, int finishIter, int cur);
 // push the send-list entries of x (inside the arena) into the peers' ghost segments and wait for ours

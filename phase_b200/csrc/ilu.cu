@@ -82,49 +82,51 @@ __global__ void k_ilu_factor(IluView V, double *__restrict__ lu, int r0, int r1)
   }
 }
 
-// forward sweep of one set: z_i = r_i - sum_{lower} l_ik z_k   (unit diagonal)
-template <int NC, bool HAS_LOWER>
+// The first set has no lower entries and the last no upper ones, so y_0 = r_0 is never
+// materialised (readers take r for columns < n0) and the last forward launch divides by the
+// diagonal straight away: 2 (nSets - 1) launches per apply, the matrix is read once.
+//
+// forward sweep of set b >= 1: y_i = r_i - sum_{lower} l_ik y_k  (unit diagonal); LAST: z_i = y_i / u_ii
+template <int NC, bool LAST>
 __global__ void k_ilu_fwd(IluView V, const double *__restrict__ lu, const double *__restrict__ r,
-                          double *__restrict__ z, int ld, int r0, int r1) {
+                          double *z, int ld, int r0, int r1, int n0) {
   const int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= r1) return;
   double acc[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) acc[c] = r[(size_t)c * ld + i];
-  if (HAS_LOWER) {
-    const int len = V.rowLen[i];
-    for (int k = 0; k < len; ++k) {
-      const size_t sl = slot_of(V.sliceOff, i, k);
-      if (V.kind[sl] != 1) continue;
-      const double l = lu[sl];
-      const int j = V.col[sl];
+  const int len = V.rowLen[i];
+  for (int k = 0; k < len; ++k) {
+    const size_t sl = slot_of(V.sliceOff, i, k);
+    if (V.kind[sl] != 1) continue;
+    const double l = lu[sl];
+    const int j = V.col[sl];
+    const double *src = j < n0 ? r : z;
 #pragma unroll
-      for (int c = 0; c < NC; ++c) acc[c] -= l * z[(size_t)c * ld + j];
-    }
+    for (int c = 0; c < NC; ++c) acc[c] -= l * src[(size_t)c * ld + j];
   }
+  const double d = LAST ? lu[slot_of(V.sliceOff, i, V.diagK[i])] : 1.;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) z[(size_t)c * ld + i] = acc[c];
+  for (int c = 0; c < NC; ++c) z[(size_t)c * ld + i] = LAST ? acc[c] / d : acc[c];
 }
 
-// backward sweep of one set: z_i = (z_i - sum_{upper} u_ij z_j) / u_ii
-template <int NC, bool HAS_UPPER>
-__global__ void k_ilu_bwd(IluView V, const double *__restrict__ lu, double *__restrict__ z, int ld, int r0,
-                          int r1) {
+// backward sweep of set b < nSets-1: z_i = (y_i - sum_{upper} u_ij z_j) / u_ii ; FIRST: y_i = r_i
+template <int NC, bool FIRST>
+__global__ void k_ilu_bwd(IluView V, const double *__restrict__ lu, const double *__restrict__ r, double *z,
+                          int ld, int r0, int r1) {
   const int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= r1) return;
   double acc[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) acc[c] = z[(size_t)c * ld + i];
-  if (HAS_UPPER) {
-    const int len = V.rowLen[i];
-    for (int k = 0; k < len; ++k) {
-      const size_t sl = slot_of(V.sliceOff, i, k);
-      if (V.kind[sl] != 3) continue;
-      const double u = lu[sl];
-      const int j = V.col[sl];
+  for (int c = 0; c < NC; ++c) acc[c] = FIRST ? r[(size_t)c * ld + i] : z[(size_t)c * ld + i];
+  const int len = V.rowLen[i];
+  for (int k = 0; k < len; ++k) {
+    const size_t sl = slot_of(V.sliceOff, i, k);
+    if (V.kind[sl] != 3) continue;
+    const double u = lu[sl];
+    const int j = V.col[sl];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) acc[c] -= u * z[(size_t)c * ld + j];
-    }
+    for (int c = 0; c < NC; ++c) acc[c] -= u * z[(size_t)c * ld + j];
   }
   const double d = lu[slot_of(V.sliceOff, i, V.diagK[i])];
 #pragma unroll
@@ -273,25 +275,25 @@ int ilu_apply(phb_solver *s, const double *r, double *z) {
   IluData &D = s->ilu;
   phb_ctx *c = s->ctx;
   const IluView V = view_of(D);
-  const int ld = s->ld;
+  const int ld = s->ld, nb = D.nBlocks, n0 = D.blockPtr[1];
 #define ILU_LAUNCH(K, NCV, FLAG, ...)                                                          \
   do {                                                                                         \
     if (FLAG) PHB_LAUNCH(c, (K<NCV, true>), grid, kThreads, 0, __VA_ARGS__);                   \
     else PHB_LAUNCH(c, (K<NCV, false>), grid, kThreads, 0, __VA_ARGS__);                       \
   } while (0)
-  for (int b = 0; b < D.nBlocks; ++b) {
+  for (int b = 1; b < nb; ++b) {
     const int r0 = D.blockPtr[b], r1 = D.blockPtr[b + 1];
     if (r1 <= r0) continue;
     const int grid = (r1 - r0 + kThreads - 1) / kThreads;
-    if (s->nComp == 1) ILU_LAUNCH(k_ilu_fwd, 1, D.hasLower[b], V, D.lu.p, r, z, ld, r0, r1);
-    else ILU_LAUNCH(k_ilu_fwd, 2, D.hasLower[b], V, D.lu.p, r, z, ld, r0, r1);
+    if (s->nComp == 1) ILU_LAUNCH(k_ilu_fwd, 1, b == nb - 1, V, D.lu.p, r, z, ld, r0, r1, n0);
+    else ILU_LAUNCH(k_ilu_fwd, 2, b == nb - 1, V, D.lu.p, r, z, ld, r0, r1, n0);
   }
-  for (int b = D.nBlocks - 1; b >= 0; --b) {
+  for (int b = std::max(0, nb - 2); b >= 0; --b) {
     const int r0 = D.blockPtr[b], r1 = D.blockPtr[b + 1];
     if (r1 <= r0) continue;
     const int grid = (r1 - r0 + kThreads - 1) / kThreads;
-    if (s->nComp == 1) ILU_LAUNCH(k_ilu_bwd, 1, D.hasUpper[b], V, D.lu.p, z, ld, r0, r1);
-    else ILU_LAUNCH(k_ilu_bwd, 2, D.hasUpper[b], V, D.lu.p, z, ld, r0, r1);
+    if (s->nComp == 1) ILU_LAUNCH(k_ilu_bwd, 1, b == 0, V, D.lu.p, r, z, ld, r0, r1);
+    else ILU_LAUNCH(k_ilu_bwd, 2, b == 0, V, D.lu.p, r, z, ld, r0, r1);
   }
 #undef ILU_LAUNCH
   return PHB_OK;
@@ -307,9 +309,7 @@ int ilu_permute(phb_solver *s, const double *x, double *y, int dir) {
 }
 
 int ilu_launches_per_apply(const phb_solver *s) {
-  int k = 0;
-  for (int b = 0; b < s->ilu.nBlocks; ++b) k += (s->ilu.blockPtr[b + 1] > s->ilu.blockPtr[b]) ? 2 : 0;
-  return k;
+  return 2 * std::max(1, s->ilu.nBlocks - 1) - (s->ilu.nBlocks == 1 ? 1 : 0);
 }
 
 }  // namespace phb

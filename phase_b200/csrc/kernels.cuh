@@ -33,8 +33,9 @@ constexpr int kMaxBlockWarps = 32;
 //   warp shuffle -> shared -> one partial per block -> the last block to arrive
 //   (ticket counter) adds the partials in fixed order and writes out[0..NS).
 // `ticket` must be zero on entry and is reset for the next launch.
+// Returns true in exactly one thread (the one that wrote `out`), after the write.
 template <int NS, bool MAX = false>
-__device__ __forceinline__ void grid_reduce(double (&v)[NS], double *partials, unsigned *ticket,
+__device__ __forceinline__ bool grid_reduce(double (&v)[NS], double *partials, unsigned *ticket,
                                             double *out) {
   __shared__ double sh[NS][kMaxBlockWarps];
   __shared__ bool isLast;
@@ -59,7 +60,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NS], double *partials, u
     }
   }
   __syncthreads();
-  if (!isLast) return;
+  if (!isLast) return false;
   __threadfence();
   double acc[NS];
 #pragma unroll
@@ -85,8 +86,12 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NS], double *partials, u
       w = MAX ? warp_max(w) : warp_sum(w);
       if (lane == 0) out[j] = w;
     }
-    if (lane == 0) *ticket = 0u;
+    if (lane == 0) {
+      *ticket = 0u;
+      return true;
+    }
   }
+  return false;
 }
 
 }  // namespace phb

@@ -17,7 +17,7 @@
 namespace phb {
 namespace {
 
-struct RedSlot { double a, b; unsigned long long epoch, pad; };  // 32 B
+struct RedSlot { double v[6]; unsigned long long epoch, pad; };  // 64 B
 struct PeerView {
   char *arena;
   char *peer[kMaxPeers];
@@ -32,7 +32,7 @@ __device__ __forceinline__ unsigned long long *halo_flag(char *arena, int ch, in
          (size_t)ch * kMaxPeers + src;
 }
 __device__ __forceinline__ unsigned long long *local_epoch(char *arena, int idx) {
-  return reinterpret_cast<unsigned long long *>(arena + 8192) + idx;
+  return reinterpret_cast<unsigned long long *>(arena + 12288) + idx;
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
   unsigned long long v;
@@ -52,7 +52,7 @@ __global__ void k_peer_allreduce(PeerView pv, int ch, double *vals, int nvals, K
                                  int finishIter, int cur) {
   if (S && done_test(S, maxIters)) return;
   const int t = threadIdx.x;
-  __shared__ double sa[kMaxPeers], sb[kMaxPeers];
+  __shared__ double sv[kMaxPeers][6];
   unsigned long long e = 0;
   if (t == 0) {
     unsigned long long *ep = local_epoch(pv.arena, ch);
@@ -60,29 +60,23 @@ __global__ void k_peer_allreduce(PeerView pv, int ch, double *vals, int nvals, K
     *ep = e;
   }
   e = __shfl_sync(0xffffffffu, e, 0);
-  const double a = vals[0], b = nvals > 1 ? vals[1] : 0.;
   if (t < pv.nProcs) {
     RedSlot *dst = red_slot(pv.peer[t], ch, pv.rank);
-    dst->a = a;
-    dst->b = b;
+    for (int k = 0; k < nvals; ++k) dst->v[k] = vals[k];
     __threadfence_system();
     st_release_sys(&dst->epoch, e);
     const RedSlot *src = red_slot(pv.arena, ch, t);
     while (ld_acquire_sys(&src->epoch) < e) {}
-    sa[t] = *reinterpret_cast<const volatile double *>(&src->a);
-    sb[t] = *reinterpret_cast<const volatile double *>(&src->b);
+    for (int k = 0; k < nvals; ++k) sv[t][k] = *reinterpret_cast<const volatile double *>(&src->v[k]);
   }
   __syncwarp();
   if (t == 0) {
-    double xa = 0., xb = 0.;
-    for (int q = 0; q < pv.nProcs; ++q) { xa += sa[q]; xb += sb[q]; }  // fixed order on every rank
-    vals[0] = xa;
-    if (nvals > 1) vals[1] = xb;
-    if (finishIter) {  // k_iter_scalars folded in
-      S->rho[cur ^ 1] = xa;
-      S->rr = xb;
-      S->iters += 1.;
+    for (int k = 0; k < nvals; ++k) {
+      double x = 0.;
+      for (int q = 0; q < pv.nProcs; ++q) x += sv[q][k];  // fixed order on every rank
+      vals[k] = x;
     }
+    if (finishIter) krylov_finish(S, cur);  // alpha, omega, beta, rho', ||r'||^2, iters
   }
 }
 

@@ -70,13 +70,13 @@ __device__ __forceinline__ void slice_dot_any(const int *__restrict__ col, const
 
 // EPI 0: y = A x
 // EPI 1: y = A x, sigma = (w . y)                       [v = A p, (rhat . v)]
-// EPI 2: y = A x, ts = (y . w), tt = (y . y)             [t = A M^-1 s, (t.s), (t.t); w = s]
+// EPI 2: y = A x, ts,tt,rs,rt,ss = (y.w),(y.y),(w2.w),(w2.y),(w.w)   [t = A M^-1 s; w = s, w2 = rhat]
 // EPI 3: y = b - A x, w2 = y, rr = rho0 = (y . y), bb = (b . b)   [initial residual]
 template <int NC, int EPI>
 __global__ void __launch_bounds__(kThreads)
 k_spmv(SellView A, const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-       int ld, const double *__restrict__ w, double *__restrict__ w2, KrylovSums *S, int maxIters,
-       double *partials, unsigned *ticket) {
+       int ld, const double *__restrict__ w, double *w2, KrylovSums *S, int maxIters,
+       double *partials, unsigned *ticket, int cur, int localFinish) {
   if (EPI == 1 || EPI == 2) {
     if (krylov_done(S, maxIters)) return;
   }
@@ -84,7 +84,7 @@ k_spmv(SellView A, const double *__restrict__ vals, const double *__restrict__ x
   const int warpsPerBlock = blockDim.x >> 5;
   const int warp = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
   const int nWarps = gridDim.x * warpsPerBlock;
-  double s0 = 0., s1 = 0.;
+  double s0 = 0., s1 = 0., s2 = 0., s3 = 0., s4 = 0.;
   for (int slice = warp; slice < A.nSlices; slice += nWarps) {
     const int off = __ldg(A.sliceOff + slice);
     const int wdt = (__ldg(A.sliceOff + slice + 1) - off) >> 5;
@@ -108,8 +108,12 @@ k_spmv(SellView A, const double *__restrict__ vals, const double *__restrict__ x
           y[idx] = acc[i];
           if (EPI == 1) s0 = fma(w[idx], acc[i], s0);
           if (EPI == 2) {
-            s0 = fma(acc[i], w[idx], s0);
+            const double sv = w[idx], rh = w2[idx];
+            s0 = fma(acc[i], sv, s0);
             s1 = fma(acc[i], acc[i], s1);
+            s2 = fma(rh, sv, s2);
+            s3 = fma(rh, acc[i], s3);
+            s4 = fma(sv, sv, s4);
           }
         }
       }
@@ -119,40 +123,58 @@ k_spmv(SellView A, const double *__restrict__ vals, const double *__restrict__ x
     double v[1] = {s0};
     grid_reduce<1>(v, partials, ticket, &S->sigma);
   } else if (EPI == 2) {
-    double v[2] = {s0, s1};
-    grid_reduce<2>(v, partials, ticket, &S->ts);
+    double v[5] = {s0, s1, s2, s3, s4};
+    if (grid_reduce<5>(v, partials, ticket, &S->ts) && localFinish) krylov_finish(S, cur);
   } else if (EPI == 3) {
     double v[2] = {s0, s1};
     grid_reduce<2>(v, partials, ticket, &S->rr);  // rr, bb adjacent
   }
 }
 
-// after the (all-reduced) initial sums: derived scalars so that iteration 0 of
-// the general recurrence gives p = r (p = v = 0, beta finite).
+// after the (all-reduced) initial sums: state such that the first fused update
+// leaves x and r untouched and sets p = r  (s = r, t = p = v = 0, alpha = omega = beta = 0)
 __global__ void k_init_scalars(KrylovSums *S, double tol) {
   S->rho[0] = S->rr;
   S->rho[1] = 1.;
   S->sigma = 1.;
-  S->ts = 1.;
-  S->tt = 1.;
+  S->ts = S->tt = S->rs = S->rt = S->ss = 0.;
+  S->alpha = S->omega = S->beta = 0.;
   S->thresh = tol * tol * S->bb;
   S->iters = 0.;
 }
 
-// p = r + beta (p - omega v)
-template <int NC>
+// fused update opening iteration i: it applies the tail of iteration i-1 and the head of i
+//   x += alpha ph + omega sh ;  r = s - omega t ;  p = r + beta (p - omega v)
+// (alpha, omega, beta of iteration i-1 from krylov_finish).  One pass: 5-7 reads, 3 writes.
+template <int NC, bool PRECOND>
 __global__ void __launch_bounds__(kThreads)
-k_update_p(int n, int ld, const double *__restrict__ r, double *__restrict__ p,
-           const double *__restrict__ v, const KrylovSums *S, int cur, int maxIters) {
+k_update_fused(int n, int ld, double *__restrict__ x, double *__restrict__ r, double *__restrict__ p,
+               const double *ph, const double *sh, const double *__restrict__ s,
+               const double *__restrict__ t, const double *__restrict__ v, const KrylovSums *S, int maxIters) {
   if (krylov_done(S, maxIters)) return;
-  const double rhoC = S->rho[cur], rhoP = S->rho[cur ^ 1];
-  const double alphaP = rhoP / S->sigma, omegaP = S->ts / S->tt;
-  const double beta = (rhoC / rhoP) * (alphaP / omegaP);
+  const double alpha = S->alpha, omega = S->omega, beta = S->beta;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const size_t k = (size_t)c * ld + i;
-      p[k] = r[k] + beta * (p[k] - omegaP * v[k]);
+      const double sk = s[k], pk = p[k];
+      x[k] += alpha * (PRECOND ? ph[k] : pk) + omega * (PRECOND ? sh[k] : sk);
+      const double rk = sk - omega * t[k];
+      r[k] = rk;
+      p[k] = rk + beta * (pk - omega * v[k]);
+    }
+  }
+}
+// x += alpha ph + omega sh of the LAST completed iteration (the loop exits before the next fused update)
+template <int NC>
+__global__ void k_final_x(int n, int ld, double *__restrict__ x, const double *__restrict__ ph,
+                          const double *__restrict__ sh, const KrylovSums *S) {
+  const double alpha = S->alpha, omega = S->omega;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const size_t k = (size_t)c * ld + i;
+      x[k] += alpha * ph[k] + omega * sh[k];
     }
   }
 }
@@ -173,39 +195,10 @@ k_update_s(int n, int ld, const double *__restrict__ r, const double *__restrict
   }
 }
 
-// x += alpha p + omega s ; r = s - omega t ; rho' = (rhat . r), rr = (r . r)
-template <int NC>
-__global__ void __launch_bounds__(kThreads)
-k_update_xr(int n, int ld, double *__restrict__ x, const double *__restrict__ ph,
-            const double *__restrict__ sh, const double *__restrict__ s, const double *__restrict__ t,
-            double *__restrict__ r,
-            const double *__restrict__ rhat, KrylovSums *S, int cur, int maxIters, double *partials,
-            unsigned *ticket) {
-  if (krylov_done(S, maxIters)) return;
-  const double alpha = S->rho[cur] / S->sigma, omega = S->ts / S->tt;
-  double s0 = 0., s1 = 0.;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const size_t k = (size_t)c * ld + i;
-      const double sk = s[k];
-      x[k] += alpha * ph[k] + omega * sh[k];
-      const double rk = sk - omega * t[k];
-      r[k] = rk;
-      s0 = fma(rhat[k], rk, s0);
-      s1 = fma(rk, rk, s1);
-    }
-  }
-  double v[2] = {s0, s1};
-  // results land in a scratch pair first: other blocks still read S->rho[cur]
-  grid_reduce<2>(v, partials, ticket, &S->pad[0]);
-}
-// publish the iteration's sums (after the all-reduce when nProcs > 1)
+// NCCL path: publish the iteration's scalars after the all-reduce of R2
 __global__ void k_iter_scalars(KrylovSums *S, int cur, int maxIters) {
   if (krylov_done(S, maxIters)) return;
-  S->rho[cur ^ 1] = S->pad[0];
-  S->rr = S->pad[1];
-  S->iters += 1.;
+  krylov_finish(S, cur);
 }
 
 // ---------------------------------------------------------------- Jacobi fold
@@ -288,16 +281,17 @@ int spmv_grid(const phb_ctx *c, const SellPattern *P) {
 }
 
 template <int EPI>
-void launch_spmv(phb_solver *s, const double *vals, const double *x, double *y, const double *w, double *w2) {
+void launch_spmv(phb_solver *s, const double *vals, const double *x, double *y, const double *w, double *w2,
+                 int cur = 0, int localFinish = 0) {
   const SellPattern *P = s->runPat ? s->runPat : s->pat;
   const SellView A = view_of(P);
   const int grid = spmv_grid(s->ctx, P);
   if (s->nComp == 1)
     PHB_LAUNCH(s->ctx, (k_spmv<1, EPI>), grid, kThreads, 0, A, vals, x, y, s->ld, w, w2, s->sums.p, s->maxIters,
-               s->partials.p, s->ticket.p);
+               s->partials.p, s->ticket.p, cur, localFinish);
   else
     PHB_LAUNCH(s->ctx, (k_spmv<2, EPI>), grid, kThreads, 0, A, vals, x, y, s->ld, w, w2, s->sums.p, s->maxIters,
-               s->partials.p, s->ticket.p);
+               s->partials.p, s->ticket.p, cur, localFinish);
 }
 
 // ghost refresh of a gathered vector before an SpMV (grid_->sendMessages analogue
@@ -348,14 +342,17 @@ int enqueue_iteration(phb_solver *s, const double *A, int cur) {
   const int n = s->pat->nRows, ld = s->ld;
   const int gv = grid_for(c, n);
   const bool ilu = s->precond == PHB_PC_ILU0;
+  const bool multi = c->nProcs > 1;
   double *ph = ilu ? s->ph.p : s->p.p, *sh = ilu ? s->sh.p : s->s.p;
-  if (s->nComp == 1)
-    PHB_LAUNCH(c, k_update_p<1>, gv, kThreads, 0, n, ld, s->r.p, s->p.p, s->v.p, s->sums.p, cur, s->maxIters);
-  else
-    PHB_LAUNCH(c, k_update_p<2>, gv, kThreads, 0, n, ld, s->r.p, s->p.p, s->v.p, s->sums.p, cur, s->maxIters);
+#define FUSED(NCV, PRE)                                                                                          \
+  PHB_LAUNCH(c, (k_update_fused<NCV, PRE>), gv, kThreads, 0, n, ld, s->x.p, s->r.p, s->p.p, ph, sh, s->s.p, s->t.p, \
+             s->v.p, s->sums.p, s->maxIters)
+  if (s->nComp == 1) { if (ilu) FUSED(1, true); else FUSED(1, false); }
+  else { if (ilu) FUSED(2, true); else FUSED(2, false); }
+#undef FUSED
   if (ilu) PHB_CHECK(ilu_apply(s, s->p.p, ph));          // ph = M^-1 p
   PHB_CHECK(halo_exchange(s, ph, true));
-  launch_spmv<1>(s, A, ph, s->v.p, s->rhat.p, nullptr);   // v = A ph, sigma = (rhat . v)
+  launch_spmv<1>(s, A, ph, s->v.p, s->rhat.p, nullptr);   // v = A ph, R1: sigma = (rhat . v)
   PHB_CHECK(reduce_sums(s, 0, &s->sums.p->sigma, 1, true, 0, cur));
   if (s->nComp == 1)
     PHB_LAUNCH(c, k_update_s<1>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->sums.p, cur, s->maxIters);
@@ -363,19 +360,15 @@ int enqueue_iteration(phb_solver *s, const double *A, int cur) {
     PHB_LAUNCH(c, k_update_s<2>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->sums.p, cur, s->maxIters);
   if (ilu) PHB_CHECK(ilu_apply(s, s->s.p, sh));          // sh = M^-1 s
   PHB_CHECK(halo_exchange(s, sh, true));
-  launch_spmv<2>(s, A, sh, s->t.p, s->s.p, nullptr);      // t = A sh, (t . s), (t . t)
-  PHB_CHECK(reduce_sums(s, 1, &s->sums.p->ts, 2, true, 0, cur));
-  if (s->nComp == 1)
-    PHB_LAUNCH(c, k_update_xr<1>, gv, kThreads, 0, n, ld, s->x.p, ph, sh, s->s.p, s->t.p, s->r.p, s->rhat.p,
-               s->sums.p, cur, s->maxIters, s->partials.p, s->ticket.p);
-  else
-    PHB_LAUNCH(c, k_update_xr<2>, gv, kThreads, 0, n, ld, s->x.p, ph, sh, s->s.p, s->t.p, s->r.p, s->rhat.p,
-               s->sums.p, cur, s->maxIters, s->partials.p, s->ticket.p);
-  if (use_peer(s)) {  // the all-reduce kernel also publishes the iteration's scalars
-    PHB_CHECK(reduce_sums(s, 2, &s->sums.p->pad[0], 2, true, 1, cur));
-  } else {
-    PHB_CHECK(comm_allreduce_sum(c, &s->sums.p->pad[0], 2));
-    PHB_LAUNCH(c, k_iter_scalars, 1, 1, 0, s->sums.p, cur, s->maxIters);
+  // t = A sh, R2: (t.s), (t.t), (rhat.s), (rhat.t), (s.s); single GPU: the last CTA finishes the iteration
+  launch_spmv<2>(s, A, sh, s->t.p, s->s.p, s->rhat.p, cur, multi ? 0 : 1);
+  if (multi) {
+    if (use_peer(s)) {  // the all-reduce kernel also finishes the iteration
+      PHB_CHECK(reduce_sums(s, 1, &s->sums.p->ts, 5, true, 1, cur));
+    } else {
+      PHB_CHECK(comm_allreduce_sum(c, &s->sums.p->ts, 5));
+      PHB_LAUNCH(c, k_iter_scalars, 1, 1, 0, s->sums.p, cur, s->maxIters);
+    }
   }
   return PHB_OK;
 }
@@ -398,8 +391,8 @@ int ensure_vectors(phb_solver *s) {
     PHB_CHECK(s->p.alloc(len)); PHB_CHECK(s->s.alloc(len));
   }
   const size_t nb = (size_t)s->ctx->numSMs * kBlocksPerSM;
-  if (s->partials.n != nb * 4) {
-    PHB_CHECK(s->partials.alloc(nb * 4));
+  if (s->partials.n != nb * 8) {
+    PHB_CHECK(s->partials.alloc(nb * 8));
     PHB_CHECK(s->ticket.alloc(1));
     PHB_CHECK(s->ticket.zero(s->ctx->stream));
     PHB_CHECK(s->sums.alloc(1));
@@ -485,11 +478,14 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
   int totalIters = 0;
   double rel = 0.;
   for (int attempt = 0; attempt < 3; ++attempt) {
-    // ---- r = b - A x, rhat = r, p = v = 0
-    PHB_CUDA(cudaMemsetAsync(s->p.p, 0, (size_t)ld * s->nComp * sizeof(double), c->stream));
-    PHB_CUDA(cudaMemsetAsync(s->v.p, 0, (size_t)ld * s->nComp * sizeof(double), c->stream));
+    // ---- r = b - A x, rhat = s = r, p = v = t = 0
+    const size_t vbytes = (size_t)ld * s->nComp * sizeof(double);
+    PHB_CUDA(cudaMemsetAsync(s->p.p, 0, vbytes, c->stream));
+    PHB_CUDA(cudaMemsetAsync(s->v.p, 0, vbytes, c->stream));
+    PHB_CUDA(cudaMemsetAsync(s->t.p, 0, vbytes, c->stream));
     PHB_CHECK(halo_exchange(s, s->x.p));
     launch_spmv<3>(s, Aw, s->x.p, s->r.p, s->b.p, s->rhat.p);
+    PHB_CUDA(cudaMemcpyAsync(s->s.p, s->r.p, vbytes, cudaMemcpyDeviceToDevice, c->stream));
     PHB_CHECK(reduce_sums(s, 3, &s->sums.p->rr, 2, false, 0, 0));
     PHB_LAUNCH(c, k_init_scalars, 1, 1, 0, s->sums.p, s->tol);
     const int budget = s->maxIters - totalIters;
@@ -519,7 +515,7 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
       if (g) cudaGraphDestroy(g);
       memcpy(s->graphKey, key, sizeof(key));
     }
-    const int launchesPerIter = 6 + ((s->halo && c->nProcs > 1) ? 2 : 0) +
+    const int launchesPerIter = 4 + ((s->halo && c->nProcs > 1) ? (use_peer(s) ? 4 : 3) : 0) +
                                 (s->precond == PHB_PC_ILU0 ? 2 * ilu_launches_per_apply(s) : 0);
     int launched = 0, burst = 1;
     bool done = false;
@@ -537,6 +533,13 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
       PHB_CUDA(cudaStreamSynchronize(c->stream));
       done = !(hs->rr > hs->thresh) || hs->iters >= (double)budget;
       burst = std::min(burst * 2, 8);
+    }
+    // the x-update of the last completed iteration is still pending (it rides in the NEXT fused update)
+    {
+      const double *ph = s->precond == PHB_PC_ILU0 ? s->ph.p : s->p.p;
+      const double *sh = s->precond == PHB_PC_ILU0 ? s->sh.p : s->s.p;
+      if (s->nComp == 1) PHB_LAUNCH(c, k_final_x<1>, gv, kThreads, 0, n, ld, s->x.p, ph, sh, s->sums.p);
+      else PHB_LAUNCH(c, k_final_x<2>, gv, kThreads, 0, n, ld, s->x.p, ph, sh, s->sums.p);
     }
     s->maxIters = saveMax;
     totalIters += (int)hs->iters;

@@ -2,17 +2,37 @@
 #pragma once
 #include "structs.cuh"
 
-// device-resident Krylov scalars (one cache line)
+// device-resident Krylov scalars.  One BiCGStab iteration needs TWO reductions:
+//   R1: sigma = (rhat . v)                                  after v = A M^-1 p
+//   R2: ts, tt, rs, rt, ss = (t.s), (t.t), (rhat.s), (rhat.t), (s.s)   after t = A M^-1 s
+// from which omega = ts/tt, rho' = rs - omega rt and ||r'||^2 = ss - 2 omega ts + omega^2 tt
+// follow without a third reduction ("finish" step, krylov_finish()).
 struct KrylovSums {
   double rho[2];   // (rhat . r), parity-indexed by iteration
-  double sigma;    // (rhat . v)
-  double ts, tt;   // (t . s), (t . t)
-  double rr;       // ||r||^2
+  double sigma;    // R1
+  double ts, tt, rs, rt, ss;  // R2 (contiguous: one all-reduce of 5 doubles)
+  double rr;       // ||r||^2 (recurrence), bb follows (contiguous pair for the initial all-reduce)
   double bb;       // ||b||^2
   double thresh;   // tol^2 * bb
-  double iters;    // iterations actually performed
-  double pad[7];
+  double iters;    // iterations completed
+  double alpha, omega, beta;  // of the last completed iteration (consumed by the fused update)
+  double pad;
 };
+
+// after R2 of iteration `cur` (single writer, no concurrent readers)
+__host__ __device__ inline void krylov_finish(KrylovSums *S, int cur) {
+  const double rho = S->rho[cur];
+  const double alpha = rho / S->sigma;
+  const double omega = S->tt != 0. ? S->ts / S->tt : 0.;
+  const double rhoN = S->rs - omega * S->rt;
+  const double rr = S->ss - 2. * omega * S->ts + omega * omega * S->tt;
+  S->alpha = alpha;
+  S->omega = omega;
+  S->beta = (rhoN / rho) * (alpha / omega);
+  S->rho[cur ^ 1] = rhoN;
+  S->rr = rr > 0. ? rr : (rr == rr ? 0. : rr);  // clamp round-off negatives, keep NaN
+  S->iters += 1.;
+}
 
 // ILU(0): permuted pattern + factors (ilu.cu)
 struct IluData {
@@ -32,7 +52,7 @@ struct phb_solver {
   // configuration (keys of LinearAlgebra.<eqn>, M/TrilinosBelosSparseMatrixSolver.cpp:44-86)
   int maxIters = 500;
   double tol = 1e-8;
-  int precond = PHB_PC_JACOBI;
+  int precond = PHB_PC_ILU0;       // the reference's Belos default: Schwarz(overlap 0) + RILUK(0)
   std::string method = "BICGSTAB";
   int itersPerGraph = 8;
   bool useGraph = true;
