@@ -75,6 +75,9 @@ int phb_fs_initialize(phb_fracstep *fs) {
   PHB_CHECK(phb::field_send_messages(fs->u));
   PHB_CHECK(phb::field_interpolate_faces(fs->u));
   PHB_CHECK(phb::field_set_boundary_faces(fs->p));
+  bool neumann = false;  // all-Neumann pressure: pEqn_ is singular, keep its right-hand side compatible
+  PHB_CHECK(phb::field_all_neumann(fs->p, &neumann));
+  PHB_CHECK(phb_solver_setup(fs->pSolver, "nullSpace", neumann ? "constant" : "none"));
   return PHB_OK;
 }
 

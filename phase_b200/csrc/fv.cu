@@ -550,6 +550,29 @@ int field_axpy_faces(phb_field *y, double a, const phb_field *x) {
   return PHB_OK;
 }
 
+// true when no patch of the field is FIXED on ANY rank: the Laplacian of such a field is singular
+int field_all_neumann(phb_field *f, bool *out) {
+  phb_mesh *m = f->m;
+  phb_ctx *c = m->ctx;
+  double has = 0.;
+  for (int fc = 0; fc < m->nFaces; ++fc) {
+    const int p = m->fPatch[fc];
+    if (m->fR[fc] < 0 && m->owner[m->fL[fc]] == m->rank && p >= 0 && p < (int)f->bc.size() && f->bc[p].type == PHB_FIXED) {
+      has = 1.;
+      break;
+    }
+  }
+  if (c->nProcs > 1) {
+    phb::DevBuf<double> d;
+    PHB_CHECK(d.upload(&has, 1, c->stream));
+    PHB_CHECK(comm_allreduce_max(c, d.p, 1));
+    PHB_CUDA(cudaMemcpyAsync(&has, d.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PHB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  *out = has == 0.;
+  return PHB_OK;
+}
+
 int field_send_messages(phb_field *f) {
   phb_mesh *m = f->m;
   phb_ctx *c = m->ctx;

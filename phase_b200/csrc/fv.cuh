@@ -10,6 +10,7 @@ int field_gradient(const phb_field *phi, phb_field *grad);
 int field_axpy_cells(phb_field *y, double a, const phb_field *x);  // owned cells
 int field_axpy_faces(phb_field *y, double a, const phb_field *x);  // all faces
 int field_send_messages(phb_field *f);
+int field_all_neumann(phb_field *f, bool *out);
 // device max over owned cells of |sum_f u_f.S_f| (mode 0) or the Courant number (mode 1)
 int field_flux_max(const phb_field *u, int mode, double dt, DevBuf<double> &scratch, DevBuf<double> &partials,
                    DevBuf<unsigned> &ticket, double *devOut);

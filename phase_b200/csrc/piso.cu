@@ -141,6 +141,9 @@ int phb_piso_initialize(phb_piso *s) {
   PHB_CHECK(phb::field_interpolate_faces(s->u));
   PHB_CHECK(phb::field_set_boundary_faces(s->p));
   PHB_CHECK(phb::field_gradient(s->p, s->gradP));
+  bool neumann = false;
+  PHB_CHECK(phb::field_all_neumann(s->p, &neumann));
+  PHB_CHECK(phb_solver_setup(s->pSolver, "nullSpace", neumann ? "constant" : "none"));
   return PHB_OK;
 }
 

@@ -242,6 +242,20 @@ __global__ void k_diag_apply(int n, int ld, const double *__restrict__ x, const 
   }
 }
 
+// sum of b over owned rows (+ row count), and b -= shift: compatibility projection for singular systems
+__global__ void __launch_bounds__(kThreads)
+k_sum_rows(int n, const double *__restrict__ b, double *partials, unsigned *ticket, double *out) {
+  double s0 = 0.;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s0 += b[i];
+  double v[2] = {s0, 0.};
+  if (blockIdx.x == 0 && threadIdx.x == 0) v[1] = (double)n;
+  grid_reduce<2>(v, partials, ticket, out);
+}
+__global__ void k_shift_rows(int n, double *__restrict__ b, const double *__restrict__ sumCount) {
+  const double shift = sumCount[0] / sumCount[1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) b[i] -= shift;
+}
+
 // halo pack: sendBuf[c][j] = x[c*ld + sendDev[j]]
 __global__ void k_pack(int nSend, int nComp, int ld, const int *__restrict__ sendDev,
                        const double *__restrict__ x, double *__restrict__ buf) {
@@ -434,6 +448,15 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
   const double *Aw = s->dVals;
   s->runPat = P;
   s->runSendDev = nullptr;
+  // ---- singular (all-Neumann) scalar systems: make the right-hand side compatible, 1^T b = 0.
+  // Round-off in an assembled b (e.g. a converged mass imbalance) otherwise leaves a component the
+  // Krylov iteration can never remove.
+  if (s->projectConstant && s->nComp == 1) {
+    PHB_CHECK(s->proj.alloc(2));
+    PHB_LAUNCH(c, k_sum_rows, gv, kThreads, 0, n, s->b.p, s->partials.p, s->ticket.p, s->proj.p);
+    PHB_CHECK(comm_allreduce_sum(c, s->proj.p, 2));
+    PHB_LAUNCH(c, k_shift_rows, gv, kThreads, 0, n, s->b.p, s->proj.p);
+  }
   // ---- ILU(0): iterate on the symmetrically permuted system (rows grouped by independent set)
   if (s->precond == PHB_PC_ILU0) {
     PHB_CHECK(ilu_prepare(s, P, (s->halo && c->nProcs > 1) ? s->halo : nullptr));
@@ -627,6 +650,9 @@ int phb_solver_setup(phb_solver *s, const char *key, const char *value) {
     if (lv == "multicolor" || lv == "multicolour" || lv == "colour" || lv == "color") s->iluOrdering = 0;
     else if (lv == "levels" || lv == "natural" || lv == "wavefront") s->iluOrdering = 1;
     else PHB_REQUIRE(false, "unknown ILU ordering \"%s\" (multicolor | levels)", value);
+  } else if (k == "nullSpace") {
+    PHB_REQUIRE(lv == "constant" || lv == "none", "nullSpace must be \"constant\" or \"none\"");
+    s->projectConstant = lv == "constant";
   } else if (k == "iluFill") {
     PHB_REQUIRE(std::stod(v) == 0., "only iluFill 0 is supported");
   } else if (k == "itersPerGraph") {

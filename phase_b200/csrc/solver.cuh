@@ -55,6 +55,7 @@ struct phb_solver {
   int precond = PHB_PC_ILU0;       // the reference's Belos default: Schwarz(overlap 0) + RILUK(0)
   std::string method = "BICGSTAB";
   int itersPerGraph = 8;
+  bool projectConstant = false;    // singular all-Neumann systems: remove the constant from b (hard part 3)
   bool useGraph = true;
   // ---- matrix as handed over by set_csr (host CSR cache for pattern reuse)
   int nRows = 0, nColsGlobal = 0;
@@ -79,7 +80,7 @@ struct phb_solver {
   int peerRegion = -1;             // slot of this solver in the peer arena (-1 unassigned, -2 not usable)
   double *runPh = nullptr, *runSh = nullptr;
   phb::DevBuf<double> b, x, r, rhat, p, v, s, t;
-  phb::DevBuf<double> partials;
+  phb::DevBuf<double> partials, proj;
   phb::DevBuf<unsigned> ticket;
   phb::DevBuf<KrylovSums> sums;
   bool haveRhs = false, haveGuess = false;
