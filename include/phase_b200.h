@@ -234,6 +234,16 @@ int phb_assemble_laplacian(phb_eqn *e, double gammaConst,
                            double theta, double sign);
 int phb_assemble_src(phb_eqn *e, const phb_field *f, double sign);
 int phb_assemble_src_div(phb_eqn *e, const phb_field *u, double sign);
+/* CICSAM (UD/Cicsam.cpp): face weights beta_f (:19-66) into beta's FACE values,
+ * cicsam::div(u, gamma, beta, theta) (:89-138) accumulated with sign, and the
+ * density-weighted momentum flux rhoU_f (:69-87) into rhoU's face values. */
+int phb_cicsam_weights(const phb_field *u, const phb_field *gamma,
+                       const phb_field *gradGamma, double dt, phb_field *beta);
+int phb_assemble_cicsam_div(phb_eqn *e, const phb_field *u, const phb_field *gamma,
+                            const phb_field *beta, double theta, double sign);
+int phb_cicsam_momentum_flux(double rho1, double rho2, const phb_field *u,
+                             const phb_field *gamma, const phb_field *beta,
+                             phb_field *rhoU);
 /* rho * eqn row scaling: UE/VectorFiniteVolumeEquation.cpp:163-170 */
 int phb_eqn_scale_rows(phb_eqn *e, const phb_field *rho);
 /* relax(omega): body recovered from UE/ScalarFiniteVolumeEquation.cpp:45-55 */

@@ -103,6 +103,10 @@ def lib():
                                   C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int,
                                   C.POINTER(C.c_double)]
+        L.or_cicsam_weights.argtypes = [vp, C.c_double] + [C.POINTER(C.c_double)] * 3
+        L.or_op_cicsam_div.restype = vp
+        L.or_op_cicsam_div.argtypes = [vp, C.c_double] + [C.POINTER(C.c_double)] * 3
+        L.or_cicsam_momentum_flux.argtypes = [vp, C.c_double, C.c_double] + [C.POINTER(C.c_double)] * 3
         L.or_multicolor_order.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.POINTER(C.c_int), C.c_int]
         L.or_bicgstab_blocks.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
@@ -376,6 +380,23 @@ class FracStep:
     def scalar_transport(self, dt, theta, rho, rho0, phi0, phi0f):
         a = [np.ascontiguousarray(v, dtype=np.float64) for v in (rho, rho0, phi0, phi0f)]
         return Crs(handle=lib().or_op_scalar_transport(self.h, dt, theta, *[_dp(v) for v in a]))
+
+    def cicsam_weights(self, dt, gx, gy):
+        gx, gy = np.ascontiguousarray(gx, np.float64), np.ascontiguousarray(gy, np.float64)
+        beta = np.zeros(self.mesh.sizes["nFaces"])
+        lib().or_cicsam_weights(self.h, dt, _dp(gx), _dp(gy), _dp(beta))
+        return beta
+
+    def cicsam_div(self, theta, beta, gamma0, gamma0f):
+        a = [np.ascontiguousarray(v, np.float64) for v in (beta, gamma0, gamma0f)]
+        return Crs(handle=lib().or_op_cicsam_div(self.h, theta, *[_dp(v) for v in a]))
+
+    def cicsam_momentum_flux(self, rho1, rho2, beta):
+        beta = np.ascontiguousarray(beta, np.float64)
+        F = self.mesh.sizes["nFaces"]
+        ox, oy = np.zeros(F), np.zeros(F)
+        lib().or_cicsam_momentum_flux(self.h, rho1, rho2, _dp(beta), _dp(ox), _dp(oy))
+        return ox, oy
 
     def view(self, name):
         """Writable numpy view of a field array (ux, uy, ufx, ufy, p, pf, gpx, ...)."""

@@ -1361,6 +1361,103 @@ OrCrs *or_op_scalar_transport(OrFracStep *s, double dt, double theta, const doub
   return e1;
 }
 
+
+/* --------------------------------------------------------------- CICSAM (A9) */
+static double clampd(double v, double lo, double hi) { return fmax(fmin(v, hi), lo); }
+/* cicsam::hc / cicsam::uq: UD/Cicsam.cpp:5-17 */
+static double cicsam_hc(double g, double co) { return g >= 0 && g <= 1 ? fmin(1., g / co) : g; }
+static double cicsam_uq(double g, double co) {
+  return g >= 0 && g <= 1 ? fmin((8. * co * g + (1. - co) * (6. * g + 3.)) / 8., cicsam_hc(g, co)) : g;
+}
+/* cicsam::faceInterpolationWeights: UD/Cicsam.cpp:19-66.  gamma = the scalar field "p" (cells),
+ * gradGamma = (gx, gy) cell values, u = the vector field's faces. */
+void or_cicsam_weights(OrFracStep *s, double dt, const double *gx, const double *gy, double *beta) {
+  OrMesh *m = s->m;
+  const double k = 1.;
+  for (int f = 0; f < m->nFaces; ++f) beta[f] = 0.;
+  for (int f = 0; f < m->nFaces; ++f) {
+    int l = m->fL[f], r = m->fR[f];
+    if (r < 0) continue;
+    double sx, sy;
+    outward_norm(m, f, m->cCx[l], m->cCy[l], &sx, &sy);
+    double flux = s->ufx[f] * sx + s->ufy[f] * sy;
+    int d = flux > 0. ? l : r, a = flux <= 0. ? l : r;
+    double rcx = m->cCx[a] - m->cCx[d], rcy = m->cCy[a] - m->cCy[d];
+    double gD = clampd(s->p[d], 0., 1.), gA = clampd(s->p[a], 0., 1.);
+    double gU = clampd(gA - 2. * (rcx * gx[d] + rcy * gy[d]), 0., 1.);
+    double gDT = (gD - gU) / (gA - gU);
+    if (!isfinite(gDT)) gDT = 0.;
+    double coD = 0.;
+    for (int j = m->ilPtr[d]; j < m->ilPtr[d + 1]; ++j)
+      coD += fmax((s->ufx[m->ilFace[j]] * m->ilSx[j] + s->ufy[m->ilFace[j]] * m->ilSy[j]) / m->vol[d] * dt, 0.);
+    for (int j = m->blPtr[d]; j < m->blPtr[d + 1]; ++j)
+      coD += fmax((s->ufx[m->blFace[j]] * m->blSx[j] + s->ufy[m->blFace[j]] * m->blSy[j]) / m->vol[d] * dt, 0.);
+    double gm = sqrt(gx[d] * gx[d] + gy[d] * gy[d]), rm = sqrt(rcx * rcx + rcy * rcy);
+    double thetaF = acos(fabs((gx[d] / gm) * (rcx / rm) + (gy[d] / gm) * (rcy / rm)));
+    double psiF = fmin(k * (cos(2 * thetaF) + 1.) / 2., 1.);
+    double gFT = psiF * cicsam_hc(gDT, coD) + (1. - psiF) * cicsam_uq(gDT, coD);
+    double b = (gFT - gDT) / (1. - gDT);
+    if (isfinite(b)) b = fmax(fmin(1., b), 0.);
+    else b = 0.;
+    beta[f] = b;
+  }
+}
+/* cicsam::div(u, gamma, beta, theta): UD/Cicsam.cpp:89-138 on the scalar field "p"; gamma0 given */
+OrCrs *or_op_cicsam_div(OrFracStep *s, double theta, const double *beta, const double *g0, const double *g0f) {
+  OrMesh *m = s->m;
+  OrCrs *e = or_crs_create(m->nLocal, 5);
+  for (int c = 0; c < m->nCells; ++c) {
+    if (m->owner[c] != m->rank) continue;
+    int r = m->localRow[c];
+    for (int j = m->ilPtr[c]; j < m->ilPtr[c + 1]; ++j) {
+      int f = m->ilFace[j], nb = m->ilCell[j];
+      double flux = s->ufx[f] * m->ilSx[j] + s->ufy[f] * m->ilSy[j];
+      int donor = flux > 0. ? c : nb, acceptor = flux <= 0. ? c : nb;
+      double b = beta[f];
+      or_crs_add_coeff(e, r, m->globalRow[donor], theta * (1. - b) * flux);
+      or_crs_add_coeff(e, r, m->globalRow[acceptor], theta * b * flux);
+      double gF = (1. - b) * g0[donor] + b * g0[acceptor];
+      e->rhs[r] += (1. - theta) * flux * gF;
+    }
+    for (int j = m->blPtr[c]; j < m->blPtr[c + 1]; ++j) {
+      int f = m->blFace[j];
+      double flux = s->ufx[f] * m->blSx[j] + s->ufy[f] * m->blSy[j];
+      switch (bc_type(s->pbc, m, f)) {
+      case OR_FIXED:
+        e->rhs[r] += theta * flux * s->pf[f];
+        e->rhs[r] += (1. - theta) * flux * g0f[f];
+        break;
+      case OR_NORMAL_GRADIENT:
+        or_crs_add_coeff(e, r, m->globalRow[c], theta * flux);
+        e->rhs[r] += (1. - theta) * flux * g0[c];
+        break;
+      default:
+        break;
+      }
+    }
+  }
+  return e;
+}
+/* cicsam::computeMomentumFlux: UD/Cicsam.cpp:69-87 -> rhoU faces (x, y) */
+void or_cicsam_momentum_flux(OrFracStep *s, double rho1, double rho2, const double *beta, double *outx, double *outy) {
+  OrMesh *m = s->m;
+  for (int f = 0; f < m->nFaces; ++f) {
+    int l = m->fL[f], r = m->fR[f];
+    double g;
+    if (r >= 0) {
+      double sx, sy;
+      outward_norm(m, f, m->cCx[l], m->cCy[l], &sx, &sy);
+      double flux = s->ufx[f] * sx + s->ufy[f] * sy;
+      int d = flux > 0. ? l : r, a = flux <= 0. ? l : r;
+      g = (1. - beta[f]) * s->p[d] + beta[f] * s->p[a];
+    } else
+      g = s->pf[f];
+    double rho = rho1 + clampd(g, 0., 1.) * (rho2 - rho1);
+    outx[f] = rho * s->ufx[f];
+    outy[f] = rho * s->ufy[f];
+  }
+}
+
 const OrCrs *or_fs_ueqn(const OrFracStep *s) { return s->uEqn; }
 const OrCrs *or_fs_peqn(const OrFracStep *s) { return s->pEqn; }
 

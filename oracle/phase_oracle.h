@@ -115,6 +115,11 @@ OrCrs *or_op_ueqn_multiphase(OrFracStep *s, double dt, const double *rhoCell,
 OrCrs *or_op_scalar_transport(OrFracStep *s, double dt, double theta, const double *rho,
                               const double *rho0, const double *phi0, const double *phi0f);
 
+/* CICSAM (A9): UD/Cicsam.cpp.  gamma = the scalar field "p", u = faces of "u". */
+void or_cicsam_weights(OrFracStep *s, double dt, const double *gradGx, const double *gradGy, double *beta);
+OrCrs *or_op_cicsam_div(OrFracStep *s, double theta, const double *beta, const double *gamma0, const double *gamma0f);
+void or_cicsam_momentum_flux(OrFracStep *s, double rho1, double rho2, const double *beta, double *outx, double *outy);
+
 /* ---- built-in CPU solver (OpenMP BiCGStab, Jacobi or ILU(0)) ---- */
 /* precond: 0 none, 1 Jacobi, 2 ILU(0).  returns iterations, *relres out.
  * x holds the initial guess on entry. */

@@ -352,6 +352,20 @@ class ScalarGradient(FiniteVolumeField):
         check(self.L.phb_field_gradient(self.phi.h, self.h))
 
 
+class cicsam:
+    """namespace cicsam (UD/Cicsam.cpp)."""
+
+    @staticmethod
+    def faceInterpolationWeights(u, gamma, gradGamma, timeStep, beta):
+        check(u.L.phb_cicsam_weights(u.h, gamma.h, gradGamma.h, timeStep, beta.h))
+        return beta
+
+    @staticmethod
+    def computeMomentumFlux(rho1, rho2, u, gamma, beta, rhoU):
+        check(u.L.phb_cicsam_momentum_flux(rho1, rho2, u.h, gamma.h, beta.h, rhoU.h))
+        return rhoU
+
+
 class FiniteVolumeEquation:
     """UE/FiniteVolumeEquation<T> on the canonical pattern, assembled on the device."""
 
@@ -400,6 +414,10 @@ class FiniteVolumeEquation:
 
     def srcDiv(self, u, sign=1.0):
         check(self.L.phb_assemble_src_div(self.h, u.h, sign))
+        return self
+
+    def cicsamDiv(self, u, gamma, beta, theta, sign=1.0):
+        check(self.L.phb_assemble_cicsam_div(self.h, u.h, gamma.h, beta.h, theta, sign))
         return self
 
     def scaleRows(self, rho):
