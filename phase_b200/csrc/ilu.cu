@@ -85,52 +85,56 @@ __global__ void k_ilu_factor(IluView V, double *__restrict__ lu, int r0, int r1)
 // The first set has no lower entries and the last no upper ones, so y_0 = r_0 is never
 // materialised (readers take r for columns < n0) and the last forward launch divides by the
 // diagonal straight away: 2 (nSets - 1) launches per apply, the matrix is read once.
+// Same access scheme as the SpMV: warp <-> 32-row slice, lane <-> row, coalesced col/val loads
+// issued four entries ahead; lower / upper membership follows from the column alone
+// (rows of a set are a contiguous range [r0, r1) of the permuted numbering):
+//   lower  <=> col <  r0          upper <=> r1 <= col < nRows        (col >= nRows: ghost, ignored)
 //
-// forward sweep of set b >= 1: y_i = r_i - sum_{lower} l_ik y_k  (unit diagonal); LAST: z_i = y_i / u_ii
-template <int NC, bool LAST>
-__global__ void k_ilu_fwd(IluView V, const double *__restrict__ lu, const double *__restrict__ r,
-                          double *z, int ld, int r0, int r1, int n0) {
-  const int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= r1) return;
-  double acc[NC];
+// MODE 0: forward, y_i = r_i - sum_lower l_ik y_k            MODE 1: same, then z_i = y_i / u_ii (last set)
+// MODE 2: backward, z_i = (y_i - sum_upper u_ij z_j) / u_ii  MODE 3: same with y_i = r_i (first set)
+template <int NC, int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_ilu_sweep(IluView V, const double *__restrict__ lu, const double *__restrict__ r, double *z, int ld, int r0,
+            int r1, int n0) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int s0 = r0 >> 5, s1 = (r1 - 1) >> 5;
+  for (int slice = s0 + blockIdx.x * wpb + (threadIdx.x >> 5); slice <= s1; slice += gridDim.x * wpb) {
+    const int off = __ldg(V.sliceOff + slice);
+    const int w = (__ldg(V.sliceOff + slice + 1) - off) >> 5;
+    const int row = slice * 32 + lane;
+    const bool active = row >= r0 && row < r1;
+    double acc[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) acc[c] = r[(size_t)c * ld + i];
-  const int len = V.rowLen[i];
-  for (int k = 0; k < len; ++k) {
-    const size_t sl = slot_of(V.sliceOff, i, k);
-    if (V.kind[sl] != 1) continue;
-    const double l = lu[sl];
-    const int j = V.col[sl];
-    const double *src = j < n0 ? r : z;
+    for (int c = 0; c < NC; ++c)
+      acc[c] = active ? ((MODE == 2) ? z[(size_t)c * ld + row] : r[(size_t)c * ld + row]) : 0.;
+    const size_t base = (size_t)off + lane;
+    for (int k0 = 0; k0 < w; k0 += 4) {
+      int cj[4];
+      double aj[4];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) acc[c] -= l * src[(size_t)c * ld + j];
+      for (int q = 0; q < 4; ++q) {
+        const bool in = k0 + q < w;
+        cj[q] = in ? ld_stream(V.col + base + (size_t)(k0 + q) * 32) : -1;
+        aj[q] = in ? ld_stream(lu + base + (size_t)(k0 + q) * 32) : 0.;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = cj[q];
+        const bool use = (MODE < 2) ? (j >= 0 && j < r0) : (j >= r1 && j < V.nRows);
+        if (use && active) {
+          const double *src = (MODE < 2 && j < n0) ? r : z;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) acc[c] -= aj[q] * src[(size_t)c * ld + j];
+        }
+      }
+    }
+    if (active) {
+      double d = 1.;
+      if (MODE != 0) d = lu[base + (size_t)V.diagK[row] * 32];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) z[(size_t)c * ld + row] = (MODE != 0) ? acc[c] / d : acc[c];
+    }
   }
-  const double d = LAST ? lu[slot_of(V.sliceOff, i, V.diagK[i])] : 1.;
-#pragma unroll
-  for (int c = 0; c < NC; ++c) z[(size_t)c * ld + i] = LAST ? acc[c] / d : acc[c];
-}
-
-// backward sweep of set b < nSets-1: z_i = (y_i - sum_{upper} u_ij z_j) / u_ii ; FIRST: y_i = r_i
-template <int NC, bool FIRST>
-__global__ void k_ilu_bwd(IluView V, const double *__restrict__ lu, const double *__restrict__ r, double *z,
-                          int ld, int r0, int r1) {
-  const int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= r1) return;
-  double acc[NC];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) acc[c] = FIRST ? r[(size_t)c * ld + i] : z[(size_t)c * ld + i];
-  const int len = V.rowLen[i];
-  for (int k = 0; k < len; ++k) {
-    const size_t sl = slot_of(V.sliceOff, i, k);
-    if (V.kind[sl] != 3) continue;
-    const double u = lu[sl];
-    const int j = V.col[sl];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) acc[c] -= u * z[(size_t)c * ld + j];
-  }
-  const double d = lu[slot_of(V.sliceOff, i, V.diagK[i])];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) z[(size_t)c * ld + i] = acc[c] / d;
 }
 
 // y[c][new] = x[c][old] (gather, dir 0) or y[c][old] = x[c][new] (scatter, dir 1) over owned rows
@@ -276,26 +280,26 @@ int ilu_apply(phb_solver *s, const double *r, double *z) {
   phb_ctx *c = s->ctx;
   const IluView V = view_of(D);
   const int ld = s->ld, nb = D.nBlocks, n0 = D.blockPtr[1];
-#define ILU_LAUNCH(K, NCV, FLAG, ...)                                                          \
-  do {                                                                                         \
-    if (FLAG) PHB_LAUNCH(c, (K<NCV, true>), grid, kThreads, 0, __VA_ARGS__);                   \
-    else PHB_LAUNCH(c, (K<NCV, false>), grid, kThreads, 0, __VA_ARGS__);                       \
-  } while (0)
+  auto launch = [&](int mode, int r0, int r1) {
+    const long long slices = ((r1 - 1) >> 5) - (r0 >> 5) + 1;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((slices * 32 + kThreads - 1) / kThreads,
+                                                                    (long long)c->numSMs * 8));
+#define SWEEP(NCV, M) PHB_LAUNCH(c, (k_ilu_sweep<NCV, M>), grid, kThreads, 0, V, D.lu.p, r, z, ld, r0, r1, n0)
+    if (s->nComp == 1) {
+      switch (mode) { case 0: SWEEP(1, 0); break; case 1: SWEEP(1, 1); break; case 2: SWEEP(1, 2); break; default: SWEEP(1, 3); }
+    } else {
+      switch (mode) { case 0: SWEEP(2, 0); break; case 1: SWEEP(2, 1); break; case 2: SWEEP(2, 2); break; default: SWEEP(2, 3); }
+    }
+#undef SWEEP
+  };
   for (int b = 1; b < nb; ++b) {
     const int r0 = D.blockPtr[b], r1 = D.blockPtr[b + 1];
-    if (r1 <= r0) continue;
-    const int grid = (r1 - r0 + kThreads - 1) / kThreads;
-    if (s->nComp == 1) ILU_LAUNCH(k_ilu_fwd, 1, b == nb - 1, V, D.lu.p, r, z, ld, r0, r1, n0);
-    else ILU_LAUNCH(k_ilu_fwd, 2, b == nb - 1, V, D.lu.p, r, z, ld, r0, r1, n0);
+    if (r1 > r0) launch(b == nb - 1 ? 1 : 0, r0, r1);
   }
   for (int b = std::max(0, nb - 2); b >= 0; --b) {
     const int r0 = D.blockPtr[b], r1 = D.blockPtr[b + 1];
-    if (r1 <= r0) continue;
-    const int grid = (r1 - r0 + kThreads - 1) / kThreads;
-    if (s->nComp == 1) ILU_LAUNCH(k_ilu_bwd, 1, b == 0, V, D.lu.p, r, z, ld, r0, r1);
-    else ILU_LAUNCH(k_ilu_bwd, 2, b == 0, V, D.lu.p, r, z, ld, r0, r1);
+    if (r1 > r0) launch(b == 0 ? 3 : 2, r0, r1);
   }
-#undef ILU_LAUNCH
   return PHB_OK;
 }
 
