@@ -879,14 +879,15 @@ int phb_solver_time_spmv(phb_solver *s, int reps, double *ms) {
 }
 
 // algorithmic bytes: SpMV 12 nnz + 4 (n+1) + 16 n per component;
-// BiCGStab iteration = 2 SpMV + 112 n per component (Jacobi folded: B_prec = 0)
+// BiCGStab iteration = 2 SpMV + 2 preconditioner applies + the fused vector passes
 int phb_solver_bytes(const phb_solver *s, double out[2]) {
   PHB_REQUIRE(s && out && s->pat, "phb_solver_bytes: no matrix bound");
   const double nnz = (double)s->pat->nnz, n = (double)s->pat->nRows, nc = s->nComp;
   out[0] = 12. * nnz + 4. * (n + 1.) + 16. * n * nc;
   // ILU(0) apply: L and U sweeps over the pattern once, 12 nnz + 8 (n+1) + 8 n + 32 n nc
   const double prec = s->precond == PHB_PC_ILU0 ? 12. * nnz + 8. * (n + 1.) + 8. * n + 32. * n * nc : 0.;
-  out[1] = 2. * out[0] + 2. * prec + 112. * n * nc;
+  // vector passes: fused update 64 n (80 n with a separate preconditioned image) + s-update 24 n, per component
+  out[1] = 2. * out[0] + 2. * prec + (s->precond == PHB_PC_ILU0 ? 104. : 88.) * n * nc;
   return PHB_OK;
 }
 
