@@ -329,6 +329,24 @@ def main():
         e2e_s = float(t.item())
     d2h_all = (2 * N + N + 2 * F + F + 2 * N) * 8
 
+    # ---- Seam 1 alone (single GPU): the reference-facing backend call with HOST CSR arrays, exactly what
+    # FiniteVolumeEquation<T>::solve hands to a SparseMatrixSolver: set(rowPtr,colInd,vals) + setRhs(-rhs_) + solve + x
+    seam1 = None
+    if world == 1:
+        from phase_b200.api import SparseMatrixSolver
+        rp, ci, va, rhs = fs.assembleP(dt).export(1)      # reference layout: ELL-5 padded, nb before diagonal
+        b = -rhs
+        s1 = SparseMatrixSolver(comm).setup(cfg)
+        s1.setup(dict(nullSpace="constant"))
+        s1.setRank(len(b)); s1.set(rp, ci, va); s1.setRhs(b); s1.solve()   # warm-up: pattern analysis, graph capture
+        t0 = time.perf_counter()
+        s1.setRank(len(b)); s1.set(rp, ci, va); s1.setRhs(b); s1.solve(); xs = s1.x()
+        t_s1 = time.perf_counter() - t0
+        seam1 = {"what": "pEqn_ (4M rows, 20M padded entries) through set(rowPtr,colInd,vals)+setRhs+solve+x with host arrays",
+                 "seconds_per_solve": t_s1, "iterations": s1.nIters(), "relres": s1.error(),
+                 "h2d_bytes": int(rp.nbytes + ci.nbytes + va.nbytes + b.nbytes), "d2h_bytes": int(xs.nbytes)}
+        s1.close()
+
     if rank != 0:
         fs.close(); grid.close(); comm.close()
         dist.destroy_process_group()
@@ -353,7 +371,7 @@ def main():
                          "note": "whole-solve GB/s = iters * bytes_per_iteration / solve time; see profiles/"},
             "e2e": {"value": world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_all,
                     "what": "host state (u, p, gradP cells+faces) copied in, FractionalStep.solve, state copied out, per step"},
-            "gpu_launches": int(launches), "clocks": clocks}
+            "e2e_seam1": seam1, "gpu_launches": int(launches), "clocks": clocks}
     if not args.no_cpu and world == 1:
         v, detail = cpu_reference_sample(nx, args.n, dt, iters_u, iters_p, precond=args.precond)
         import oracle as O

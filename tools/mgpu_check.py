@@ -72,9 +72,27 @@ def main():
     ep = np.linalg.norm((p[mine] - pm) - (po[gid[mine]] - po.mean())) / np.linalg.norm(po - po.mean())
     # ghosts must hold their owners' values after the last sendMessages(u)
     eg = rel(u[0][~mine], ofs.view("ux")[gid[~mine]]) if (~mine).any() else 0.0
-    ok = eu < 1e-6 and ep < 1e-6 and eg < 1e-6
-    print("rank %d/%d: cells %d owned %d  relL2 u %.2e p %.2e ghosts %.2e  itersP %d  div %.1e  %s" %
-          (rank, world, len(owner), int(mine.sum()), eu, ep, eg, st["itersP"], st["maxDivergence"],
+    # Seam 1 on a distributed system: the rank's rows with GLOBAL columns (reference IndexMap numbering),
+    # host arrays, halo lists from the local mesh
+    from phase_b200.api import SparseMatrixSolver
+    rp, ci, va, rhs = fs.assembleP(dt).export(1)
+    s1 = SparseMatrixSolver(comm).setup(dict(tolerance=1e-11, maxIters=50000, preconditioner=a.precond,
+                                             nullSpace="constant"))
+    s1.setHalo(gl)
+    s1.setRank(len(rhs)); s1.set(rp, ci, va); s1.setRhs(-rhs); s1.solve()
+    x1 = s1.x()
+    fs.pEqn.solver.setup(dict(tolerance=1e-11))
+    fs.p.fill(0.0)
+    fs.pEqn.solve(warmStart=False)
+    pd = fs.p.get("cells")[mine]
+    lrow = gl.i32("localRow")[mine]
+    t1 = torch.tensor([x1.sum(), float(len(x1)), pd.sum()], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t1)
+    xm, pm2 = (t1[0] / t1[1]).item(), (t1[2] / t1[1]).item()
+    es = np.linalg.norm((x1[lrow] - xm) - (pd - pm2)) / max(np.linalg.norm(pd - pm2), 1e-300)
+    ok = eu < 1e-6 and ep < 1e-6 and eg < 1e-6 and es < 1e-6
+    print("rank %d/%d: cells %d owned %d  relL2 u %.2e p %.2e ghosts %.2e seam1 %.2e  itersP %d  div %.1e  %s" %
+          (rank, world, len(owner), int(mine.sum()), eu, ep, eg, es, st["itersP"], st["maxDivergence"],
            "OK" if ok else "FAIL"), flush=True)
     t = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(t)
