@@ -168,7 +168,7 @@ def run_reference(args):
               "%.0f (uEqn) / %.0f (pEqn) iterations per solve (%s)" % (args.precond, cores, iu, ip, src))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, 1),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "detail": detail},
@@ -185,13 +185,17 @@ def block_layout(nprocs):
 
 
 def workload_config(args, nprocs):
-    return {"workload": "lid-driven cavity (rho=1, mu=0.1, lid u=1), %dx%d quads = %d cells per GPU, "
+    px, py = block_layout(nprocs)
+    strong = getattr(args, "scaling", "strong") == "strong"
+    gx, gy = (args.n, args.n) if strong else (args.n * px, args.n * py)
+    return {"workload": "lid-driven cavity (rho=1, mu=0.1, lid u=1), %dx%d quads = %d cells%s, "
                         "FractionalStep time step (the snapshot's PISO successor), dt = 0.5 h (maxCo 0.5), "
                         "BiCGStab + %s, tolerance %g on ||r||/||b||, warm start from the previous step"
-                        % (args.n, args.n, args.n * args.n, args.precond, args.tol),
-            "cells_per_gpu": args.n * args.n, "global_cells": args.n * args.n * nprocs,
+                        % (gx, gy, gx * gy, "" if strong or nprocs == 1 else " (%dx%d per GPU)" % (args.n, args.n),
+                           args.precond, args.tol),
+            "cells_per_gpu": gx * gy // nprocs, "global_cells": gx * gy,
             "partition": "none" if nprocs == 1 else "%dx%d blocks of %dx%d cells, one per GPU (global grid %dx%d)" % (
-                block_layout(nprocs) + (args.n, args.n, args.n * block_layout(nprocs)[0], args.n * block_layout(nprocs)[1])),
+                px, py, gx // px, gy // py, gx, gy),
             "l2": "inputs larger than L2 (matrix + vectors ~0.6 GB per solve vs 126 MB L2); no flush needed",
             "tolerance": args.tol, "max_iters": args.max_iters, "preconditioner": args.precond,
             "comm": "single GPU" if nprocs == 1 else (
@@ -210,6 +214,8 @@ def main():
     ap.add_argument("--max-iters", type=int, default=20000)
     ap.add_argument("--precond", default="ilu0", choices=["ilu0", "jacobi", "none"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = the same side x side problem split over the GPUs; weak = side x side cells per GPU")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="in-loop halo/all-reduce: NVLink peer-memory kernels (default) or NCCL calls")
     args = ap.parse_args()
@@ -233,11 +239,14 @@ def main():
         uid = box[0]
     comm = Communicator(local_rank, rank, world, uid)
     px, py = block_layout(world)
-    nx, ny = args.n * px, args.n * py
+    if args.scaling == "weak":
+        nx, ny, width, height = args.n * px, args.n * py, float(px), float(py)
+    else:
+        nx, ny, width, height = args.n, args.n, 1.0, 1.0
     if world == 1:
         grid = FiniteVolumeGrid2D.rectilinear(comm, nx, ny, 1.0, 1.0)
     else:
-        grid = FiniteVolumeGrid2D.rectilinear_block(comm, nx, ny, float(px), float(py), px, py)
+        grid = FiniteVolumeGrid2D.rectilinear_block(comm, nx, ny, width, height, px, py)
     if world > 1 and args.comm == "peer":
         def all_gather(obj):
             out = [None] * world
@@ -283,9 +292,10 @@ def main():
         ms = float(t.item())
     ms_per_step = ms / args.steps
     steps_per_s = 1e3 / ms_per_step
-    # whole-job aggregate: every rank advances its 4M-cell block one time step per step, so the job
-    # processes `world` 4M-cell time-steps per step (equals time-steps/s at N = 1)
-    value = steps_per_s * world
+    # strong scaling: the job advances ONE side x side problem, value = its time steps per second.
+    # weak scaling: every rank advances a side x side block, so the job processes `world` such
+    # block-steps per step (aggregate; equals time-steps/s at N = 1)
+    value = steps_per_s * (world if args.scaling == "weak" else 1)
 
     # ---- dominant kernel: the SpMV inside BiCGStab, timed alone on the resident pEqn matrix
     spmv_ms = fs.pEqn.solver.time_spmv(50)
@@ -354,9 +364,10 @@ def main():
     iters_u = float(np.mean([s["itersU"] for s in timed]))
     iters_p = float(np.mean([s["itersP"] for s in timed]))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
-            "value_definition": "4M-cell time-steps per second summed over GPUs = n_gpus x (time steps of the global problem per second)",
+            "value_definition": ("time steps per second of the %dx%d-cell problem (split over the GPUs)" % (nx, ny)) if args.scaling == "strong"
+            else "4M-cell block time-steps per second summed over GPUs = n_gpus x (time steps of the global problem per second)",
             "global_time_steps_per_s": steps_per_s,
             "cell_updates_per_s": steps_per_s * sizes["nLocal"] * world,
             "ms_per_bicgstab_iteration": ms_per_step / max(1.0, float(np.mean([s["itersP"] + s["itersU"] for s in timed]))),
@@ -369,7 +380,7 @@ def main():
                          "algorithmic_bytes_per_launch": b_spmv, "ms_per_launch": spmv_ms, "peak_source": peak_src},
             "bicgstab": {"bytes_per_iteration": b_iter,
                          "note": "whole-solve GB/s = iters * bytes_per_iteration / solve time; see profiles/"},
-            "e2e": {"value": world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_all,
+            "e2e": {"value": (world if args.scaling == "weak" else 1) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_all,
                     "what": "host state (u, p, gradP cells+faces) copied in, FractionalStep.solve, state copied out, per step"},
             "e2e_seam1": seam1, "gpu_launches": int(launches), "clocks": clocks}
     if not args.no_cpu and world == 1:
