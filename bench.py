@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = the same side x side problem split over the GPUs; weak = side x side cells per GPU")
+    ap.add_argument("--guess-order", type=int, default=1, help="pEqn_ initial guess: 0 previous p, 1 extrapolated")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="in-loop halo/all-reduce: NVLink peer-memory kernels (default) or NCCL calls")
     args = ap.parse_args()
@@ -255,6 +256,7 @@ def main():
         comm.enable_peer_memory(grid, all_gather)
     cfg = dict(solver="BICGSTAB", maxIters=args.max_iters, tolerance=args.tol, preconditioner=args.precond)
     fs = lid_driven_cavity(grid, 1.0, 0.1, solver=cfg)
+    fs.setup(guessOrder=args.guess_order)
     dt = 0.5 / nx
     stream = torch.cuda.ExternalStream(comm.stream())
     sizes = grid.sizes()

@@ -466,6 +466,11 @@ class FractionalStep:
         self.uEqn.solver = SparseMatrixSolver(grid.comm, handle=C.c_void_p(self.L.phb_fs_solver(h, b"uEqn")))
         self.pEqn.solver = SparseMatrixSolver(grid.comm, handle=C.c_void_p(self.L.phb_fs_solver(h, b"pEqn")))
 
+    def setup(self, **keys):
+        for k, v in keys.items():
+            check(self.L.phb_fs_setup(self.h, k.encode(), float(v)))
+        return self
+
     def initialize(self):
         check(self.L.phb_fs_initialize(self.h))
 

@@ -3,6 +3,7 @@
 // BiCGStab solver so that a whole time step runs without host<->device field
 // traffic.  Fields, equations and solvers are exposed so callers can drive the
 // pieces themselves (the C++ mirror in include/phase/ does).
+#include <algorithm>
 #include <cmath>
 
 #include "comm.cuh"
@@ -18,7 +19,22 @@ struct phb_fracstep {
   phb::DevBuf<double> scratch, partials, out;
   phb::DevBuf<unsigned> ticket;
   bool warmStart = true;
+  // initial guess of pEqn_: 0 = previous p (plain warm start), 1 = linear extrapolation 2 p^n - p^(n-1)
+  int guessOrder = 1;
+  phb::DevBuf<double> pPrev;  // p^(n-1), owned cells
+  int nStepsDone = 0;
 };
+
+namespace {
+// x = 2 x - xPrev ; xPrev = old x        (owned cells of a scalar field)
+__global__ void k_extrapolate(int n, double *__restrict__ x, double *__restrict__ xPrev, int apply) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double cur = x[i], old = xPrev[i];
+    xPrev[i] = cur;
+    if (apply) x[i] = 2. * cur - old;
+  }
+}
+}  // namespace
 
 extern "C" {
 
@@ -116,7 +132,15 @@ int phb_fs_step(phb_fracstep *fs, double dt, double stats[6]) {
   PHB_CHECK(phb::field_interpolate_faces(fs->u));
   // ---- solvePEqn (:96-107)
   PHB_CHECK(phb_fs_assemble_p(fs, dt));
+  if (fs->warmStart && fs->guessOrder == 1) {
+    // the reference passes no guess at all; p^n is the natural one, 2 p^n - p^(n-1) a better one
+    const int n = fs->m->nLocal;
+    PHB_CHECK(fs->pPrev.alloc((size_t)n));
+    const int g = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)c->numSMs * 8));
+    PHB_LAUNCH(c, k_extrapolate, g, 256, 0, n, fs->p->cells.p, fs->pPrev.p, fs->nStepsDone >= 2 ? 1 : 0);
+  }
   PHB_CHECK(phb_eqn_solve(fs->pEqn, fs->pSolver, fs->p, fs->warmStart, &itP, &rrP));
+  fs->nStepsDone++;
   PHB_CHECK(phb::field_send_messages(fs->p));
   PHB_CHECK(phb::field_set_boundary_faces(fs->p));
   PHB_CHECK(phb::field_gradient(fs->p, fs->gradP));
@@ -133,6 +157,15 @@ int phb_fs_step(phb_fracstep *fs, double dt, double stats[6]) {
     stats[0] = itU; stats[1] = itP; stats[2] = rrU; stats[3] = rrP;
     stats[4] = c->pinned[64]; stats[5] = c->pinned[65];
   }
+  return PHB_OK;
+}
+
+// driver options: "warmStart" 0/1 (guess = previous field values), "guessOrder" 0/1 (pEqn_ guess extrapolation)
+int phb_fs_setup(phb_fracstep *fs, const char *key, double value) {
+  PHB_REQUIRE(fs && key, "phb_fs_setup: NULL argument");
+  if (!strcmp(key, "warmStart")) fs->warmStart = value != 0.;
+  else if (!strcmp(key, "guessOrder")) fs->guessOrder = (int)value;
+  else PHB_REQUIRE(false, "phb_fs_setup: unknown key \"%s\"", key);
   return PHB_OK;
 }
 
