@@ -28,7 +28,7 @@
 
 namespace phase {
 struct Term {
-  enum Kind { DDT, DIV, DIVE, LAPLACIAN, SRC, SRC_DIV } kind;
+  enum Kind { DDT, DIV, DIVE, LAPLACIAN, SRC, SRC_DIV, CICSAM_DIV } kind;
   double sign;
   phb_field *phi, *u, *aux;  // phi: transported/solved field, u: advecting field, aux: rho / gamma field
   double c0, c1, c2;         // rho or gamma constant, dt, theta
@@ -229,6 +229,7 @@ protected:
         case phase::Term::LAPLACIAN: rc = phb_assemble_laplacian(e_, t.c0, t.aux, t.phi, t.c2, t.sign); break;
         case phase::Term::SRC: rc = phb_assemble_src(e_, t.phi, t.sign); break;
         case phase::Term::SRC_DIV: rc = phb_assemble_src_div(e_, t.u, t.sign); break;
+        case phase::Term::CICSAM_DIV: rc = phb_assemble_cicsam_div(e_, t.u, t.phi, t.aux, t.c2, t.sign); break;
         }
         phase::check(rc, "FiniteVolumeEquation<T>", "operator=");
       }

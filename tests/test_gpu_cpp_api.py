@@ -44,3 +44,16 @@ def test_fractional_step_module_matches_oracle(exes, tmp_path):
     p, po = got[2], ofs.view("p").copy()
     assert rel_l2(p - p.mean(), po - po.mean()) < 1e-6
     assert "FiniteVolumeEquation pEqn: Krylov iterations =" in r.stdout
+
+
+def test_phase_piso_legacy_case(exes, tmp_path):
+    """Config 1: the shipped cavity case in its legacy PISO format (timeStep 10, relaxation 0.8 / 0.2)."""
+    out = tmp_path / "piso.bin"
+    r = subprocess.run([exes["phase_piso"], os.path.join(ROOT, "examples", "LidDrivenCavityPiso", "case"), "100", str(out)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    a = np.fromfile(out, dtype=np.float64)
+    n = 100 * 100
+    ux = a[:n].reshape(100, 100)
+    assert np.isfinite(a).all() and ux[98, 50] > 0.4 and ux[30, 50] < 0.0       # primary vortex under the lid
+    assert "final mass imbalance" in r.stdout
