@@ -70,7 +70,7 @@ __device__ __forceinline__ void slice_dot_any(const int *__restrict__ col, const
 
 // EPI 0: y = A x
 // EPI 1: y = A x, sigma = (w . y)                       [v = A p, (rhat . v)]
-// EPI 2: y = A x, ts,tt,rt = (y.w),(y.y),(w2.y)          [t = A M^-1 s; w = s, w2 = rhat]
+// EPI 2: y = A x, ts,tt,rs,rt,ss = (y.w),(y.y),(w2.w),(w2.y),(w.w)   [t = A M^-1 s; w = s, w2 = rhat]
 // EPI 3: y = b - A x, w2 = y, rr = rho0 = (y . y), bb = (b . b)   [initial residual]
 template <int NC, int EPI>
 __global__ void __launch_bounds__(kThreads)
@@ -84,7 +84,7 @@ k_spmv(SellView A, const double *__restrict__ vals, const double *__restrict__ x
   const int warpsPerBlock = blockDim.x >> 5;
   const int warp = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
   const int nWarps = gridDim.x * warpsPerBlock;
-  double s0 = 0., s1 = 0., s2 = 0.;
+  double s0 = 0., s1 = 0., s2 = 0., s3 = 0., s4 = 0.;
   for (int slice = warp; slice < A.nSlices; slice += nWarps) {
     const int off = __ldg(A.sliceOff + slice);
     const int wdt = (__ldg(A.sliceOff + slice + 1) - off) >> 5;
@@ -108,9 +108,12 @@ k_spmv(SellView A, const double *__restrict__ vals, const double *__restrict__ x
           y[idx] = acc[i];
           if (EPI == 1) s0 = fma(w[idx], acc[i], s0);
           if (EPI == 2) {
-            s0 = fma(acc[i], w[idx], s0);
+            const double sv = w[idx], rh = w2[idx];
+            s0 = fma(acc[i], sv, s0);
             s1 = fma(acc[i], acc[i], s1);
-            s2 = fma(w2[idx], acc[i], s2);
+            s2 = fma(rh, sv, s2);
+            s3 = fma(rh, acc[i], s3);
+            s4 = fma(sv, sv, s4);
           }
         }
       }
@@ -120,8 +123,8 @@ k_spmv(SellView A, const double *__restrict__ vals, const double *__restrict__ x
     double v[1] = {s0};
     grid_reduce<1>(v, partials, ticket, &S->sigma);
   } else if (EPI == 2) {
-    double v[3] = {s0, s1, s2};
-    if (grid_reduce<3>(v, partials, ticket, &S->ts) && localFinish) krylov_finish(S, cur);
+    double v[5] = {s0, s1, s2, s3, s4};
+    if (grid_reduce<5>(v, partials, ticket, &S->ts) && localFinish) krylov_finish(S, cur);
   } else if (EPI == 3) {
     double v[2] = {s0, s1};
     grid_reduce<2>(v, partials, ticket, &S->rr);  // rr, bb adjacent
@@ -134,7 +137,7 @@ __global__ void k_init_scalars(KrylovSums *S, double tol) {
   S->rho[0] = S->rr;
   S->rho[1] = 1.;
   S->sigma = 1.;
-  S->ts = S->tt = S->rt = S->rs = S->ss = 0.;
+  S->ts = S->tt = S->rs = S->rt = S->ss = 0.;
   S->alpha = S->omega = S->beta = 0.;
   S->thresh = tol * tol * S->bb;
   S->iters = 0.;
@@ -176,27 +179,20 @@ __global__ void k_final_x(int n, int ld, double *__restrict__ x, const double *_
   }
 }
 
-// s = r - alpha v, with the two sums of R2 that only need s: rs = (rhat . s), ss = (s . s)
+// s = r - alpha v
 template <int NC>
 __global__ void __launch_bounds__(kThreads)
 k_update_s(int n, int ld, const double *__restrict__ r, const double *__restrict__ v,
-           double *__restrict__ s, const double *__restrict__ rhat, KrylovSums *S, int cur, int maxIters,
-           double *partials, unsigned *ticket) {
+           double *__restrict__ s, const KrylovSums *S, int cur, int maxIters) {
   if (krylov_done(S, maxIters)) return;
   const double alpha = S->rho[cur] / S->sigma;
-  double s0 = 0., s1 = 0.;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const size_t k = (size_t)c * ld + i;
-      const double sk = r[k] - alpha * v[k];
-      s[k] = sk;
-      s0 = fma(rhat[k], sk, s0);
-      s1 = fma(sk, sk, s1);
+      s[k] = r[k] - alpha * v[k];
     }
   }
-  double vv[2] = {s0, s1};
-  grid_reduce<2>(vv, partials, ticket, &S->rs);
 }
 
 // NCCL path: publish the iteration's scalars after the all-reduce of R2
@@ -373,15 +369,12 @@ int enqueue_iteration(phb_solver *s, const double *A, int cur) {
   launch_spmv<1>(s, A, ph, s->v.p, s->rhat.p, nullptr);   // v = A ph, R1: sigma = (rhat . v)
   PHB_CHECK(reduce_sums(s, 0, &s->sums.p->sigma, 1, true, 0, cur));
   if (s->nComp == 1)
-    PHB_LAUNCH(c, k_update_s<1>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->rhat.p, s->sums.p, cur,
-               s->maxIters, s->partials.p, s->ticket.p);
+    PHB_LAUNCH(c, k_update_s<1>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->sums.p, cur, s->maxIters);
   else
-    PHB_LAUNCH(c, k_update_s<2>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->rhat.p, s->sums.p, cur,
-               s->maxIters, s->partials.p, s->ticket.p);
+    PHB_LAUNCH(c, k_update_s<2>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->sums.p, cur, s->maxIters);
   if (ilu) PHB_CHECK(ilu_apply(s, s->s.p, sh));          // sh = M^-1 s
   PHB_CHECK(halo_exchange(s, sh, true));
-  // t = A sh, R2: (t.s), (t.t), (rhat.t) here, (rhat.s), (s.s) from the s-update; single GPU: the last CTA
-  // finishes the iteration
+  // t = A sh, R2: (t.s), (t.t), (rhat.s), (rhat.t), (s.s); single GPU: the last CTA finishes the iteration
   launch_spmv<2>(s, A, sh, s->t.p, s->s.p, s->rhat.p, cur, multi ? 0 : 1);
   if (multi) {
     if (use_peer(s)) {  // the all-reduce kernel also finishes the iteration

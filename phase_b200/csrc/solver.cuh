@@ -4,13 +4,13 @@
 
 // device-resident Krylov scalars.  One BiCGStab iteration needs TWO reductions:
 //   R1: sigma = (rhat . v)                                  after v = A M^-1 p
-//   R2: ts, tt, rt = (t.s), (t.t), (rhat.t) after t = A M^-1 s; rs, ss = (rhat.s), (s.s) from the s-update
+//   R2: ts, tt, rs, rt, ss = (t.s), (t.t), (rhat.s), (rhat.t), (s.s)   after t = A M^-1 s
 // from which omega = ts/tt, rho' = rs - omega rt and ||r'||^2 = ss - 2 omega ts + omega^2 tt
 // follow without a third reduction ("finish" step, krylov_finish()).
 struct KrylovSums {
   double rho[2];   // (rhat . r), parity-indexed by iteration
   double sigma;    // R1
-  double ts, tt, rt, rs, ss;  // R2 (contiguous: one all-reduce of 5 doubles); rs, ss come from the s-update
+  double ts, tt, rs, rt, ss;  // R2 (contiguous: one all-reduce of 5 doubles)
   double rr;       // ||r||^2 (recurrence), bb follows (contiguous pair for the initial all-reduce)
   double bb;       // ||b||^2
   double thresh;   // tol^2 * bb
