@@ -188,6 +188,16 @@ def workload_config(args, nprocs):
     px, py = block_layout(nprocs)
     strong = getattr(args, "scaling", "strong") == "strong"
     gx, gy = (args.n, args.n) if strong else (args.n * px, args.n * py)
+    if getattr(args, "mesh", "quad") == "tri":
+        import math
+        tn = int(round(args.n / math.sqrt(2.0)))
+        return {"workload": "lid-driven cavity (rho=1, mu=0.1, lid u=1), unstructured triangles: %dx%d lattice split along "
+                            "alternating diagonals = %d cells, FractionalStep time step, dt = 0.5 h, BiCGStab + %s, tolerance %g, "
+                            "warm start" % (tn, tn, 2 * tn * tn, args.precond, args.tol),
+                "cells_per_gpu": 2 * tn * tn // nprocs, "global_cells": 2 * tn * tn,
+                "partition": "none" if nprocs == 1 else "RCB, %d parts" % nprocs,
+                "l2": "inputs larger than L2; no flush needed", "tolerance": args.tol, "max_iters": args.max_iters,
+                "preconditioner": args.precond, "comm": "single GPU" if nprocs == 1 else args.comm}
     return {"workload": "lid-driven cavity (rho=1, mu=0.1, lid u=1), %dx%d quads = %d cells%s, "
                         "FractionalStep time step (the snapshot's PISO successor), dt = 0.5 h (maxCo 0.5), "
                         "BiCGStab + %s, tolerance %g on ||r||/||b||, warm start from the previous step"
@@ -214,6 +224,9 @@ def main():
     ap.add_argument("--max-iters", type=int, default=20000)
     ap.add_argument("--precond", default="ilu0", choices=["ilu0", "jacobi", "none"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mesh", default="quad", choices=["quad", "tri"],
+                    help="quad: side x side quads; tri: the same cell count as triangles (each quad of a "
+                         "side/sqrt(2) lattice split along alternating diagonals, unstructured connectivity)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = the same side x side problem split over the GPUs; weak = side x side cells per GPU")
     ap.add_argument("--guess-order", type=int, default=1, help="pEqn_ initial guess: 0 previous p, 1 extrapolated")
@@ -244,7 +257,18 @@ def main():
         nx, ny, width, height = args.n * px, args.n * py, float(px), float(py)
     else:
         nx, ny, width, height = args.n, args.n, 1.0, 1.0
-    if world == 1:
+    if args.mesh == "tri":
+        import math
+        tn = int(round(args.n / math.sqrt(2.0)))            # 2 tn^2 triangles ~ side^2 cells
+        if world == 1:
+            grid = FiniteVolumeGrid2D.triangulated(comm, tn, tn, 1.0, 1.0)
+        else:                                                # generic path: global mesh on the host, RCB, local mesh
+            hostc = Communicator(Communicator.HOST_ONLY)
+            gg = FiniteVolumeGrid2D.triangulated(hostc, tn, tn, 1.0, 1.0)
+            grid = gg.local(gg.partition_rcb(world), comm)
+            gg.close()
+        nx = ny = tn
+    elif world == 1:
         grid = FiniteVolumeGrid2D.rectilinear(comm, nx, ny, 1.0, 1.0)
     else:
         grid = FiniteVolumeGrid2D.rectilinear_block(comm, nx, ny, width, height, px, py)
@@ -257,7 +281,11 @@ def main():
     cfg = dict(solver="BICGSTAB", maxIters=args.max_iters, tolerance=args.tol, preconditioner=args.precond)
     fs = lid_driven_cavity(grid, 1.0, 0.1, solver=cfg)
     fs.setup(guessOrder=args.guess_order)
-    dt = 0.5 / nx
+    dt = 0.5 / nx                                            # maxCo 0.5 with the unit lid speed, h = 1/nx
+    if args.scaling == "weak" and args.mesh == "quad":
+        dt = 0.5 / args.n                                     # same cell size h = 1/side in every block
+    if args.mesh == "tri":
+        dt = 0.25 / nx                                        # triangles: half the lattice spacing
     stream = torch.cuda.ExternalStream(comm.stream())
     sizes = grid.sizes()
     N, F = sizes["nCells"], sizes["nFaces"]
@@ -386,7 +414,7 @@ def main():
                     "what": "host state (u, p, gradP cells+faces) copied in, FractionalStep.solve, state copied out, per step"},
             "e2e_seam1": seam1, "gpu_launches": int(launches), "clocks": clocks}
     if not args.no_cpu and world == 1:
-        v, detail = cpu_reference_sample(nx, args.n, dt, iters_u, iters_p, precond=args.precond)
+        v, detail = cpu_reference_sample(args.n, args.n, 0.5 / args.n, iters_u, iters_p, precond=args.precond)
         import oracle as O
         cores = O.lib().or_num_threads()
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
