@@ -209,8 +209,10 @@ def workload_config(args, nprocs):
             "l2": "inputs larger than L2 (matrix + vectors ~0.6 GB per solve vs 126 MB L2); no flush needed",
             "tolerance": args.tol, "max_iters": args.max_iters, "preconditioner": args.precond,
             "comm": "single GPU" if nprocs == 1 else (
-                "NVLink peer-memory kernels (halo + all-reduce fused into the Krylov loop), NCCL outside the loop"
-                if args.comm == "peer" else "NCCL send/recv + all-reduce")}
+                "NVLink peer memory: halo push/wait and the sigma all-reduce ride inside the compute kernels, one small "
+                "kernel for the 5-sum all-reduce; NCCL outside the loop" if args.comm == "peer" else
+                "NVLink peer memory, separate halo / all-reduce kernels" if args.comm == "peer-unfused" else
+                "NCCL send/recv + all-reduce")}
 
 
 def main():
@@ -230,7 +232,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = the same side x side problem split over the GPUs; weak = side x side cells per GPU")
     ap.add_argument("--guess-order", type=int, default=1, help="pEqn_ initial guess: 0 previous p, 1 extrapolated")
-    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--comm", default="peer", choices=["peer", "peer-unfused", "nccl"],
                     help="in-loop halo/all-reduce: NVLink peer-memory kernels (default) or NCCL calls")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -272,13 +274,14 @@ def main():
         grid = FiniteVolumeGrid2D.rectilinear(comm, nx, ny, 1.0, 1.0)
     else:
         grid = FiniteVolumeGrid2D.rectilinear_block(comm, nx, ny, width, height, px, py)
-    if world > 1 and args.comm == "peer":
+    if world > 1 and args.comm.startswith("peer"):
         def all_gather(obj):
             out = [None] * world
             dist.all_gather_object(out, obj)
             return out
         comm.enable_peer_memory(grid, all_gather)
-    cfg = dict(solver="BICGSTAB", maxIters=args.max_iters, tolerance=args.tol, preconditioner=args.precond)
+    cfg = dict(solver="BICGSTAB", maxIters=args.max_iters, tolerance=args.tol, preconditioner=args.precond,
+               peerFusion=0 if args.comm == "peer-unfused" else 1)
     fs = lid_driven_cavity(grid, 1.0, 0.1, solver=cfg)
     fs.setup(guessOrder=args.guess_order)
     dt = 0.5 / nx                                            # maxCo 0.5 with the unit lid speed, h = 1/nx

@@ -95,7 +95,7 @@ __global__ void k_ilu_factor(IluView V, double *__restrict__ lu, int r0, int r1)
 template <int NC, int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_ilu_sweep(IluView V, const double *__restrict__ lu, const double *__restrict__ r, double *z, int ld, int r0,
-            int r1, int n0) {
+            int r1, int n0, PeerFuse F, unsigned *ticket) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int s0 = r0 >> 5, s1 = (r1 - 1) >> 5;
   for (int slice = s0 + blockIdx.x * wpb + (threadIdx.x >> 5); slice <= s1; slice += gridDim.x * wpb) {
@@ -134,6 +134,9 @@ k_ilu_sweep(IluView V, const double *__restrict__ lu, const double *__restrict__
 #pragma unroll
       for (int c = 0; c < NC; ++c) z[(size_t)c * ld + row] = (MODE != 0) ? acc[c] / d : acc[c];
     }
+  }
+  if (F.on && F.pushHalo) {  // final launch of an apply: the last CTA ships z's boundary values to the peers
+    if (last_block(ticket)) halo_push_block(F, z, NC, ld);
   }
 }
 
@@ -275,16 +278,19 @@ int ilu_factor(phb_solver *s, const double *vals) {
 }
 
 // z = U^-1 L^-1 r  (vectors in the permuted numbering, leading dimension ld)
-int ilu_apply(phb_solver *s, const double *r, double *z) {
+int ilu_apply(phb_solver *s, const double *r, double *z, const PeerFuse *pushHalo) {
   IluData &D = s->ilu;
   phb_ctx *c = s->ctx;
   const IluView V = view_of(D);
   const int ld = s->ld, nb = D.nBlocks, n0 = D.blockPtr[1];
+  // the launch that completes z (set 0 of the backward sweep, or the only set) carries the halo push
+  const int finalMode = 3;
   auto launch = [&](int mode, int r0, int r1) {
+    const PeerFuse F = (pushHalo && mode == finalMode) ? *pushHalo : PeerFuse();
     const long long slices = ((r1 - 1) >> 5) - (r0 >> 5) + 1;
     const int grid = (int)std::max<long long>(1, std::min<long long>((slices * 32 + kThreads - 1) / kThreads,
                                                                     (long long)c->numSMs * 8));
-#define SWEEP(NCV, M) PHB_LAUNCH(c, (k_ilu_sweep<NCV, M>), grid, kThreads, 0, V, D.lu.p, r, z, ld, r0, r1, n0)
+#define SWEEP(NCV, M) PHB_LAUNCH(c, (k_ilu_sweep<NCV, M>), grid, kThreads, 0, V, D.lu.p, r, z, ld, r0, r1, n0, F, s->ticket.p)
     if (s->nComp == 1) {
       switch (mode) { case 0: SWEEP(1, 0); break; case 1: SWEEP(1, 1); break; case 2: SWEEP(1, 2); break; default: SWEEP(1, 3); }
     } else {

@@ -33,7 +33,8 @@ constexpr int kMaxBlockWarps = 32;
 //   warp shuffle -> shared -> one partial per block -> the last block to arrive
 //   (ticket counter) adds the partials in fixed order and writes out[0..NS).
 // `ticket` must be zero on entry and is reset for the next launch.
-// Returns true in exactly one thread (the one that wrote `out`), after the write.
+// Returns true in ALL lanes of warp 0 of the last CTA (warp-uniform) after lane 0 wrote `out`;
+// scalar follow-ups must be guarded with lane == 0.
 template <int NS, bool MAX = false>
 __device__ __forceinline__ bool grid_reduce(double (&v)[NS], double *partials, unsigned *ticket,
                                             double *out) {
@@ -86,10 +87,9 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], double *partials, u
       w = MAX ? warp_max(w) : warp_sum(w);
       if (lane == 0) out[j] = w;
     }
-    if (lane == 0) {
-      *ticket = 0u;
-      return true;
-    }
+    if (lane == 0) *ticket = 0u;
+    __syncwarp();
+    return true;
   }
   return false;
 }

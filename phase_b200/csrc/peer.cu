@@ -11,37 +11,11 @@
 //   * spins on its own flags until the peers' contributions have landed.
 // All ranks sum the contributions in rank order, so the reduced values (and hence
 // every convergence decision) are bitwise identical on all ranks.
-#include "comm.cuh"
+#include "peerdev.cuh"
 #include "solver.cuh"
 
 namespace phb {
 namespace {
-
-struct RedSlot { double v[6]; unsigned long long epoch, pad; };  // 64 B
-struct PeerView {
-  char *arena;
-  char *peer[kMaxPeers];
-  int rank, nProcs;
-};
-
-__device__ __forceinline__ RedSlot *red_slot(char *arena, int ch, int src) {
-  return reinterpret_cast<RedSlot *>(arena) + (size_t)ch * kMaxPeers + src;
-}
-__device__ __forceinline__ unsigned long long *halo_flag(char *arena, int ch, int src) {
-  return reinterpret_cast<unsigned long long *>(arena + kPeerRedChannels * kMaxPeers * sizeof(RedSlot)) +
-         (size_t)ch * kMaxPeers + src;
-}
-__device__ __forceinline__ unsigned long long *local_epoch(char *arena, int idx) {
-  return reinterpret_cast<unsigned long long *>(arena + 12288) + idx;
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 __device__ __forceinline__ bool done_test(const KrylovSums *S, int maxIters) {
   return !(S->rr > S->thresh) || S->iters >= (double)maxIters;
@@ -116,7 +90,9 @@ k_peer_halo(PeerView pv, int ch, PeerHalo h, const double *x, size_t vecOff, int
   __syncthreads();
 }
 
-PeerView view_of(const phb_ctx *c) {
+}  // namespace
+
+PeerView peer_view(const phb_ctx *c) {
   PeerView v;
   v.arena = c->peer.arena;
   for (int q = 0; q < kMaxPeers; ++q) v.peer[q] = c->peer.peerArena[q];
@@ -124,8 +100,6 @@ PeerView view_of(const phb_ctx *c) {
   v.nProcs = c->nProcs;
   return v;
 }
-
-}  // namespace
 
 int peer_arena_create(phb_ctx *c, long long maxCols, int maxRegions, void *handle64) {
   PHB_REQUIRE(c && handle64 && maxCols > 0 && maxRegions > 0, "phb_ctx_peer_arena_create: bad argument");
@@ -187,7 +161,7 @@ bool peer_owns(const phb_ctx *c, const void *p) {
 
 int peer_allreduce(phb_ctx *c, int ch, double *vals, int nvals, void *S, int maxIters, int finishIter, int cur) {
   PHB_REQUIRE(ch >= 0 && ch < kPeerRedChannels, "peer_allreduce: channel %d out of range", ch);
-  PHB_LAUNCH(c, k_peer_allreduce, 1, 32, 0, view_of(c), ch, vals, nvals, (KrylovSums *)S, maxIters, finishIter, cur);
+  PHB_LAUNCH(c, k_peer_allreduce, 1, 32, 0, peer_view(c), ch, vals, nvals, (KrylovSums *)S, maxIters, finishIter, cur);
   return PHB_OK;
 }
 
@@ -195,7 +169,7 @@ int peer_halo(phb_ctx *c, int ch, const PeerHalo &h, double *x, int nComp, int l
   PHB_REQUIRE(ch >= 0 && ch < kPeerHaloChannels, "peer_halo: channel %d out of range", ch);
   PHB_REQUIRE(peer_owns(c, x), "peer_halo: vector is not inside the peer arena");
   const size_t vecOff = (size_t)((char *)x - c->peer.arena);
-  PHB_LAUNCH(c, k_peer_halo, 1, 1024, 0, view_of(c), ch, h, x, vecOff, nComp, ld, (KrylovSums *)S, maxIters);
+  PHB_LAUNCH(c, k_peer_halo, 1, 1024, 0, peer_view(c), ch, h, x, vecOff, nComp, ld, (KrylovSums *)S, maxIters);
   return PHB_OK;
 }
 

@@ -15,6 +15,7 @@
 
 #include "comm.cuh"
 #include "kernels.cuh"
+#include "peerdev.cuh"
 #include "solver.cuh"
 
 using namespace phb;
@@ -76,9 +77,10 @@ template <int NC, int EPI>
 __global__ void __launch_bounds__(kThreads)
 k_spmv(SellView A, const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
        int ld, const double *__restrict__ w, double *w2, KrylovSums *S, int maxIters,
-       double *partials, unsigned *ticket, int cur, int localFinish) {
+       double *partials, unsigned *ticket, int cur, int localFinish, PeerFuse F) {
   if (EPI == 1 || EPI == 2) {
     if (krylov_done(S, maxIters)) return;
+    if (F.on && F.waitHalo) halo_wait_block(F);  // the peers' ghost values of x have landed
   }
   const int lane = threadIdx.x & 31;
   const int warpsPerBlock = blockDim.x >> 5;
@@ -121,10 +123,11 @@ k_spmv(SellView A, const double *__restrict__ vals, const double *__restrict__ x
   }
   if (EPI == 1) {
     double v[1] = {s0};
-    grid_reduce<1>(v, partials, ticket, &S->sigma);
+    const bool fin = grid_reduce<1>(v, partials, ticket, &S->sigma);
+    if (fin && F.on && F.pushRed) reduce_push_warp(F.pv, F.redCh, &S->sigma, 1);  // my partial -> every peer
   } else if (EPI == 2) {
     double v[5] = {s0, s1, s2, s3, s4};
-    if (grid_reduce<5>(v, partials, ticket, &S->ts) && localFinish) krylov_finish(S, cur);
+    if (grid_reduce<5>(v, partials, ticket, &S->ts) && localFinish && lane == 0) krylov_finish(S, cur);
   } else if (EPI == 3) {
     double v[2] = {s0, s1};
     grid_reduce<2>(v, partials, ticket, &S->rr);  // rr, bb adjacent
@@ -150,7 +153,8 @@ template <int NC, bool PRECOND>
 __global__ void __launch_bounds__(kThreads)
 k_update_fused(int n, int ld, double *__restrict__ x, double *__restrict__ r, double *__restrict__ p,
                const double *ph, const double *sh, const double *__restrict__ s,
-               const double *__restrict__ t, const double *__restrict__ v, const KrylovSums *S, int maxIters) {
+               const double *__restrict__ t, const double *__restrict__ v, const KrylovSums *S, int maxIters,
+               PeerFuse F, unsigned *ticket) {
   if (krylov_done(S, maxIters)) return;
   const double alpha = S->alpha, omega = S->omega, beta = S->beta;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -163,6 +167,9 @@ k_update_fused(int n, int ld, double *__restrict__ x, double *__restrict__ r, do
       r[k] = rk;
       p[k] = rk + beta * (pk - omega * v[k]);
     }
+  }
+  if (F.on && F.pushHalo) {  // the last CTA ships the boundary values of the new p to the peers
+    if (last_block(ticket)) halo_push_block(F, p, NC, ld);
   }
 }
 // x += alpha ph + omega sh of the LAST completed iteration (the loop exits before the next fused update)
@@ -183,15 +190,27 @@ __global__ void k_final_x(int n, int ld, double *__restrict__ x, const double *_
 template <int NC>
 __global__ void __launch_bounds__(kThreads)
 k_update_s(int n, int ld, const double *__restrict__ r, const double *__restrict__ v,
-           double *__restrict__ s, const KrylovSums *S, int cur, int maxIters) {
+           double *__restrict__ s, KrylovSums *S, int cur, int maxIters, PeerFuse F, unsigned *ticket) {
   if (krylov_done(S, maxIters)) return;
-  const double alpha = S->rho[cur] / S->sigma;
+  double sigma;
+  if (F.on && F.waitRed) {  // R1 across the GPUs: sum the peers' partial (rhat . v) in rank order
+    double g[1];
+    reduce_wait_block<1>(F.pv, F.redCh, g);
+    sigma = g[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) S->sigma = sigma;  // for krylov_finish (no reader in this kernel)
+  } else {
+    sigma = S->sigma;
+  }
+  const double alpha = S->rho[cur] / sigma;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const size_t k = (size_t)c * ld + i;
       s[k] = r[k] - alpha * v[k];
     }
+  }
+  if (F.on && F.pushHalo) {
+    if (last_block(ticket)) halo_push_block(F, s, NC, ld);
   }
 }
 
@@ -296,16 +315,16 @@ int spmv_grid(const phb_ctx *c, const SellPattern *P) {
 
 template <int EPI>
 void launch_spmv(phb_solver *s, const double *vals, const double *x, double *y, const double *w, double *w2,
-                 int cur = 0, int localFinish = 0) {
+                 int cur = 0, int localFinish = 0, const PeerFuse &F = PeerFuse()) {
   const SellPattern *P = s->runPat ? s->runPat : s->pat;
   const SellView A = view_of(P);
   const int grid = spmv_grid(s->ctx, P);
   if (s->nComp == 1)
     PHB_LAUNCH(s->ctx, (k_spmv<1, EPI>), grid, kThreads, 0, A, vals, x, y, s->ld, w, w2, s->sums.p, s->maxIters,
-               s->partials.p, s->ticket.p, cur, localFinish);
+               s->partials.p, s->ticket.p, cur, localFinish, F);
   else
     PHB_LAUNCH(s->ctx, (k_spmv<2, EPI>), grid, kThreads, 0, A, vals, x, y, s->ld, w, w2, s->sums.p, s->maxIters,
-               s->partials.p, s->ticket.p, cur, localFinish);
+               s->partials.p, s->ticket.p, cur, localFinish, F);
 }
 
 // ghost refresh of a gathered vector before an SpMV (grid_->sendMessages analogue
@@ -351,31 +370,65 @@ int reduce_sums(phb_solver *s, int which, double *vals, int n, bool inLoop, int 
   return comm_allreduce_sum(s->ctx, vals, n);
 }
 
+// communication duties of one kernel when the peer exchanges are fused into the compute kernels
+PeerFuse make_fuse(phb_solver *s, const double *vec, int redWhich) {
+  PeerFuse F;
+  const phb_mesh *m = s->halo;
+  F.on = 1;
+  F.pv = peer_view(s->ctx);
+  F.redCh = s->peerRegion * 4 + redWhich;
+  if (vec) {
+    const int vi = vec == s->p.p ? 0 : vec == s->s.p ? 1 : vec == s->ph.p ? 2 : 3;
+    F.haloCh = s->peerRegion * 4 + vi;
+    F.vecOff = (size_t)((const char *)vec - s->ctx->peer.arena);
+  }
+  F.halo.sendDev = s->runSendDev ? s->runSendDev : m->dSendDev.p;
+  for (int q = 0; q < kMaxPeers; ++q) {
+    const bool in = q < s->ctx->nProcs;
+    F.halo.sendOff[q] = in ? m->hSendOff[q] : 0; F.halo.sendCnt[q] = in ? m->hSendCnt[q] : 0;
+    F.halo.recvCnt[q] = in ? m->hRecvCnt[q] : 0;
+    F.halo.peerRecvOff[q] = in ? m->peerRecvOff[q] : 0; F.halo.peerLd[q] = in ? m->peerLd[q] : 0;
+  }
+  return F;
+}
+
 int enqueue_iteration(phb_solver *s, const double *A, int cur) {
   phb_ctx *c = s->ctx;
   const int n = s->pat->nRows, ld = s->ld;
   const int gv = grid_for(c, n);
   const bool ilu = s->precond == PHB_PC_ILU0;
   const bool multi = c->nProcs > 1;
+  const bool fused = multi && use_peer(s) && s->peerFused;   // exchanges ride inside the compute kernels
   double *ph = ilu ? s->ph.p : s->p.p, *sh = ilu ? s->sh.p : s->s.p;
+  PeerFuse none, fPushP, fSpmv1, fUpdS, fSpmv2, fPushPh, fPushSh;
+  if (fused) {
+    fPushP = make_fuse(s, s->p.p, 0); fPushP.pushHalo = 1;              // Jacobi: p leaves with the fused update
+    fPushPh = make_fuse(s, ph, 0); fPushPh.pushHalo = 1;                // ILU: p^ leaves with the last sweep
+    fSpmv1 = make_fuse(s, ph, 0); fSpmv1.waitHalo = 1; fSpmv1.pushRed = 1;
+    fUpdS = make_fuse(s, s->s.p, 0); fUpdS.waitRed = 1; fUpdS.pushHalo = ilu ? 0 : 1;
+    fPushSh = make_fuse(s, sh, 0); fPushSh.pushHalo = 1;
+    fSpmv2 = make_fuse(s, sh, 1); fSpmv2.waitHalo = 1;
+  }
 #define FUSED(NCV, PRE)                                                                                          \
   PHB_LAUNCH(c, (k_update_fused<NCV, PRE>), gv, kThreads, 0, n, ld, s->x.p, s->r.p, s->p.p, ph, sh, s->s.p, s->t.p, \
-             s->v.p, s->sums.p, s->maxIters)
+             s->v.p, s->sums.p, s->maxIters, (fused && !ilu) ? fPushP : none, s->ticket.p)
   if (s->nComp == 1) { if (ilu) FUSED(1, true); else FUSED(1, false); }
   else { if (ilu) FUSED(2, true); else FUSED(2, false); }
 #undef FUSED
-  if (ilu) PHB_CHECK(ilu_apply(s, s->p.p, ph));          // ph = M^-1 p
-  PHB_CHECK(halo_exchange(s, ph, true));
-  launch_spmv<1>(s, A, ph, s->v.p, s->rhat.p, nullptr);   // v = A ph, R1: sigma = (rhat . v)
-  PHB_CHECK(reduce_sums(s, 0, &s->sums.p->sigma, 1, true, 0, cur));
+  if (ilu) PHB_CHECK(ilu_apply(s, s->p.p, ph, fused ? &fPushPh : nullptr));   // ph = M^-1 p
+  if (!fused) PHB_CHECK(halo_exchange(s, ph, true));
+  launch_spmv<1>(s, A, ph, s->v.p, s->rhat.p, nullptr, cur, 0, fused ? fSpmv1 : none);   // v = A ph, R1
+  if (!fused) PHB_CHECK(reduce_sums(s, 0, &s->sums.p->sigma, 1, true, 0, cur));
   if (s->nComp == 1)
-    PHB_LAUNCH(c, k_update_s<1>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->sums.p, cur, s->maxIters);
+    PHB_LAUNCH(c, k_update_s<1>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->sums.p, cur, s->maxIters,
+               fused ? fUpdS : none, s->ticket.p);
   else
-    PHB_LAUNCH(c, k_update_s<2>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->sums.p, cur, s->maxIters);
-  if (ilu) PHB_CHECK(ilu_apply(s, s->s.p, sh));          // sh = M^-1 s
-  PHB_CHECK(halo_exchange(s, sh, true));
+    PHB_LAUNCH(c, k_update_s<2>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->sums.p, cur, s->maxIters,
+               fused ? fUpdS : none, s->ticket.p);
+  if (ilu) PHB_CHECK(ilu_apply(s, s->s.p, sh, fused ? &fPushSh : nullptr));   // sh = M^-1 s
+  if (!fused) PHB_CHECK(halo_exchange(s, sh, true));
   // t = A sh, R2: (t.s), (t.t), (rhat.s), (rhat.t), (s.s); single GPU: the last CTA finishes the iteration
-  launch_spmv<2>(s, A, sh, s->t.p, s->s.p, s->rhat.p, cur, multi ? 0 : 1);
+  launch_spmv<2>(s, A, sh, s->t.p, s->s.p, s->rhat.p, cur, multi ? 0 : 1, fused ? fSpmv2 : none);
   if (multi) {
     if (use_peer(s)) {  // the all-reduce kernel also finishes the iteration
       PHB_CHECK(reduce_sums(s, 1, &s->sums.p->ts, 5, true, 1, cur));
@@ -538,7 +591,7 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
       if (g) cudaGraphDestroy(g);
       memcpy(s->graphKey, key, sizeof(key));
     }
-    const int launchesPerIter = 4 + ((s->halo && c->nProcs > 1) ? (use_peer(s) ? 4 : 3) : 0) +
+    const int launchesPerIter = 4 + ((s->halo && c->nProcs > 1) ? (use_peer(s) ? (s->peerFused ? 1 : 4) : 3) : 0) +
                                 (s->precond == PHB_PC_ILU0 ? 2 * ilu_launches_per_apply(s) : 0);
     int launched = 0, burst = 1;
     bool done = false;
@@ -650,6 +703,9 @@ int phb_solver_setup(phb_solver *s, const char *key, const char *value) {
     if (lv == "multicolor" || lv == "multicolour" || lv == "colour" || lv == "color") s->iluOrdering = 0;
     else if (lv == "levels" || lv == "natural" || lv == "wavefront") s->iluOrdering = 1;
     else PHB_REQUIRE(false, "unknown ILU ordering \"%s\" (multicolor | levels)", value);
+  } else if (k == "peerFusion") {
+    s->peerFused = std::stoi(v) != 0;
+    if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
   } else if (k == "nullSpace") {
     PHB_REQUIRE(lv == "constant" || lv == "none", "nullSpace must be \"constant\" or \"none\"");
     s->projectConstant = lv == "constant";

@@ -1,5 +1,6 @@
 // solver.cuh -- internal definition of phb_solver.
 #pragma once
+#include "peerdev.cuh"
 #include "structs.cuh"
 
 // device-resident Krylov scalars.  One BiCGStab iteration needs TWO reductions:
@@ -77,6 +78,7 @@ struct phb_solver {
   // run-time view of the system being iterated on (permuted when ILU is active)
   const SellPattern *runPat = nullptr;
   const int *runSendDev = nullptr;
+  bool peerFused = true;           // peer exchanges inside the compute kernels (else separate peer kernels)
   int peerRegion = -1;             // slot of this solver in the peer arena (-1 unassigned, -2 not usable)
   double *runPh = nullptr, *runSh = nullptr;
   phb::DevBuf<double> b, x, r, rhat, p, v, s, t;
@@ -101,7 +103,7 @@ int solver_bind(phb_solver *s, const SellPattern *pat, const double *dVals, int 
                 const phb_mesh *halo);
 int ilu_prepare(phb_solver *s, const SellPattern *P, const phb_mesh *halo);
 int ilu_factor(phb_solver *s, const double *vals);
-int ilu_apply(phb_solver *s, const double *r, double *z);
+int ilu_apply(phb_solver *s, const double *r, double *z, const PeerFuse *pushHalo = nullptr);
 int ilu_permute(phb_solver *s, const double *x, double *y, int dir);
 int ilu_launches_per_apply(const phb_solver *s);
 }  // namespace phb
