@@ -209,9 +209,9 @@ def workload_config(args, nprocs):
             "l2": "inputs larger than L2 (matrix + vectors ~0.6 GB per solve vs 126 MB L2); no flush needed",
             "tolerance": args.tol, "max_iters": args.max_iters, "preconditioner": args.precond,
             "comm": "single GPU" if nprocs == 1 else (
-                "NVLink peer memory: halo push/wait and the sigma all-reduce ride inside the compute kernels, one small "
-                "kernel for the 5-sum all-reduce; NCCL outside the loop" if args.comm == "peer" else
-                "NVLink peer memory, separate halo / all-reduce kernels" if args.comm == "peer-unfused" else
+                "NVLink peer-memory kernels inside the Krylov loop (2 halo + 2 all-reduce one-CTA kernels per iteration, "
+                "in the CUDA graph); NCCL outside the loop" if args.comm == "peer" else
+                "NVLink peer memory, halo push/wait and the sigma all-reduce inside the compute kernels" if args.comm == "peer-fused" else
                 "NCCL send/recv + all-reduce")}
 
 
@@ -232,7 +232,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = the same side x side problem split over the GPUs; weak = side x side cells per GPU")
     ap.add_argument("--guess-order", type=int, default=1, help="pEqn_ initial guess: 0 previous p, 1 extrapolated")
-    ap.add_argument("--comm", default="peer", choices=["peer", "peer-unfused", "nccl"],
+    ap.add_argument("--comm", default="peer", choices=["peer", "peer-fused", "nccl"],
                     help="in-loop halo/all-reduce: NVLink peer-memory kernels (default) or NCCL calls")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -281,7 +281,7 @@ def main():
             return out
         comm.enable_peer_memory(grid, all_gather)
     cfg = dict(solver="BICGSTAB", maxIters=args.max_iters, tolerance=args.tol, preconditioner=args.precond,
-               peerFusion=0 if args.comm == "peer-unfused" else 1)
+               peerFusion=1 if args.comm == "peer-fused" else 0)
     fs = lid_driven_cavity(grid, 1.0, 0.1, solver=cfg)
     fs.setup(guessOrder=args.guess_order)
     dt = 0.5 / nx                                            # maxCo 0.5 with the unit lid speed, h = 1/nx

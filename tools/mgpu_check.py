@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--strip", action="store_true")
     ap.add_argument("--precond", default="jacobi")
     ap.add_argument("--peer", action="store_true", help="NVLink peer-memory exchanges inside the Krylov loop")
-    ap.add_argument("--unfused", action="store_true", help="separate peer kernels instead of fused pushes/waits")
+    ap.add_argument("--fused", action="store_true", help="peer pushes/waits inside the compute kernels")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -53,7 +53,7 @@ def main():
             return out
         comm.enable_peer_memory(gl, all_gather)
     fs = lid_driven_cavity(gl, 1.0, 0.1, solver=dict(tolerance=1e-11, maxIters=50000, preconditioner=a.precond,
-                                                     peerFusion=0 if a.unfused else 1))
+                                                     peerFusion=1 if a.fused else 0))
     om = (O.Mesh.rectilinear if a.kind == "rect" else O.Mesh.triangulated)(a.nx, a.ny, 1.0, 1.0)
     ofs = O.cavity(om, 1.0, 0.1)
     ofs.use_direct_solver()
