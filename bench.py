@@ -156,6 +156,8 @@ def run_reference(args):
     import oracle as O
     nx = ny = args.n
     dt = 0.5 / nx
+    if args.precond == "amg":
+        args.precond = "ilu0"        # the reference arm always runs the reference's algorithm
     iu, ip, src = typical_iters(args.precond)
     vals = []
     detail = None
@@ -202,7 +204,8 @@ def workload_config(args, nprocs):
                         "FractionalStep time step (the snapshot's PISO successor), dt = 0.5 h (maxCo 0.5), "
                         "BiCGStab + %s, tolerance %g on ||r||/||b||, warm start from the previous step"
                         % (gx, gy, gx * gy, "" if strong or nprocs == 1 else " (%dx%d per GPU)" % (args.n, args.n),
-                           args.precond, args.tol),
+                           "smoothed-aggregation AMG V(1,1) on pEqn_ / ILU(0) on uEqn_" if args.precond == "amg"
+                           else args.precond, args.tol),
             "cells_per_gpu": gx * gy // nprocs, "global_cells": gx * gy,
             "partition": "none" if nprocs == 1 else "%dx%d blocks of %dx%d cells, one per GPU (global grid %dx%d)" % (
                 px, py, gx // px, gy // py, gx, gy),
@@ -224,7 +227,8 @@ def main():
     ap.add_argument("--side", dest="n", type=int, default=2000, help="cells per side per GPU (2000 -> 4M cells)")
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--max-iters", type=int, default=20000)
-    ap.add_argument("--precond", default="ilu0", choices=["ilu0", "jacobi", "none"])
+    ap.add_argument("--precond", default="ilu0", choices=["ilu0", "jacobi", "none", "amg"],
+                    help="amg = smoothed-aggregation V-cycle on pEqn_ (uEqn_ keeps ILU(0))")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--mesh", default="quad", choices=["quad", "tri"],
                     help="quad: side x side quads; tri: the same cell count as triangles (each quad of a "
@@ -280,9 +284,10 @@ def main():
             dist.all_gather_object(out, obj)
             return out
         comm.enable_peer_memory(grid, all_gather)
-    cfg = dict(solver="BICGSTAB", maxIters=args.max_iters, tolerance=args.tol, preconditioner=args.precond,
-               peerFusion=1 if args.comm == "peer-fused" else 0)
-    fs = lid_driven_cavity(grid, 1.0, 0.1, solver=cfg)
+    amg = args.precond == "amg"
+    cfg = dict(solver="BICGSTAB", maxIters=args.max_iters, tolerance=args.tol,
+               preconditioner="ilu0" if amg else args.precond, peerFusion=1 if args.comm == "peer-fused" else 0)
+    fs = lid_driven_cavity(grid, 1.0, 0.1, solver=cfg, pSolver=dict(preconditioner="amg") if amg else None)
     fs.setup(guessOrder=args.guess_order)
     dt = 0.5 / nx                                            # maxCo 0.5 with the unit lid speed, h = 1/nx
     if args.scaling == "weak" and args.mesh == "quad":
@@ -416,14 +421,22 @@ def main():
             "e2e": {"value": (world if args.scaling == "weak" else 1) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_all,
                     "what": "host state (u, p, gradP cells+faces) copied in, FractionalStep.solve, state copied out, per step"},
             "e2e_seam1": seam1, "gpu_launches": int(launches), "clocks": clocks}
+    if amg:
+        line["amg"] = fs.pEqn.solver.amgInfo()
+        line["amg"]["note"] = ("hierarchy built on the host in the first (warm-up) solve and reused: pEqn_ = laplacian(dt, p) "
+                               "is constant up to the scalar dt; setupMs is that one-off cost, outside the timed steps")
     if not args.no_cpu and world == 1:
-        v, detail = cpu_reference_sample(args.n, args.n, 0.5 / args.n, iters_u, iters_p, precond=args.precond)
+        # the CPU arm runs the reference's algorithm (BiCGStab + ILU(0)); with AMG on the GPU arm its bounded
+        # sample is scaled by the ILU(0) iteration counts measured for this workload (profiles/iters_4M.json)
+        cpc = "ilu0" if amg else args.precond
+        ciu, cip, csrc = (typical_iters("ilu0") if amg else (iters_u, iters_p, "this run"))
+        v, detail = cpu_reference_sample(args.n, args.n, 0.5 / args.n, ciu, cip, precond=cpc)
         import oracle as O
         cores = O.lib().or_num_threads()
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "1 assembled 4M-cell step + 12/24 BiCGStab(%s) iterations per solve on %d "
-                                          "OpenMP threads, scaled to this run's %.0f/%.0f iterations per solve" %
-                                          (args.precond, cores, iters_u, iters_p), "detail": detail}
+                                          "OpenMP threads, scaled to %.0f/%.0f iterations per solve (%s)" %
+                                          (cpc, cores, ciu, cip, csrc), "detail": detail}
     print(json.dumps(line), flush=True)
     fs.close(); grid.close(); comm.close()
     if world > 1:

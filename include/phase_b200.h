@@ -37,7 +37,7 @@ typedef enum {
 /* boundary types: UF/FiniteVolumeField.h:12 enum BoundaryType */
 enum { PHB_FIXED = 0, PHB_NORMAL_GRADIENT = 1, PHB_SYMMETRY = 2 };
 /* preconditioners */
-enum { PHB_PC_NONE = 0, PHB_PC_JACOBI = 1, PHB_PC_ILU0 = 2 };
+enum { PHB_PC_NONE = 0, PHB_PC_JACOBI = 1, PHB_PC_ILU0 = 2, PHB_PC_AMG = 3 };
 
 typedef struct phb_ctx phb_ctx;
 typedef struct phb_mesh phb_mesh;
@@ -184,6 +184,29 @@ int phb_solver_spmv(phb_solver *s, const double *x, double *y, int n);
 int phb_solver_time_spmv(phb_solver *s, int reps, double *msPerLaunch);
 /* algorithmic byte counts of the current matrix: [spmv, bicgstabIteration] */
 int phb_solver_bytes(const phb_solver *s, double out[2]);
+
+/* `preconditioner amg` -- smoothed-aggregation multigrid V-cycle (the reference's `lib muelu`,
+ * Math/TrilinosMueluSparseMatrixSolver.cpp:27-32).  Extra setup keys: amgTheta (strength threshold, 0),
+ * amgCoarsest (rows of the densely inverted coarsest level, 400), amgSweeps (Jacobi sweeps before and
+ * after the coarse correction, 1), amgSmootherWeight (4/3, divided by the Gershgorin bound of
+ * rho(D^-1 A)), amgRebuild (auto | always).  The hierarchy is built on the host once per matrix and
+ * reused while the matrix stays a scalar multiple of it or the iteration count does not degrade.
+ * info = [levels, operator complexity, host setup ms, setups so far, coarsest rows, kernel launches
+ *         per cycle, iterations of the first solve after the last setup, hierarchy stale (0/1)] */
+int phb_solver_amg_info(const phb_solver *s, double info[8]);
+/* The same setup on a host CSR matrix, level matrices readable (works on a host-only context; used by
+ * the CPU tests to check the Galerkin products and the cycle against scipy).
+ * which: 0 = A_l, 1 = P_l (n_l x n_{l+1}), 2 = R_l = P_l^T */
+typedef struct phb_amg_host phb_amg_host;
+int phb_amg_host_build(int n, const int *rowPtr, const int *colInd, const double *vals, double theta,
+                       int coarsest, phb_amg_host **out);
+int phb_amg_host_levels(const phb_amg_host *h, int *nLevels, int *singular, int *denseCoarse);
+int phb_amg_host_level_size(const phb_amg_host *h, int level, int which, int *nRows, int *nCols,
+                            long long *nnz, double *rho);
+int phb_amg_host_level_csr(const phb_amg_host *h, int level, int which, int *rowPtr, int *colInd,
+                           double *vals);
+int phb_amg_host_coarse_inverse(const phb_amg_host *h, double *inv);
+int phb_amg_host_destroy(phb_amg_host *h);
 
 /* ---------------------------------------------------------- fields, equations
  * Seam 2.  Device mirrors of FiniteVolumeField<T> (cells + faces, BC table,

@@ -60,6 +60,13 @@ SIGNATURES = {
     "phb_solver_spmv": (ci, [vp, pd, pd, ci]),
     "phb_solver_time_spmv": (ci, [vp, ci, pd]),
     "phb_solver_bytes": (ci, [vp, pd]),
+    "phb_solver_amg_info": (ci, [vp, pd]),
+    "phb_amg_host_build": (ci, [ci, pi, pi, pd, cd, ci, pvp]),
+    "phb_amg_host_levels": (ci, [vp, pi, pi, pi]),
+    "phb_amg_host_level_size": (ci, [vp, ci, ci, pi, pi, C.POINTER(cll), pd]),
+    "phb_amg_host_level_csr": (ci, [vp, ci, ci, pi, pi, pd]),
+    "phb_amg_host_coarse_inverse": (ci, [vp, pd]),
+    "phb_amg_host_destroy": (ci, [vp]),
     "phb_field_create": (ci, [vp, ci, cs, pvp]),
     "phb_field_destroy": (ci, [vp]),
     "phb_field_set_bc": (ci, [vp, cs, ci, cd, cd]),

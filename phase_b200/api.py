@@ -278,6 +278,13 @@ class SparseMatrixSolver:
         check(self.L.phb_solver_bytes(self.h, out))
         return float(out[0]), float(out[1])
 
+    def amgInfo(self):
+        out = (C.c_double * 8)()
+        check(self.L.phb_solver_amg_info(self.h, out))
+        keys = ("levels", "operatorComplexity", "setupMs", "setups", "coarsestRows", "launchesPerCycle",
+                "itersAfterSetup", "stale")
+        return dict(zip(keys, (float(v) for v in out)))
+
     def close(self):
         if self.own and self.h:
             self.L.phb_solver_destroy(self.h)
@@ -529,8 +536,9 @@ class Piso:
             self.h = None
 
 
-def lid_driven_cavity(grid, rho=1.0, mu=0.1, lid=1.0, solver=None):
-    """Examples/LidDrivenCavity/case/boundaries.info on any grid with x-/x+/y-/y+ patches."""
+def lid_driven_cavity(grid, rho=1.0, mu=0.1, lid=1.0, solver=None, pSolver=None):
+    """Examples/LidDrivenCavity/case/boundaries.info on any grid with x-/x+/y-/y+ patches.
+    `solver` = LinearAlgebra keys of both equations, `pSolver` = overrides for pEqn (e.g. preconditioner amg)."""
     fs = FractionalStep(grid, rho, mu)
     for pt in ("x-", "x+", "y-"):
         fs.u.setBoundary(pt, FIXED, (0.0, 0.0))
@@ -540,6 +548,8 @@ def lid_driven_cavity(grid, rho=1.0, mu=0.1, lid=1.0, solver=None):
     cfg = dict(solver="BICGSTAB", maxIters=20000, tolerance=1e-10, preconditioner="ilu0")
     cfg.update(solver or {})
     fs.uEqn.solver.setup(cfg)
-    fs.pEqn.solver.setup(cfg)
+    pcfg = dict(cfg)
+    pcfg.update(pSolver or {})
+    fs.pEqn.solver.setup(pcfg)
     fs.initialize()
     return fs

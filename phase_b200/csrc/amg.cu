@@ -1,0 +1,738 @@
+// amg.cu -- smoothed-aggregation algebraic multigrid preconditioner (`preconditioner amg`).
+//
+// Role in the reference: the MueLu backend (Math/TrilinosMueluSparseMatrixSolver.cpp:27-32 builds a
+// MueLu hierarchy from the Tpetra matrix and hands it to Belos as the right preconditioner, `lib muelu`);
+// here it is a preconditioner choice of the one B200 backend.  One V(nu,nu) cycle with damped-Jacobi
+// smoothing is a fixed linear operator, so it drops into the right-preconditioned BiCGStab unchanged.
+//
+// Split of the work:
+//   * setup (host, once per matrix): strength graph -> greedy aggregation -> tentative prolongator T
+//     (piecewise constant) -> P = (I - w D^-1 A) T -> R = P^T -> A_c = R A P, repeated until the level
+//     has <= `amgCoarsest` rows; the coarsest operator is inverted densely (regularised with the
+//     constant vector when the system is singular, i.e. all-Neumann pressure).  The hierarchy is kept
+//     while the matrix stays a scalar multiple of the one it was built from (FractionalStep's pEqn_ is
+//     `laplacian(dt, p)`: constant up to dt) and rebuilt only when the iteration count degrades.
+//   * cycle (device, inside the CUDA graph of the Krylov loop): every level operator, P and R are
+//     sliced-ELL matrices driven by the same warp<->slice streaming code as the Krylov SpMV.
+// Rank-local on several GPUs (ghost columns dropped) = the reference's additive Schwarz with overlap 0.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <numeric>
+
+#include "kernels.cuh"
+#include "solver.cuh"
+
+using namespace phb;
+
+// ===================================================================== host setup
+namespace {
+
+struct HCsr {
+  int n = 0, m = 0;  // rows, cols
+  std::vector<int> rp, ci;
+  std::vector<double> v;
+  long long nnz() const { return (long long)ci.size(); }
+};
+
+HCsr transpose(const HCsr &A) {
+  HCsr T;
+  T.n = A.m; T.m = A.n;
+  T.rp.assign(T.n + 1, 0);
+  for (int c : A.ci) T.rp[c + 1]++;
+  for (int i = 0; i < T.n; ++i) T.rp[i + 1] += T.rp[i];
+  T.ci.resize(A.ci.size());
+  T.v.resize(A.ci.size());
+  std::vector<int> fill(T.rp.begin(), T.rp.end() - 1);
+  for (int i = 0; i < A.n; ++i)
+    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) {
+      const int dst = fill[A.ci[k]]++;
+      T.ci[dst] = i;
+      T.v[dst] = A.v[k];
+    }
+  return T;
+}
+
+// C = A B (Gustavson, marker array); rows of C sorted by column
+HCsr spgemm(const HCsr &A, const HCsr &B) {
+  HCsr C;
+  C.n = A.n; C.m = B.m;
+  C.rp.assign(C.n + 1, 0);
+  std::vector<long long> marker(B.m, -1);
+  std::vector<std::pair<int, double>> row;
+  for (int i = 0; i < A.n; ++i) {
+    const long long start = (long long)C.ci.size();
+    for (int ka = A.rp[i]; ka < A.rp[i + 1]; ++ka) {
+      const int j = A.ci[ka];
+      const double a = A.v[ka];
+      for (int kb = B.rp[j]; kb < B.rp[j + 1]; ++kb) {
+        const int c = B.ci[kb];
+        if (marker[c] < start) {
+          marker[c] = (long long)C.ci.size();
+          C.ci.push_back(c);
+          C.v.push_back(a * B.v[kb]);
+        } else {
+          C.v[marker[c]] += a * B.v[kb];
+        }
+      }
+    }
+    const long long end = (long long)C.ci.size();
+    row.clear();
+    for (long long k = start; k < end; ++k) row.push_back({C.ci[k], C.v[k]});
+    std::sort(row.begin(), row.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) {
+      return x.first < y.first;
+    });
+    for (long long k = start; k < end; ++k) { C.ci[k] = row[k - start].first; C.v[k] = row[k - start].second; }
+    for (long long k = start; k < end; ++k) marker[C.ci[k]] = -1;  // positions moved: forget them
+    C.rp[i + 1] = (int)end;
+  }
+  return C;
+}
+
+std::vector<double> diagonal(const HCsr &A) {
+  std::vector<double> d(A.n, 0.);
+  for (int i = 0; i < A.n; ++i)
+    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
+      if (A.ci[k] == i) d[i] += A.v[k];
+  return d;
+}
+
+// Greedy aggregation on the strength graph |a_ij|^2 >= theta^2 |a_ii a_jj| (three passes: roots whose
+// strong neighbourhood is free, leftovers join a neighbouring aggregate, the rest seed new aggregates).
+int aggregate(const HCsr &A, const std::vector<double> &d, double theta, std::vector<int> &agg,
+              std::vector<char> &strong) {
+  const int n = A.n;
+  strong.assign(A.ci.size(), 0);
+  for (int i = 0; i < n; ++i)
+    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) {
+      const int j = A.ci[k];
+      const double a = A.v[k];
+      strong[k] = (j != i && a != 0. && a * a >= theta * theta * std::fabs(d[i] * d[j])) ? 1 : 0;
+    }
+  agg.assign(n, -1);
+  int nc = 0;
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] >= 0) continue;
+    bool free_ = true;
+    for (int k = A.rp[i]; k < A.rp[i + 1] && free_; ++k)
+      if (strong[k] && agg[A.ci[k]] >= 0) free_ = false;
+    if (!free_) continue;
+    agg[i] = nc;
+    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
+      if (strong[k]) agg[A.ci[k]] = nc;
+    ++nc;
+  }
+  std::vector<int> pass2(agg);
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] >= 0) continue;
+    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
+      if (strong[k] && agg[A.ci[k]] >= 0) { pass2[i] = agg[A.ci[k]]; break; }
+  }
+  agg.swap(pass2);
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] >= 0) continue;
+    agg[i] = nc;
+    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
+      if (strong[k] && agg[A.ci[k]] < 0) agg[A.ci[k]] = nc;
+    ++nc;
+  }
+  return nc;
+}
+
+struct HostLevel {
+  HCsr A, P, R;
+  std::vector<double> diag;  // of the (filtered) operator the smoother uses
+  double rho = 2.;           // Gershgorin bound of rho(D^-1 A)
+};
+
+struct HostHierarchy {
+  std::vector<HostLevel> lev;
+  std::vector<double> coarseInv;  // dense, row-major, lev.back().A.n squared (empty: Jacobi sweeps instead)
+  bool singular = false;
+  double setupMs = 0.;
+  double opComplexity = 1.;
+};
+
+constexpr int kDenseMax = 1024;
+
+bool dense_inverse(std::vector<double> &M, int n) {
+  // Gauss-Jordan with partial pivoting on [M | I]
+  std::vector<double> I((size_t)n * n, 0.);
+  for (int i = 0; i < n; ++i) I[(size_t)i * n + i] = 1.;
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    double best = std::fabs(M[(size_t)c * n + c]);
+    for (int r = c + 1; r < n; ++r)
+      if (std::fabs(M[(size_t)r * n + c]) > best) { best = std::fabs(M[(size_t)r * n + c]); piv = r; }
+    if (!(best > 0.)) return false;
+    if (piv != c)
+      for (int k = 0; k < n; ++k) {
+        std::swap(M[(size_t)c * n + k], M[(size_t)piv * n + k]);
+        std::swap(I[(size_t)c * n + k], I[(size_t)piv * n + k]);
+      }
+    const double inv = 1. / M[(size_t)c * n + c];
+    for (int k = 0; k < n; ++k) { M[(size_t)c * n + k] *= inv; I[(size_t)c * n + k] *= inv; }
+    for (int r = 0; r < n; ++r) {
+      if (r == c) continue;
+      const double f = M[(size_t)r * n + c];
+      if (f == 0.) continue;
+      double *mr = &M[(size_t)r * n], *mc = &M[(size_t)c * n], *ir = &I[(size_t)r * n], *ic = &I[(size_t)c * n];
+      for (int k = 0; k < n; ++k) { mr[k] -= f * mc[k]; ir[k] -= f * ic[k]; }
+    }
+  }
+  M.swap(I);
+  return true;
+}
+
+int build_hierarchy(HCsr A0, double theta, int coarsest, double omegaP, HostHierarchy &H) {
+  const auto t0 = std::chrono::steady_clock::now();
+  H.lev.clear();
+  // singular with the constant in the null space? (all-Neumann pressure: every row sums to zero)
+  {
+    double maxRow = 0., maxDiag = 0.;
+    for (int i = 0; i < A0.n; ++i) {
+      double sum = 0.;
+      for (int k = A0.rp[i]; k < A0.rp[i + 1]; ++k) {
+        sum += A0.v[k];
+        if (A0.ci[k] == i) maxDiag = std::max(maxDiag, std::fabs(A0.v[k]));
+      }
+      maxRow = std::max(maxRow, std::fabs(sum));
+    }
+    H.singular = maxRow <= 1e-10 * maxDiag;
+  }
+  const long long nnz0 = std::max<long long>(1, A0.nnz());
+  long long nnzAll = 0;
+  HCsr A = std::move(A0);
+  for (int level = 0;; ++level) {
+    HostLevel L;
+    const int n = A.n;
+    std::vector<double> d = diagonal(A);
+    for (int i = 0; i < n; ++i)
+      if (d[i] == 0.) { set_error("amg: zero diagonal in row %d of level %d", i, level); return PHB_ERR_BREAKDOWN; }
+    nnzAll += A.nnz();
+    const bool last = n <= coarsest || level >= 15;
+    std::vector<int> agg;
+    std::vector<char> strong;
+    int nc = 0;
+    if (!last) nc = aggregate(A, d, theta, agg, strong);
+    if (last || nc >= n || nc * 10 > n * 9) {  // coarsest level (or coarsening stalled)
+      L.diag = d;
+      double rho = 0.;
+      for (int i = 0; i < n; ++i) {
+        double s = 0.;
+        for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) s += std::fabs(A.v[k]);
+        rho = std::max(rho, s / std::fabs(d[i]));
+      }
+      L.rho = rho;
+      L.A = std::move(A);
+      H.lev.push_back(std::move(L));
+      break;
+    }
+    // filtered operator: weak off-diagonals lumped onto the diagonal (identity when theta = 0)
+    std::vector<double> df(d);
+    for (int i = 0; i < n; ++i)
+      for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
+        if (!strong[k] && A.ci[k] != i) df[i] += A.v[k];
+    for (int i = 0; i < n; ++i)
+      if (df[i] == 0. || (df[i] > 0.) != (d[i] > 0.)) df[i] = d[i];
+    double rho = 0.;
+    for (int i = 0; i < n; ++i) {
+      double s = std::fabs(df[i]);
+      for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
+        if (strong[k]) s += std::fabs(A.v[k]);
+      rho = std::max(rho, s / std::fabs(df[i]));
+    }
+    // smoother data uses the full operator
+    {
+      double r2 = 0.;
+      for (int i = 0; i < n; ++i) {
+        double s = 0.;
+        for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) s += std::fabs(A.v[k]);
+        r2 = std::max(r2, s / std::fabs(d[i]));
+      }
+      L.rho = r2;
+      L.diag = d;
+    }
+    // P = (I - (omegaP / rho) Df^-1 Af) T,  T(i, agg[i]) = 1
+    HCsr P;
+    P.n = n; P.m = nc;
+    P.rp.assign(n + 1, 0);
+    std::vector<std::pair<int, double>> row;
+    const double w = omegaP / rho;
+    for (int i = 0; i < n; ++i) {
+      row.clear();
+      row.push_back({agg[i], 1. - w});  // diagonal term of Af: df/df = 1
+      for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) {
+        if (!strong[k]) continue;
+        const int c = agg[A.ci[k]];
+        const double val = -w * A.v[k] / df[i];
+        bool hit = false;
+        for (auto &e : row)
+          if (e.first == c) { e.second += val; hit = true; break; }
+        if (!hit) row.push_back({c, val});
+      }
+      std::sort(row.begin(), row.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) {
+        return x.first < y.first;
+      });
+      for (auto &e : row) { P.ci.push_back(e.first); P.v.push_back(e.second); }
+      P.rp[i + 1] = (int)P.ci.size();
+    }
+    L.R = transpose(P);
+    HCsr AP = spgemm(A, P);
+    HCsr Ac = spgemm(L.R, AP);
+    L.P = std::move(P);
+    L.A = std::move(A);
+    H.lev.push_back(std::move(L));
+    A = std::move(Ac);
+  }
+  H.opComplexity = (double)nnzAll / (double)nnz0;
+  // coarsest solve
+  const HCsr &C = H.lev.back().A;
+  H.coarseInv.clear();
+  if (C.n <= kDenseMax) {
+    const int n = C.n;
+    std::vector<double> M((size_t)n * n, 0.);
+    double meanDiag = 0.;
+    for (int i = 0; i < n; ++i)
+      for (int k = C.rp[i]; k < C.rp[i + 1]; ++k) {
+        M[(size_t)i * n + C.ci[k]] += C.v[k];
+        if (C.ci[k] == i) meanDiag += C.v[k] / n;
+      }
+    if (H.singular)
+      for (size_t k = 0; k < M.size(); ++k) M[k] += meanDiag / n;  // + (mean diag / n) 1 1^T
+    if (dense_inverse(M, n)) H.coarseInv.swap(M);
+  }
+  H.setupMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return PHB_OK;
+}
+
+// sliced-ELL image of a host CSR matrix (diagonal moved to entry 0 when square)
+void sell_from_csr(const HCsr &A, bool diagFirst, SellPattern &S, std::vector<double> &slotVals) {
+  S.nRows = A.n; S.nCols = A.m;
+  S.nSlices = (A.n + 31) / 32;
+  S.hRowLen.assign(A.n, 0);
+  S.nnz = A.nnz();
+  for (int r = 0; r < A.n; ++r) S.hRowLen[r] = A.rp[r + 1] - A.rp[r];
+  S.hSliceOff.assign(S.nSlices + 1, 0);
+  for (int sl = 0; sl < S.nSlices; ++sl) {
+    int w = 1;
+    for (int r = sl * 32; r < std::min(A.n, sl * 32 + 32); ++r) w = std::max(w, S.hRowLen[r]);
+    S.hSliceOff[sl + 1] = S.hSliceOff[sl] + w * 32;
+  }
+  S.nSlots = S.hSliceOff[S.nSlices];
+  S.hCol.assign(S.nSlots, 0);
+  slotVals.assign(S.nSlots, 0.);
+  for (int sl = 0; sl < S.nSlices; ++sl) {
+    const int w = (S.hSliceOff[sl + 1] - S.hSliceOff[sl]) / 32;
+    for (int lane = 0; lane < 32; ++lane) {
+      const int r = sl * 32 + lane;
+      const int pad = diagFirst ? std::min(r, A.n - 1) : 0;
+      int k = 0;
+      if (r < A.n) {
+        if (diagFirst)
+          for (int j = A.rp[r]; j < A.rp[r + 1]; ++j)
+            if (A.ci[j] == r) {
+              const size_t slot = (size_t)S.hSliceOff[sl] + lane;
+              S.hCol[slot] = r; slotVals[slot] = A.v[j]; k = 1;
+              break;
+            }
+        for (int j = A.rp[r]; j < A.rp[r + 1]; ++j) {
+          if (diagFirst && A.ci[j] == r) continue;
+          const size_t slot = (size_t)S.hSliceOff[sl] + (size_t)k * 32 + lane;
+          S.hCol[slot] = A.ci[j]; slotVals[slot] = A.v[j];
+          ++k;
+        }
+      }
+      for (; k < w; ++k) S.hCol[(size_t)S.hSliceOff[sl] + (size_t)k * 32 + lane] = pad;
+    }
+  }
+}
+
+// local block (owned rows x owned columns) of a sliced-ELL matrix as host CSR
+HCsr csr_from_sell(const SellPattern &S, const std::vector<double> &slotVals) {
+  HCsr A;
+  A.n = A.m = S.nRows;
+  A.rp.assign(A.n + 1, 0);
+  std::vector<std::pair<int, double>> row;
+  for (int r = 0; r < A.n; ++r) {
+    const int sl = r >> 5, lane = r & 31;
+    row.clear();
+    for (int k = 0; k < S.hRowLen[r]; ++k) {
+      const size_t slot = (size_t)S.hSliceOff[sl] + (size_t)k * 32 + lane;
+      const int c = S.hCol[slot];
+      if (c >= A.n) continue;  // ghost column: rank-local preconditioner
+      bool hit = false;
+      for (auto &e : row)
+        if (e.first == c) { e.second += slotVals[slot]; hit = true; break; }
+      if (!hit) row.push_back({c, slotVals[slot]});
+    }
+    std::sort(row.begin(), row.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) {
+      return x.first < y.first;
+    });
+    for (auto &e : row) { A.ci.push_back(e.first); A.v.push_back(e.second); }
+    A.rp[r + 1] = (int)A.ci.size();
+  }
+  return A;
+}
+
+// ===================================================================== device cycle
+constexpr int kThreads = 256;
+constexpr int kBlocksPerSM = 8;
+
+// MODE 0: y = M x          MODE 1: y = b - M x
+// MODE 2: y = x + w (b - M x)   (damped Jacobi, out of place; w = omega / a_ii)
+// MODE 3: y += M x
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_amg_spmv(SellView M, const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+           const double *__restrict__ b, const double *__restrict__ w, const KrylovSums *S, int maxIters) {
+  if (S && krylov_done(S, maxIters)) return;
+  const int lane = threadIdx.x & 31;
+  const int warpsPerBlock = blockDim.x >> 5;
+  const int warp = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
+  const int nWarps = gridDim.x * warpsPerBlock;
+  for (int slice = warp; slice < M.nSlices; slice += nWarps) {
+    const int off = __ldg(M.sliceOff + slice);
+    const int wdt = (__ldg(M.sliceOff + slice + 1) - off) >> 5;
+    const int row = slice * 32 + lane;
+    double acc[1] = {0.};
+    slice_dot_any<1>(M.col, vals, (size_t)off + lane, wdt, x, 0, acc);
+    if (row < M.nRows) {
+      if (MODE == 0) y[row] = acc[0];
+      if (MODE == 1) y[row] = b[row] - acc[0];
+      if (MODE == 2) y[row] = x[row] + w[row] * (b[row] - acc[0]);
+      if (MODE == 3) y[row] += acc[0];
+    }
+  }
+}
+
+// x = w .* b  (first pre-smoothing sweep from a zero guess)
+__global__ void k_amg_scale(int n, const double *__restrict__ w, const double *__restrict__ b,
+                            double *__restrict__ x, const KrylovSums *S, int maxIters) {
+  if (S && krylov_done(S, maxIters)) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = w[i] * b[i];
+}
+
+// coarsest level: x = Ainv b, one warp per row of the dense inverse
+__global__ void k_amg_dense(int n, const double *__restrict__ Ainv, const double *__restrict__ b,
+                            double *__restrict__ x, const KrylovSums *S, int maxIters) {
+  if (S && krylov_done(S, maxIters)) return;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  double acc = 0.;
+  for (int k = lane; k < n; k += 32) acc = fma(Ainv[(size_t)row * n + k], b[k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) x[row] = acc;
+}
+
+// max relative deviation of `a` from ratio * ref over the slots, ratio = a[first] / ref[first]
+__global__ void __launch_bounds__(kThreads)
+k_amg_changed(long long nSlots, const double *__restrict__ a, const double *__restrict__ ref, int first,
+              double *partials, unsigned *ticket, double *out) {
+  const double ratio = ref[first] != 0. ? a[first] / ref[first] : 1.;
+  double dev = 0.;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nSlots;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double r = ratio * ref[i];
+    const double d = fabs(a[i] - r);
+    if (d > 0.) dev = fmax(dev, d / fmax(fabs(r), 1e-300));
+  }
+  double v[1] = {dev};
+  if (grid_reduce<1, true>(v, partials, ticket, out) && (threadIdx.x & 31) == 0) out[1] = ratio;
+}
+
+int grid_rows(const phb_ctx *c, long long rows) {
+  const long long g = (rows + kThreads - 1) / kThreads;
+  const long long cap = (long long)c->numSMs * kBlocksPerSM;
+  return (int)std::max<long long>(1, std::min(g, cap));
+}
+
+template <int MODE>
+void launch(phb_solver *s, const SellPattern &P, const double *vals, const double *x, double *y, const double *b,
+            const double *w, bool inLoop) {
+  const SellView V = view_of(&P);
+  PHB_LAUNCH(s->ctx, k_amg_spmv<MODE>, grid_rows(s->ctx, (long long)P.nSlices * 32), kThreads, 0, V, vals, x, y, b, w,
+             inLoop ? s->sums.p : nullptr, s->maxIters);
+}
+
+int upload_mat(phb_ctx *c, const HCsr &H, bool diagFirst, AmgMat &M) {
+  std::vector<double> slotVals;
+  sell_from_csr(H, diagFirst, M.pat, slotVals);
+  PHB_CHECK(M.pat.sliceOff.upload(M.pat.hSliceOff, c->stream));
+  PHB_CHECK(M.pat.rowLen.upload(M.pat.hRowLen, c->stream));
+  PHB_CHECK(M.pat.col.upload(M.pat.hCol, c->stream));
+  PHB_CHECK(M.vals.upload(slotVals, c->stream));
+  PHB_CUDA(cudaStreamSynchronize(c->stream));  // slotVals goes out of scope
+  return PHB_OK;
+}
+
+int rebuild(phb_solver *s) {
+  phb_ctx *c = s->ctx;
+  AmgData &D = s->amg;
+  const SellPattern *P = s->pat;
+  std::vector<double> slotVals((size_t)P->nSlots);
+  PHB_CUDA(cudaMemcpyAsync(slotVals.data(), s->dVals, slotVals.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                           c->stream));
+  PHB_CUDA(cudaStreamSynchronize(c->stream));
+  HostHierarchy H;
+  PHB_CHECK(build_hierarchy(csr_from_sell(*P, slotVals), D.theta, D.coarsest, 4. / 3., H));
+  D.lev.clear();
+  const int nLev = (int)H.lev.size();
+  for (int l = 0; l < nLev; ++l) {
+    std::unique_ptr<AmgLevel> L(new AmgLevel());
+    HostLevel &h = H.lev[l];
+    L->n = h.A.n;
+    if (l > 0) PHB_CHECK(upload_mat(c, h.A, true, L->A));
+    if (l + 1 < nLev) {
+      PHB_CHECK(upload_mat(c, h.P, false, L->P));
+      PHB_CHECK(upload_mat(c, h.R, false, L->R));
+    }
+    std::vector<double> w(L->n);
+    for (int i = 0; i < L->n; ++i) w[i] = (D.omegaS / h.rho) / h.diag[i];
+    PHB_CHECK(L->w.upload(w, c->stream));
+    PHB_CUDA(cudaStreamSynchronize(c->stream));
+    const size_t len = l == 0 ? (size_t)P->nCols : (size_t)L->n;  // level 0 vectors carry (zero) ghost entries
+    PHB_CHECK(L->x.alloc(len)); PHB_CHECK(L->x2.alloc(len)); PHB_CHECK(L->r.alloc(len));
+    PHB_CHECK(L->x.zero(c->stream)); PHB_CHECK(L->x2.zero(c->stream)); PHB_CHECK(L->r.zero(c->stream));
+    if (l > 0) { PHB_CHECK(L->b.alloc(len)); PHB_CHECK(L->b.zero(c->stream)); }
+    D.lev.push_back(std::move(L));
+  }
+  D.nCoarse = H.lev.back().A.n;
+  D.denseCoarse = !H.coarseInv.empty();
+  if (D.denseCoarse) PHB_CHECK(D.coarseInv.upload(H.coarseInv, c->stream));
+  PHB_CHECK(D.refVals.alloc((size_t)P->nSlots));
+  PHB_CUDA(cudaMemcpyAsync(D.refVals.p, s->dVals, (size_t)P->nSlots * sizeof(double), cudaMemcpyDeviceToDevice,
+                           c->stream));
+  PHB_CUDA(cudaStreamSynchronize(c->stream));
+  D.src = P;
+  D.built = true;
+  D.setups++;
+  D.setupMs = H.setupMs;
+  D.opComplexity = H.opComplexity;
+  D.itersAfterSetup = -1;
+  D.stale = false;
+  if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
+  return PHB_OK;
+}
+
+}  // namespace
+
+namespace phb {
+
+// Called once per solve, before the Krylov loop: (re)build the hierarchy when there is none, the pattern
+// changed, or the matrix drifted from the one it was built from AND the last solve needed markedly more
+// iterations than the first solve after the setup did.
+int amg_prepare(phb_solver *s) {
+  phb_ctx *c = s->ctx;
+  AmgData &D = s->amg;
+  if (s->nComp != 1) {
+    set_error("preconditioner amg handles scalar equations only (use ilu0 for vector equations)");
+    return PHB_ERR_UNSUPPORTED;
+  }
+  bool need = !D.built || D.src != s->pat || D.refVals.n != (size_t)s->pat->nSlots;
+  if (!need) {
+    PHB_CHECK(D.chk.alloc(2));
+    int first = 0;
+    PHB_LAUNCH(c, k_amg_changed, grid_rows(c, s->pat->nSlots), kThreads, 0, s->pat->nSlots, s->dVals, D.refVals.p,
+               first, s->partials.p, s->ticket.p, D.chk.p);
+    PHB_CUDA(cudaMemcpyAsync(c->pinned, D.chk.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PHB_CUDA(cudaStreamSynchronize(c->stream));
+    const double dev = c->pinned[0];
+    D.stale = !(dev <= 1e-9);
+    if (D.stale && D.itersAfterSetup >= 0 && s->lastIters > std::max(2 * D.itersAfterSetup, D.itersAfterSetup + 10))
+      need = true;
+    if (D.rebuildAlways && D.stale) need = true;
+  }
+  if (need) PHB_CHECK(rebuild(s));
+  return PHB_OK;
+}
+
+void amg_record_iters(phb_solver *s, int iters) {
+  if (s->amg.built && s->amg.itersAfterSetup < 0) s->amg.itersAfterSetup = iters;
+}
+
+int amg_launches_per_apply(const phb_solver *s) {
+  const AmgData &D = s->amg;
+  const int L = (int)D.lev.size();
+  if (L == 0) return 0;
+  const int perLevel = 1 + (D.nu - 1) + 2 + 1 + D.nu;  // scale, extra pre, residual + restrict, prolong, post
+  return (L - 1) * perLevel + (D.denseCoarse ? 1 : 1 + kCoarseSweeps);
+}
+
+// algorithmic bytes of one cycle: every matrix streamed once per use (12 B per entry + 4 B per row
+// pointer), vectors 8 B per element read or written
+double amg_cycle_bytes(const phb_solver *s) {
+  const AmgData &D = s->amg;
+  const int L = (int)D.lev.size();
+  if (L == 0) return 0.;
+  auto mat = [](const SellPattern &P) { return 12. * (double)P.nnz + 4. * (P.nRows + 1.); };
+  double total = 0.;
+  for (int l = 0; l < L; ++l) {
+    const AmgLevel &V = *D.lev[l];
+    const double n = V.n, a = mat(l == 0 ? *s->pat : V.A.pat);
+    const double jac = a + 40. * n, res = a + 24. * n;  // x gather + x, b, w reads + y write | x, b, y
+    if (l + 1 < L) {
+      const double nc = D.lev[l + 1]->n;
+      total += 24. * n + (D.nu - 1) * jac + res + (mat(V.R.pat) + 8. * n + 8. * nc) + (mat(V.P.pat) + 8. * nc + 16. * n) +
+               D.nu * jac;
+    } else {
+      total += D.denseCoarse ? 8. * n * n + 16. * n : 24. * n + kCoarseSweeps * jac;
+    }
+  }
+  return total;
+}
+
+// z = M^-1 r : one V(nu, nu) cycle.  All kernels test the device-side convergence flag first, so the
+// tail of a graph after convergence costs launches only.
+int amg_apply(phb_solver *s, const double *in, double *out, bool inLoop) {
+  phb_ctx *c = s->ctx;
+  AmgData &D = s->amg;
+  const int L = (int)D.lev.size();
+  const KrylovSums *S = inLoop ? s->sums.p : nullptr;
+  std::vector<const double *> bOf(L);
+  std::vector<double *> xOf(L);
+  bOf[0] = in;
+  for (int l = 1; l < L; ++l) bOf[l] = D.lev[l]->b.p;
+  auto matPat = [&](int l) -> const SellPattern & { return l == 0 ? *s->pat : D.lev[l]->A.pat; };
+  auto matVal = [&](int l) -> const double * { return l == 0 ? D.refVals.p : D.lev[l]->A.vals.p; };
+  for (int l = 0; l + 1 < L; ++l) {
+    AmgLevel &V = *D.lev[l];
+    double *x = V.x.p, *x2 = V.x2.p;
+    PHB_LAUNCH(c, k_amg_scale, grid_rows(c, V.n), kThreads, 0, V.n, V.w.p, bOf[l], x, S, s->maxIters);
+    for (int k = 1; k < D.nu; ++k) {
+      launch<2>(s, matPat(l), matVal(l), x, x2, bOf[l], V.w.p, inLoop);
+      std::swap(x, x2);
+    }
+    launch<1>(s, matPat(l), matVal(l), x, V.r.p, bOf[l], nullptr, inLoop);
+    launch<0>(s, V.R.pat, V.R.vals.p, V.r.p, D.lev[l + 1]->b.p, nullptr, nullptr, inLoop);
+    xOf[l] = x;
+  }
+  {
+    AmgLevel &V = *D.lev[L - 1];
+    double *x = V.x.p, *x2 = V.x2.p;
+    double *dst = L == 1 ? out : x;
+    if (D.denseCoarse) {
+      PHB_LAUNCH(c, k_amg_dense, (V.n + 7) / 8, 256, 0, V.n, D.coarseInv.p, bOf[L - 1], dst, S, s->maxIters);
+      xOf[L - 1] = dst;
+    } else {
+      PHB_LAUNCH(c, k_amg_scale, grid_rows(c, V.n), kThreads, 0, V.n, V.w.p, bOf[L - 1], x, S, s->maxIters);
+      for (int k = 0; k < kCoarseSweeps; ++k) {
+        double *y = (L == 1 && k == kCoarseSweeps - 1) ? out : x2;
+        launch<2>(s, matPat(L - 1), matVal(L - 1), x, y, bOf[L - 1], V.w.p, inLoop);
+        x2 = x; x = y;
+      }
+      xOf[L - 1] = x;
+    }
+  }
+  for (int l = L - 2; l >= 0; --l) {
+    AmgLevel &V = *D.lev[l];
+    double *x = xOf[l];
+    double *x2 = x == V.x.p ? V.x2.p : V.x.p;
+    launch<3>(s, V.P.pat, V.P.vals.p, xOf[l + 1], x, nullptr, nullptr, inLoop);
+    for (int k = 0; k < D.nu; ++k) {
+      double *y = (l == 0 && k == D.nu - 1) ? out : x2;
+      launch<2>(s, matPat(l), matVal(l), x, y, bOf[l], V.w.p, inLoop);
+      x2 = x; x = y;
+    }
+    xOf[l] = x;
+  }
+  return PHB_OK;
+}
+
+}  // namespace phb
+
+// ===================================================================== C ABI (inspection / tests)
+struct phb_amg_host {
+  HostHierarchy H;
+};
+
+extern "C" {
+
+int phb_amg_host_build(int n, const int *rowPtr, const int *colInd, const double *vals, double theta,
+                       int coarsest, phb_amg_host **out) {
+  PHB_TRY_BEGIN
+  PHB_REQUIRE(n > 0 && rowPtr && colInd && vals && out, "phb_amg_host_build: bad argument");
+  HCsr A;
+  A.n = A.m = n;
+  A.rp.assign(n + 1, 0);
+  std::vector<std::pair<int, double>> row;
+  for (int r = 0; r < n; ++r) {
+    row.clear();
+    for (int k = rowPtr[r]; k < rowPtr[r + 1]; ++k) {
+      if (colInd[k] < 0) continue;
+      PHB_REQUIRE(colInd[k] < n, "phb_amg_host_build: column %d out of range", colInd[k]);
+      row.push_back({colInd[k], vals[k]});
+    }
+    std::sort(row.begin(), row.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) {
+      return x.first < y.first;
+    });
+    for (auto &e : row) { A.ci.push_back(e.first); A.v.push_back(e.second); }
+    A.rp[r + 1] = (int)A.ci.size();
+  }
+  std::unique_ptr<phb_amg_host> h(new phb_amg_host());
+  PHB_CHECK(build_hierarchy(std::move(A), theta, coarsest > 0 ? coarsest : 400, 4. / 3., h->H));
+  *out = h.release();
+  return PHB_OK;
+  PHB_TRY_END
+}
+
+int phb_amg_host_levels(const phb_amg_host *h, int *nLevels, int *singular, int *denseCoarse) {
+  PHB_REQUIRE(h && nLevels, "phb_amg_host_levels: NULL argument");
+  *nLevels = (int)h->H.lev.size();
+  if (singular) *singular = h->H.singular ? 1 : 0;
+  if (denseCoarse) *denseCoarse = h->H.coarseInv.empty() ? 0 : 1;
+  return PHB_OK;
+}
+
+static const HCsr *pick(const phb_amg_host *h, int level, int which) {
+  if (level < 0 || level >= (int)h->H.lev.size()) return nullptr;
+  const HostLevel &L = h->H.lev[level];
+  const HCsr *M = which == 0 ? &L.A : which == 1 ? &L.P : which == 2 ? &L.R : nullptr;
+  if (M && which != 0 && level + 1 == (int)h->H.lev.size()) return nullptr;
+  return M;
+}
+
+int phb_amg_host_level_size(const phb_amg_host *h, int level, int which, int *nRows, int *nCols, long long *nnz,
+                            double *rho) {
+  PHB_REQUIRE(h && nRows && nCols && nnz, "phb_amg_host_level_size: NULL argument");
+  const HCsr *M = pick(h, level, which);
+  PHB_REQUIRE(M, "phb_amg_host_level_size: no matrix %d on level %d", which, level);
+  *nRows = M->n; *nCols = M->m; *nnz = M->nnz();
+  if (rho) *rho = h->H.lev[level].rho;
+  return PHB_OK;
+}
+
+int phb_amg_host_level_csr(const phb_amg_host *h, int level, int which, int *rowPtr, int *colInd, double *vals) {
+  PHB_REQUIRE(h && rowPtr && colInd && vals, "phb_amg_host_level_csr: NULL argument");
+  const HCsr *M = pick(h, level, which);
+  PHB_REQUIRE(M, "phb_amg_host_level_csr: no matrix %d on level %d", which, level);
+  std::copy(M->rp.begin(), M->rp.end(), rowPtr);
+  std::copy(M->ci.begin(), M->ci.end(), colInd);
+  std::copy(M->v.begin(), M->v.end(), vals);
+  return PHB_OK;
+}
+
+int phb_amg_host_coarse_inverse(const phb_amg_host *h, double *inv) {
+  PHB_REQUIRE(h && inv, "phb_amg_host_coarse_inverse: NULL argument");
+  PHB_REQUIRE(!h->H.coarseInv.empty(), "phb_amg_host_coarse_inverse: the coarsest level is not dense");
+  std::copy(h->H.coarseInv.begin(), h->H.coarseInv.end(), inv);
+  return PHB_OK;
+}
+
+int phb_amg_host_destroy(phb_amg_host *h) {
+  delete h;
+  return PHB_OK;
+}
+
+// [levels, operator complexity, setup ms (host), setups so far, coarsest rows, kernel launches per cycle,
+//  iterations of the first solve after the last setup, hierarchy currently stale (0/1)]
+int phb_solver_amg_info(const phb_solver *s, double out[8]) {
+  PHB_REQUIRE(s && out, "phb_solver_amg_info: NULL argument");
+  const AmgData &D = s->amg;
+  out[0] = (double)D.lev.size(); out[1] = D.opComplexity; out[2] = D.setupMs; out[3] = D.setups;
+  out[4] = D.nCoarse; out[5] = phb::amg_launches_per_apply(s); out[6] = D.itersAfterSetup; out[7] = D.stale ? 1. : 0.;
+  return PHB_OK;
+}
+
+}  // extern "C"

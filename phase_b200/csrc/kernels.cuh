@@ -94,4 +94,40 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], double *partials, u
   return false;
 }
 
+template <int NC, int W>
+__device__ __forceinline__ void slice_dot(const int *__restrict__ col, const double *__restrict__ vals,
+                                          size_t base, const double *__restrict__ x, int ld,
+                                          double (&acc)[NC]) {
+  int c[W];
+  double a[W];
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    c[k] = ld_stream(col + base + (size_t)k * 32);
+    a[k] = ld_stream(vals + base + (size_t)k * 32);
+  }
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) acc[i] = fma(a[k], __ldg(x + (size_t)i * ld + c[k]), acc[i]);
+  }
+}
+
+template <int NC>
+__device__ __forceinline__ void slice_dot_any(const int *__restrict__ col, const double *__restrict__ vals,
+                                              size_t base, int w, const double *__restrict__ x, int ld,
+                                              double (&acc)[NC]) {
+  switch (w) {
+    case 3: slice_dot<NC, 3>(col, vals, base, x, ld, acc); break;
+    case 4: slice_dot<NC, 4>(col, vals, base, x, ld, acc); break;
+    case 5: slice_dot<NC, 5>(col, vals, base, x, ld, acc); break;
+    case 6: slice_dot<NC, 6>(col, vals, base, x, ld, acc); break;
+    case 7: slice_dot<NC, 7>(col, vals, base, x, ld, acc); break;
+    default: {
+      int k = 0;
+      for (; k + 4 <= w; k += 4) slice_dot<NC, 4>(col, vals, base + (size_t)k * 32, x, ld, acc);
+      for (; k < w; ++k) slice_dot<NC, 1>(col, vals, base + (size_t)k * 32, x, ld, acc);
+    }
+  }
+}
+
 }  // namespace phb

@@ -25,50 +25,10 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kBlocksPerSM = 8;
 
-__device__ __forceinline__ bool krylov_done(const KrylovSums *S, int maxIters) {
-  return !(S->rr > S->thresh) || S->iters >= (double)maxIters;
-}
-
 // ------------------------------------------------------------------ SpMV
 // One warp per 32-row slice, lane <-> row: every load of col/vals is a fully
 // coalesced 128 B / 256 B warp transaction; x is gathered through L1/L2 (banded
 // matrices keep the window resident).  NC components share the coefficients.
-template <int NC, int W>
-__device__ __forceinline__ void slice_dot(const int *__restrict__ col, const double *__restrict__ vals,
-                                          size_t base, const double *__restrict__ x, int ld,
-                                          double (&acc)[NC]) {
-  int c[W];
-  double a[W];
-#pragma unroll
-  for (int k = 0; k < W; ++k) {
-    c[k] = ld_stream(col + base + (size_t)k * 32);
-    a[k] = ld_stream(vals + base + (size_t)k * 32);
-  }
-#pragma unroll
-  for (int k = 0; k < W; ++k) {
-#pragma unroll
-    for (int i = 0; i < NC; ++i) acc[i] = fma(a[k], __ldg(x + (size_t)i * ld + c[k]), acc[i]);
-  }
-}
-
-template <int NC>
-__device__ __forceinline__ void slice_dot_any(const int *__restrict__ col, const double *__restrict__ vals,
-                                              size_t base, int w, const double *__restrict__ x, int ld,
-                                              double (&acc)[NC]) {
-  switch (w) {
-    case 3: slice_dot<NC, 3>(col, vals, base, x, ld, acc); break;
-    case 4: slice_dot<NC, 4>(col, vals, base, x, ld, acc); break;
-    case 5: slice_dot<NC, 5>(col, vals, base, x, ld, acc); break;
-    case 6: slice_dot<NC, 6>(col, vals, base, x, ld, acc); break;
-    case 7: slice_dot<NC, 7>(col, vals, base, x, ld, acc); break;
-    default: {
-      int k = 0;
-      for (; k + 4 <= w; k += 4) slice_dot<NC, 4>(col, vals, base + (size_t)k * 32, x, ld, acc);
-      for (; k < w; ++k) slice_dot<NC, 1>(col, vals, base + (size_t)k * 32, x, ld, acc);
-    }
-  }
-}
-
 // EPI 0: y = A x
 // EPI 1: y = A x, sigma = (w . y)                       [v = A p, (rhat . v)]
 // EPI 2: y = A x, ts,tt,rs,rt,ss = (y.w),(y.y),(w2.w),(w2.y),(w.w)   [t = A M^-1 s; w = s, w2 = rhat]
@@ -293,16 +253,6 @@ __global__ void k_scatter_vals(long long nnz, const int *__restrict__ csr2slot,
   }
 }
 
-SellView view_of(const SellPattern *P) {
-  SellView v;
-  v.sliceOff = P->sliceOff.p;
-  v.col = P->col.p;
-  v.nRows = P->nRows;
-  v.nSlices = P->nSlices;
-  v.nCols = P->nCols;
-  return v;
-}
-
 int grid_for(const phb_ctx *c, long long work) {
   long long g = (work + kThreads - 1) / kThreads;
   const long long cap = (long long)c->numSMs * kBlocksPerSM;
@@ -396,9 +346,10 @@ int enqueue_iteration(phb_solver *s, const double *A, int cur) {
   phb_ctx *c = s->ctx;
   const int n = s->pat->nRows, ld = s->ld;
   const int gv = grid_for(c, n);
-  const bool ilu = s->precond == PHB_PC_ILU0;
+  const bool amg = s->precond == PHB_PC_AMG;
+  const bool ilu = s->precond == PHB_PC_ILU0 || amg;   // explicit preconditioner: p^ = M^-1 p, s^ = M^-1 s
   const bool multi = c->nProcs > 1;
-  const bool fused = multi && use_peer(s) && s->peerFused;   // exchanges ride inside the compute kernels
+  const bool fused = multi && use_peer(s) && s->peerFused && !amg;   // exchanges ride inside the compute kernels
   double *ph = ilu ? s->ph.p : s->p.p, *sh = ilu ? s->sh.p : s->s.p;
   PeerFuse none, fPushP, fSpmv1, fUpdS, fSpmv2, fPushPh, fPushSh;
   if (fused) {
@@ -415,7 +366,8 @@ int enqueue_iteration(phb_solver *s, const double *A, int cur) {
   if (s->nComp == 1) { if (ilu) FUSED(1, true); else FUSED(1, false); }
   else { if (ilu) FUSED(2, true); else FUSED(2, false); }
 #undef FUSED
-  if (ilu) PHB_CHECK(ilu_apply(s, s->p.p, ph, fused ? &fPushPh : nullptr));   // ph = M^-1 p
+  if (amg) PHB_CHECK(amg_apply(s, s->p.p, ph, true));
+  else if (ilu) PHB_CHECK(ilu_apply(s, s->p.p, ph, fused ? &fPushPh : nullptr));   // ph = M^-1 p
   if (!fused) PHB_CHECK(halo_exchange(s, ph, true));
   launch_spmv<1>(s, A, ph, s->v.p, s->rhat.p, nullptr, cur, 0, fused ? fSpmv1 : none);   // v = A ph, R1
   if (!fused) PHB_CHECK(reduce_sums(s, 0, &s->sums.p->sigma, 1, true, 0, cur));
@@ -425,7 +377,8 @@ int enqueue_iteration(phb_solver *s, const double *A, int cur) {
   else
     PHB_LAUNCH(c, k_update_s<2>, gv, kThreads, 0, n, ld, s->r.p, s->v.p, s->s.p, s->sums.p, cur, s->maxIters,
                fused ? fUpdS : none, s->ticket.p);
-  if (ilu) PHB_CHECK(ilu_apply(s, s->s.p, sh, fused ? &fPushSh : nullptr));   // sh = M^-1 s
+  if (amg) PHB_CHECK(amg_apply(s, s->s.p, sh, true));
+  else if (ilu) PHB_CHECK(ilu_apply(s, s->s.p, sh, fused ? &fPushSh : nullptr));   // sh = M^-1 s
   if (!fused) PHB_CHECK(halo_exchange(s, sh, true));
   // t = A sh, R2: (t.s), (t.t), (rhat.s), (rhat.t), (s.s); single GPU: the last CTA finishes the iteration
   launch_spmv<2>(s, A, sh, s->t.p, s->s.p, s->rhat.p, cur, multi ? 0 : 1, fused ? fSpmv2 : none);
@@ -527,6 +480,14 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
     s->runPat = &s->ilu.pat;
     s->runSendDev = s->ilu.sendDev.p;
   }
+  // ---- AMG: V-cycle on the natural ordering, hierarchy cached across solves
+  if (s->precond == PHB_PC_AMG) {
+    PHB_CHECK(amg_prepare(s));
+    const size_t len = (size_t)ld * s->nComp;
+    if (s->ph.owned) { PHB_CHECK(s->ph.alloc(len)); PHB_CHECK(s->sh.alloc(len)); }
+    PHB_CUDA(cudaMemsetAsync(s->ph.p, 0, len * sizeof(double), c->stream));
+    PHB_CUDA(cudaMemsetAsync(s->sh.p, 0, len * sizeof(double), c->stream));
+  }
   // ---- Jacobi fold: iterate on y = D x with A D^-1
   if (s->precond == PHB_PC_JACOBI) {
     PHB_CHECK(s->dinv.alloc((size_t)ld));
@@ -569,7 +530,9 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
     const int saveMax = s->maxIters;
     s->maxIters = budget;  // kernels count iterations of this attempt
     // ---- iterations: graphs of K iterations, polled every `burst` graphs
-    const int K = std::max(2, s->itersPerGraph & ~1);
+    // AMG converges in tens of iterations: short graphs, polled every time
+    const bool amg = s->precond == PHB_PC_AMG;
+    const int K = amg ? 2 : std::max(2, s->itersPerGraph & ~1);
     bool graphOk = s->useGraph;
     const void *key[4] = {s->runPat, Aw,
                           (const void *)(intptr_t)(s->nComp * 1000003 + s->maxIters + 7919 * s->precond), s->halo};
@@ -592,7 +555,8 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
       memcpy(s->graphKey, key, sizeof(key));
     }
     const int launchesPerIter = 4 + ((s->halo && c->nProcs > 1) ? (use_peer(s) ? (s->peerFused ? 1 : 4) : 3) : 0) +
-                                (s->precond == PHB_PC_ILU0 ? 2 * ilu_launches_per_apply(s) : 0);
+                                (s->precond == PHB_PC_ILU0 ? 2 * ilu_launches_per_apply(s) : 0) +
+                                (amg ? 2 * amg_launches_per_apply(s) : 0);
     int launched = 0, burst = 1;
     bool done = false;
     while (!done && launched < budget) {
@@ -608,12 +572,13 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
       PHB_CUDA(cudaMemcpyAsync(hs, s->sums.p, sizeof(KrylovSums), cudaMemcpyDeviceToHost, c->stream));
       PHB_CUDA(cudaStreamSynchronize(c->stream));
       done = !(hs->rr > hs->thresh) || hs->iters >= (double)budget;
-      burst = std::min(burst * 2, 8);
+      burst = amg ? 1 : std::min(burst * 2, 8);
     }
     // the x-update of the last completed iteration is still pending (it rides in the NEXT fused update)
     {
-      const double *ph = s->precond == PHB_PC_ILU0 ? s->ph.p : s->p.p;
-      const double *sh = s->precond == PHB_PC_ILU0 ? s->sh.p : s->s.p;
+      const bool pre = s->precond == PHB_PC_ILU0 || s->precond == PHB_PC_AMG;
+      const double *ph = pre ? s->ph.p : s->p.p;
+      const double *sh = pre ? s->sh.p : s->s.p;
       if (s->nComp == 1) PHB_LAUNCH(c, k_final_x<1>, gv, kThreads, 0, n, ld, s->x.p, ph, sh, s->sums.p);
       else PHB_LAUNCH(c, k_final_x<2>, gv, kThreads, 0, n, ld, s->x.p, ph, sh, s->sums.p);
     }
@@ -651,6 +616,7 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
   s->runSendDev = nullptr;
   s->lastIters = totalIters;
   s->lastRelres = rel;
+  if (s->precond == PHB_PC_AMG) amg_record_iters(s, totalIters);
   if (iters) *iters = totalIters;
   if (relres) *relres = rel;
   return PHB_OK;
@@ -698,11 +664,28 @@ int phb_solver_setup(phb_solver *s, const char *key, const char *value) {
     if (lv == "none") s->precond = PHB_PC_NONE;
     else if (lv == "jacobi" || lv == "diagonal") s->precond = PHB_PC_JACOBI;
     else if (lv == "ilu0" || lv == "riluk" || lv == "schwarz" || lv == "ilu") s->precond = PHB_PC_ILU0;
+    else if (lv == "amg" || lv == "muelu" || lv == "sa" || lv == "multigrid") s->precond = PHB_PC_AMG;
     else PHB_REQUIRE(false, "unknown preconditioner \"%s\"", value);
   } else if (k == "ordering" || k == "iluOrdering") {
     if (lv == "multicolor" || lv == "multicolour" || lv == "colour" || lv == "color") s->iluOrdering = 0;
     else if (lv == "levels" || lv == "natural" || lv == "wavefront") s->iluOrdering = 1;
     else PHB_REQUIRE(false, "unknown ILU ordering \"%s\" (multicolor | levels)", value);
+  } else if (k == "amgTheta") {
+    s->amg.theta = std::stod(v); s->amg.built = false;
+    PHB_REQUIRE(s->amg.theta >= 0. && s->amg.theta < 1., "amgTheta must lie in [0, 1)");
+  } else if (k == "amgCoarsest") {
+    s->amg.coarsest = std::stoi(v); s->amg.built = false;
+    PHB_REQUIRE(s->amg.coarsest >= 1, "amgCoarsest must be positive");
+  } else if (k == "amgSweeps") {
+    s->amg.nu = std::stoi(v);
+    PHB_REQUIRE(s->amg.nu >= 1 && s->amg.nu <= 4, "amgSweeps must lie in 1..4");
+    if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
+  } else if (k == "amgSmootherWeight") {
+    s->amg.omegaS = std::stod(v); s->amg.built = false;
+    PHB_REQUIRE(s->amg.omegaS > 0. && s->amg.omegaS < 2., "amgSmootherWeight must lie in (0, 2)");
+  } else if (k == "amgRebuild") {
+    PHB_REQUIRE(lv == "auto" || lv == "always", "amgRebuild must be \"auto\" or \"always\"");
+    s->amg.rebuildAlways = lv == "always";
   } else if (k == "peerFusion") {
     s->peerFused = std::stoi(v) != 0;
     if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
@@ -941,9 +924,11 @@ int phb_solver_bytes(const phb_solver *s, double out[2]) {
   const double nnz = (double)s->pat->nnz, n = (double)s->pat->nRows, nc = s->nComp;
   out[0] = 12. * nnz + 4. * (n + 1.) + 16. * n * nc;
   // ILU(0) apply: L and U sweeps over the pattern once, 12 nnz + 8 (n+1) + 8 n + 32 n nc
-  const double prec = s->precond == PHB_PC_ILU0 ? 12. * nnz + 8. * (n + 1.) + 8. * n + 32. * n * nc : 0.;
+  const double prec = s->precond == PHB_PC_ILU0 ? 12. * nnz + 8. * (n + 1.) + 8. * n + 32. * n * nc
+                      : s->precond == PHB_PC_AMG ? phb::amg_cycle_bytes(s) : 0.;
   // vector passes: fused update 64 n (80 n with a separate preconditioned image) + s-update 24 n, per component
-  out[1] = 2. * out[0] + 2. * prec + (s->precond == PHB_PC_ILU0 ? 104. : 88.) * n * nc;
+  const bool pre = s->precond == PHB_PC_ILU0 || s->precond == PHB_PC_AMG;
+  out[1] = 2. * out[0] + 2. * prec + (pre ? 104. : 88.) * n * nc;
   return PHB_OK;
 }
 

@@ -1,5 +1,6 @@
 // solver.cuh -- internal definition of phb_solver.
 #pragma once
+#include "kernels.cuh"
 #include "peerdev.cuh"
 #include "structs.cuh"
 
@@ -35,6 +36,20 @@ __host__ __device__ inline void krylov_finish(KrylovSums *S, int cur) {
   S->iters += 1.;
 }
 
+__device__ __forceinline__ bool krylov_done(const KrylovSums *S, int maxIters) {
+  return !(S->rr > S->thresh) || S->iters >= (double)maxIters;
+}
+
+inline phb::SellView view_of(const SellPattern *P) {
+  phb::SellView v;
+  v.sliceOff = P->sliceOff.p;
+  v.col = P->col.p;
+  v.nRows = P->nRows;
+  v.nSlices = P->nSlices;
+  v.nCols = P->nCols;
+  return v;
+}
+
 // ILU(0): permuted pattern + factors (ilu.cu)
 struct IluData {
   const SellPattern *src = nullptr;
@@ -46,6 +61,27 @@ struct IluData {
   phb::DevBuf<int> slotMap, diagK, blockOf, new2old, sendDev;
   phb::DevBuf<signed char> kind;   // per slot: 0 pad/ghost, 1 lower, 2 diagonal, 3 upper
   phb::DevBuf<double> vals, lu;
+};
+
+// smoothed-aggregation AMG hierarchy (amg.cu)
+struct AmgMat {
+  SellPattern pat;
+  phb::DevBuf<double> vals;
+};
+struct AmgLevel {
+  int n = 0;
+  AmgMat A, P, R;                  // level operator (levels >= 1), prolongator n x n_c, restriction n_c x n
+  phb::DevBuf<double> w;           // smoother weight omega / a_ii
+  phb::DevBuf<double> x, x2, b, r;
+};
+constexpr int kCoarseSweeps = 8;   // Jacobi sweeps on a coarsest level too large for a dense inverse
+struct AmgData {
+  std::vector<std::unique_ptr<AmgLevel>> lev;
+  phb::DevBuf<double> coarseInv, refVals, chk;
+  const SellPattern *src = nullptr;
+  bool built = false, denseCoarse = false, stale = false, rebuildAlways = false;
+  int nCoarse = 0, nu = 1, coarsest = 400, setups = 0, itersAfterSetup = -1;
+  double theta = 0., omegaS = 4. / 3., setupMs = 0., opComplexity = 1.;
 };
 
 struct phb_solver {
@@ -74,6 +110,7 @@ struct phb_solver {
   phb::DevBuf<double> scaled, dinv;
   IluData ilu;
   int iluOrdering = 0;             // 0 multicolour, 1 wavefront levels of the given ordering
+  AmgData amg;
   phb::DevBuf<double> ph, sh;      // M^-1 p, M^-1 s (ILU only; alias p, s otherwise)
   // run-time view of the system being iterated on (permuted when ILU is active)
   const SellPattern *runPat = nullptr;
@@ -109,4 +146,9 @@ int ilu_factor(phb_solver *s, const double *vals);
 int ilu_apply(phb_solver *s, const double *r, double *z, const PeerFuse *pushHalo = nullptr);
 int ilu_permute(phb_solver *s, const double *x, double *y, int dir);
 int ilu_launches_per_apply(const phb_solver *s);
+int amg_prepare(phb_solver *s);
+int amg_apply(phb_solver *s, const double *in, double *out, bool inLoop);
+int amg_launches_per_apply(const phb_solver *s);
+void amg_record_iters(phb_solver *s, int iters);
+double amg_cycle_bytes(const phb_solver *s);
 }  // namespace phb

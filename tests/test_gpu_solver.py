@@ -170,3 +170,69 @@ def test_variable_coefficient_iteration_counts_match_oracle(comm):
     assert s.error() <= 1e-10 and rel_l2(s.x(), xd) < 1e-6 and rel_l2(xo, xd) < 1e-6
     assert abs(s.nIters() - ito) <= max(10, ito // 2), (s.nIters(), ito)
     s.close()
+
+
+# ------------------------------------------------------------------ smoothed-aggregation AMG (`preconditioner amg`)
+@pytest.mark.parametrize("kind,nx,ny,coarsest", [("rect", 48, 40, 40), ("tri", 30, 26, 40), ("rect", 12, 9, 400)])
+def test_amg_vs_direct(comm, kind, nx, ny, coarsest):
+    from phase_b200.api import SparseMatrixSolver
+    rp, ci, va, b = poisson_system(kind, nx, ny)
+    xd = O.direct_solve(rp, ci, va, b)
+    s = SparseMatrixSolver(comm).setup(dict(solver="BICGSTAB", maxIters=200, tolerance=1e-11, preconditioner="amg",
+                                            amgCoarsest=coarsest))
+    s.setRank(len(b))
+    s.set(rp, ci, va)
+    s.setRhs(b)
+    err = s.solve()
+    info = s.amgInfo()
+    assert err <= 1e-11 and 0 < s.nIters() <= 30, (s.nIters(), info)
+    assert info["levels"] >= (3 if coarsest == 40 else 1) and info["setups"] == 1
+    assert rel_l2(s.x(), xd) < 1e-8
+    # scaled matrix (a time-step change): hierarchy kept, still converges; new values: kept until iterations degrade
+    s.set(rp, ci, 3.0 * va)
+    s.setRhs(3.0 * b)
+    s.solve()
+    assert s.amgInfo()["setups"] == 1 and s.amgInfo()["stale"] == 0 and rel_l2(s.x(), xd) < 1e-8
+    s.close()
+
+
+def test_amg_fewer_iterations_than_ilu0(comm):
+    from phase_b200.api import SparseMatrixSolver
+    rp, ci, va, b = poisson_system("rect", 128, 128)
+    its = {}
+    for pc in ("ilu0", "amg"):
+        s = SparseMatrixSolver(comm).setup(dict(maxIters=5000, tolerance=1e-9, preconditioner=pc))
+        s.set(rp, ci, va)
+        s.setRhs(b)
+        s.solve()
+        its[pc] = s.nIters()
+        x = s.x()
+        A = O.csr_to_scipy(rp, ci, va)
+        assert np.linalg.norm(b - A @ x) <= 1.01e-9 * np.linalg.norm(b)
+        s.close()
+    assert its["amg"] <= 20 and its["amg"] * 4 < its["ilu0"], its
+
+
+def test_amg_singular_neumann_system(comm):
+    from phase_b200.api import SparseMatrixSolver
+    rp, ci, va, b = poisson_system("rect", 64, 48, fixed_top=False)
+    s = SparseMatrixSolver(comm).setup(dict(maxIters=200, tolerance=1e-10, preconditioner="amg", amgCoarsest=30,
+                                            nullSpace="constant"))
+    s.set(rp, ci, va)
+    s.setRhs(b)                                  # 1^T b removed by the solver
+    s.solve()
+    assert s.nIters() <= 30
+    bc = b - b.mean()
+    x, xd = s.x(), O.direct_solve(rp, ci, va, bc)
+    assert rel_l2(x - x.mean(), xd - xd.mean()) < 1e-7
+    s.close()
+
+
+def test_amg_rejects_vector_equations_loudly(comm):
+    from phase_b200.api import FiniteVolumeGrid2D, lid_driven_cavity, PhaseB200Error
+    g = FiniteVolumeGrid2D.rectilinear(comm, 8, 8, 1.0, 1.0)
+    fs = lid_driven_cavity(g, solver=dict(preconditioner="amg"))
+    with pytest.raises(PhaseB200Error):
+        fs.solve(1e-3)
+    fs.close()
+    g.close()

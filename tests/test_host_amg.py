@@ -1,0 +1,176 @@
+"""CPU checks of the smoothed-aggregation setup behind `preconditioner amg` (phase_b200/csrc/amg.cu).
+
+The hierarchy is built on the host, so everything but the device cycle can be verified here: aggregates cover
+every row, R = P^T, the coarse operators are the Galerkin products R A P, the constant is reproduced by P
+(singular all-Neumann systems) and a scipy transcription of the V(1,1) cycle preconditions BiCGStab into tens of
+iterations, independent of the mesh size."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from phase_b200 import _capi
+
+
+def neumann_laplacian(nx, ny, fixed_left=False, sign=-1.0):
+    def d1(n):
+        e = np.ones(n)
+        T = sp.diags([-e[:-1], 2 * e, -e[:-1]], [-1, 0, 1]).tolil()
+        T[0, 0] = 1
+        T[n - 1, n - 1] = 1
+        return T.tocsr()
+    A = (sp.kron(sp.eye(ny), d1(nx)) + sp.kron(d1(ny), sp.eye(nx))).tocsr()
+    if fixed_left:
+        d = np.zeros(nx * ny)
+        d[::nx] = 2.0
+        A = (A + sp.diags(d)).tocsr()
+    return (sign * A).tocsr()
+
+
+class HostAmg:
+    def __init__(self, A, theta=0.0, coarsest=400):
+        self.L = _capi.lib()
+        A = A.tocsr()
+        A.sort_indices()
+        rp = A.indptr.astype(np.int32)
+        ci = A.indices.astype(np.int32)
+        v = A.data.astype(np.float64)
+        h = C.c_void_p()
+        rc = self.L.phb_amg_host_build(A.shape[0], rp.ctypes.data_as(_capi.pi), ci.ctypes.data_as(_capi.pi),
+                                       v.ctypes.data_as(_capi.pd), theta, coarsest, C.byref(h))
+        assert rc == 0, self.L.phb_last_error()
+        self.h = h
+        n, s, d = C.c_int(), C.c_int(), C.c_int()
+        assert self.L.phb_amg_host_levels(h, C.byref(n), C.byref(s), C.byref(d)) == 0
+        self.nLevels, self.singular, self.dense = n.value, bool(s.value), bool(d.value)
+
+    def mat(self, level, which):
+        nr, nc, nnz, rho = C.c_int(), C.c_int(), C.c_longlong(), C.c_double()
+        rc = self.L.phb_amg_host_level_size(self.h, level, which, C.byref(nr), C.byref(nc), C.byref(nnz), C.byref(rho))
+        assert rc == 0, self.L.phb_last_error()
+        rp = np.zeros(nr.value + 1, np.int32)
+        ci = np.zeros(nnz.value, np.int32)
+        v = np.zeros(nnz.value)
+        rc = self.L.phb_amg_host_level_csr(self.h, level, which, rp.ctypes.data_as(_capi.pi),
+                                           ci.ctypes.data_as(_capi.pi), v.ctypes.data_as(_capi.pd))
+        assert rc == 0
+        return sp.csr_matrix((v, ci, rp), shape=(nr.value, nc.value)), rho.value
+
+    def coarse_inverse(self):
+        n = self.mat(self.nLevels - 1, 0)[0].shape[0]
+        inv = np.zeros((n, n))
+        assert self.L.phb_amg_host_coarse_inverse(self.h, inv.ctypes.data_as(_capi.pd)) == 0
+        return inv
+
+    def cycle(self, nu=1, omega_s=4.0 / 3.0):
+        """scipy transcription of amg_apply() (amg.cu)"""
+        lv = []
+        for l in range(self.nLevels):
+            A, rho = self.mat(l, 0)
+            e = dict(A=A, w=(omega_s / rho) / A.diagonal())
+            if l + 1 < self.nLevels:
+                e["P"] = self.mat(l, 1)[0]
+                e["R"] = self.mat(l, 2)[0]
+            lv.append(e)
+        inv = self.coarse_inverse()
+
+        def cyc(l, b):
+            L = lv[l]
+            if l == self.nLevels - 1:
+                return inv @ b
+            x = L["w"] * b
+            for _ in range(nu - 1):
+                x = x + L["w"] * (b - L["A"] @ x)
+            x = x + L["P"] @ cyc(l + 1, L["R"] @ (b - L["A"] @ x))
+            for _ in range(nu):
+                x = x + L["w"] * (b - L["A"] @ x)
+            return x
+        return lambda b: cyc(0, b)
+
+    def close(self):
+        self.L.phb_amg_host_destroy(self.h)
+
+
+def bicgstab_iters(A, M, b, tol=1e-8):
+    its = [0]
+
+    def cb(_):
+        its[0] += 1
+    x, info = spla.bicgstab(A, b, rtol=tol, atol=0, M=spla.LinearOperator(A.shape, matvec=M), callback=cb, maxiter=200)
+    assert info == 0
+    return its[0], np.linalg.norm(b - A @ x) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("fixed", [False, True])
+def test_hierarchy_is_galerkin(fixed):
+    A = neumann_laplacian(60, 50, fixed_left=fixed)
+    H = HostAmg(A, coarsest=50)
+    assert H.nLevels >= 3 and H.dense
+    assert H.singular == (not fixed)
+    A0, _ = H.mat(0, 0)
+    assert abs(A0 - A).max() == 0.0
+    prev = A0
+    for l in range(H.nLevels - 1):
+        P, _ = H.mat(l, 1)
+        R, _ = H.mat(l, 2)
+        Ac, _ = H.mat(l + 1, 0)
+        assert P.shape == (prev.shape[0], Ac.shape[0])
+        assert abs(R - P.T).max() == 0.0
+        G = (R @ prev @ P).tocsr()
+        assert abs(G - Ac).max() <= 1e-12 * abs(Ac).max()
+        assert Ac.shape[0] < 0.5 * prev.shape[0]                      # coarsening does coarsen
+        assert np.all(np.diff(P.indptr) >= 1)                         # every row belongs to an aggregate
+        if not fixed:                                                 # constant reproduced level by level
+            assert np.abs(P @ np.ones(P.shape[1]) - 1.0).max() < 1e-12
+            assert np.abs(Ac @ np.ones(Ac.shape[0])).max() < 1e-10 * abs(Ac).max()
+        prev = Ac
+    H.close()
+
+
+def test_cycle_preconditions_bicgstab_mesh_independently():
+    rng = np.random.default_rng(0)
+    counts = []
+    for n in (64, 128, 256):
+        A = neumann_laplacian(n, n)
+        H = HostAmg(A)
+        b = rng.standard_normal(n * n)
+        b -= b.mean()
+        its, rel = bicgstab_iters(A, H.cycle(), b)
+        assert rel < 2e-8
+        counts.append(its)
+        H.close()
+    assert max(counts) <= 20, counts
+
+
+def test_variable_coefficient_and_threshold():
+    """density ratio 815 (config 4's pEqn): both theta = 0 and the classical 0.08 give a usable hierarchy"""
+    nx, ny = 96, 192
+    x = (np.arange(nx) + .5) / nx
+    y = 2 * (np.arange(ny) + .5) / ny
+    X, Y = np.meshgrid(x, y)
+    rho = np.where(((X - .5) ** 2 + (Y - .5) ** 2 < .125 ** 2) | (Y > 1.5), 1.225, 998.).ravel()
+    idx = np.arange(nx * ny).reshape(ny, nx)
+    A = sp.csr_matrix((nx * ny, nx * ny))
+    for a, b in ((idx[:, :-1].ravel(), idx[:, 1:].ravel()), (idx[:-1, :].ravel(), idx[1:, :].ravel())):
+        w = 1. / (0.5 * (rho[a] + rho[b]))
+        A = A + sp.coo_matrix((np.r_[-w, -w, w, w], (np.r_[a, b, a, b], np.r_[b, a, a, b])), shape=A.shape)
+    d = np.zeros(nx * ny)
+    d[idx[-1, :]] = 2. / rho[idx[-1, :]]
+    A = (A + sp.diags(d)).tocsr()
+    b = np.random.default_rng(1).standard_normal(nx * ny)
+    for theta in (0.0, 0.08):
+        H = HostAmg(A, theta=theta)
+        assert not H.singular
+        its, rel = bicgstab_iters(A, H.cycle(), b)
+        assert rel < 2e-8 and its <= 30, (theta, its)
+        H.close()
+
+
+def test_tiny_matrix_is_one_dense_level():
+    A = neumann_laplacian(6, 5, fixed_left=True)
+    H = HostAmg(A)
+    assert H.nLevels == 1 and H.dense
+    assert np.abs(H.coarse_inverse() @ A.toarray() - np.eye(30)).max() < 1e-10
+    H.close()

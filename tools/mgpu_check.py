@@ -52,8 +52,11 @@ def main():
             dist.all_gather_object(out, obj)
             return out
         comm.enable_peer_memory(gl, all_gather)
-    fs = lid_driven_cavity(gl, 1.0, 0.1, solver=dict(tolerance=1e-11, maxIters=50000, preconditioner=a.precond,
-                                                     peerFusion=1 if a.fused else 0))
+    amg = a.precond == "amg"      # scalar systems only: pEqn_ gets the V-cycle, uEqn_ keeps ILU(0)
+    fs = lid_driven_cavity(gl, 1.0, 0.1, solver=dict(tolerance=1e-11, maxIters=50000,
+                                                     preconditioner="ilu0" if amg else a.precond,
+                                                     peerFusion=1 if a.fused else 0),
+                           pSolver=dict(preconditioner="amg", amgCoarsest=40) if amg else None)
     om = (O.Mesh.rectilinear if a.kind == "rect" else O.Mesh.triangulated)(a.nx, a.ny, 1.0, 1.0)
     ofs = O.cavity(om, 1.0, 0.1)
     ofs.use_direct_solver()
