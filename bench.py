@@ -204,7 +204,7 @@ def workload_config(args, nprocs):
                         "FractionalStep time step (the snapshot's PISO successor), dt = 0.5 h (maxCo 0.5), "
                         "BiCGStab + %s, tolerance %g on ||r||/||b||, warm start from the previous step"
                         % (gx, gy, gx * gy, "" if strong or nprocs == 1 else " (%dx%d per GPU)" % (args.n, args.n),
-                           "smoothed-aggregation AMG V(1,1) on pEqn_ / ILU(0) on uEqn_" if args.precond == "amg"
+                           "smoothed-aggregation AMG V(1,1) on pEqn_ / %s on uEqn_" % getattr(args, "u_precond", "ilu0") if args.precond == "amg"
                            else args.precond, args.tol),
             "cells_per_gpu": gx * gy // nprocs, "global_cells": gx * gy,
             "partition": "none" if nprocs == 1 else "%dx%d blocks of %dx%d cells, one per GPU (global grid %dx%d)" % (
@@ -228,7 +228,8 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--max-iters", type=int, default=20000)
     ap.add_argument("--precond", default="ilu0", choices=["ilu0", "jacobi", "none", "amg"],
-                    help="amg = smoothed-aggregation V-cycle on pEqn_ (uEqn_ keeps ILU(0))")
+                    help="amg = smoothed-aggregation V-cycle on pEqn_; uEqn_ per --u-precond")
+    ap.add_argument("--u-precond", default="ilu0", choices=["ilu0", "amg"], help="uEqn_ preconditioner when --precond amg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--mesh", default="quad", choices=["quad", "tri"],
                     help="quad: side x side quads; tri: the same cell count as triangles (each quad of a "
@@ -286,7 +287,7 @@ def main():
         comm.enable_peer_memory(grid, all_gather)
     amg = args.precond == "amg"
     cfg = dict(solver="BICGSTAB", maxIters=args.max_iters, tolerance=args.tol,
-               preconditioner="ilu0" if amg else args.precond, peerFusion=1 if args.comm == "peer-fused" else 0)
+               preconditioner=args.u_precond if amg else args.precond, peerFusion=1 if args.comm == "peer-fused" else 0)
     fs = lid_driven_cavity(grid, 1.0, 0.1, solver=cfg, pSolver=dict(preconditioner="amg") if amg else None)
     fs.setup(guessOrder=args.guess_order)
     dt = 0.5 / nx                                            # maxCo 0.5 with the unit lid speed, h = 1/nx
@@ -364,11 +365,9 @@ def main():
         fs.p.set("cells", host["pc"].numpy()); fs.p.set("faces", host["pf"].numpy())
         fs.gradP.set("cells", host["gc"].numpy())
         st = fs.solve(dt)
-        host["uc"].numpy()[:] = fs.u.get("cells").reshape(-1)
-        host["pc"].numpy()[:] = fs.p.get("cells").reshape(-1)
-        host["uf"].numpy()[:] = fs.u.get("faces").reshape(-1)
-        host["pf"].numpy()[:] = fs.p.get("faces").reshape(-1)
-        host["gc"].numpy()[:] = fs.gradP.get("cells").reshape(-1)
+        fs.u.get("cells", out=host["uc"].numpy()); fs.p.get("cells", out=host["pc"].numpy())
+        fs.u.get("faces", out=host["uf"].numpy()); fs.p.get("faces", out=host["pf"].numpy())
+        fs.gradP.get("cells", out=host["gc"].numpy())
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     if world > 1:
@@ -385,7 +384,7 @@ def main():
         rp, ci, va, rhs = fs.assembleP(dt).export(1)      # reference layout: ELL-5 padded, nb before diagonal
         b = -rhs
         s1 = SparseMatrixSolver(comm).setup(cfg)
-        s1.setup(dict(nullSpace="constant"))
+        s1.setup(dict(nullSpace="constant", preconditioner=args.precond))
         s1.setRank(len(b)); s1.set(rp, ci, va); s1.setRhs(b); s1.solve()   # warm-up: pattern analysis, graph capture
         t0 = time.perf_counter()
         s1.setRank(len(b)); s1.set(rp, ci, va); s1.setRhs(b); s1.solve(); xs = s1.x()
@@ -423,6 +422,7 @@ def main():
             "e2e_seam1": seam1, "gpu_launches": int(launches), "clocks": clocks}
     if amg:
         line["amg"] = fs.pEqn.solver.amgInfo()
+        line["amg"]["uEqn"] = fs.uEqn.solver.amgInfo() if args.u_precond == "amg" else "ilu0"
         line["amg"]["note"] = ("hierarchy built on the host in the first (warm-up) solve and reused: pEqn_ = laplacian(dt, p) "
                                "is constant up to the scalar dt; setupMs is that one-off cost, outside the timed steps")
     if not args.no_cpu and world == 1:

@@ -314,9 +314,13 @@ class FiniteVolumeField:
         v = np.ascontiguousarray(v, np.float64).reshape(-1)
         check(self.L.phb_field_set(self.h, part.encode(), _dp(v), len(v)))
 
-    def get(self, part):
-        out = np.zeros(self._len(part), np.float64)
-        check(self.L.phb_field_get(self.h, part.encode(), _dp(out), len(out)))
+    def get(self, part, out=None):
+        """`out`: caller's buffer (e.g. pinned host memory) to receive the values instead of a new array"""
+        if out is None:
+            out = np.zeros(self._len(part), np.float64)
+        else:
+            assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == self._len(part)
+        check(self.L.phb_field_get(self.h, part.encode(), _dp(out), out.size))
         return out.reshape(self.nComp, -1) if self.nComp > 1 else out
 
     def fill(self, vx, vy=0.0):

@@ -382,10 +382,12 @@ constexpr int kBlocksPerSM = 8;
 // MODE 0: y = M x          MODE 1: y = b - M x
 // MODE 2: y = x + w (b - M x)   (damped Jacobi, out of place; w = omega / a_ii)
 // MODE 3: y += M x
-template <int MODE>
+// NC components share the coefficients; x has leading dimension ldx, y and b have ldy.
+template <int MODE, int NC>
 __global__ void __launch_bounds__(kThreads)
-k_amg_spmv(SellView M, const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-           const double *__restrict__ b, const double *__restrict__ w, const KrylovSums *S, int maxIters) {
+k_amg_spmv(SellView M, const double *__restrict__ vals, const double *__restrict__ x, int ldx,
+           double *__restrict__ y, int ldy, const double *__restrict__ b, const double *__restrict__ w,
+           const KrylovSums *S, int maxIters) {
   if (S && krylov_done(S, maxIters)) return;
   const int lane = threadIdx.x & 31;
   const int warpsPerBlock = blockDim.x >> 5;
@@ -395,35 +397,47 @@ k_amg_spmv(SellView M, const double *__restrict__ vals, const double *__restrict
     const int off = __ldg(M.sliceOff + slice);
     const int wdt = (__ldg(M.sliceOff + slice + 1) - off) >> 5;
     const int row = slice * 32 + lane;
-    double acc[1] = {0.};
-    slice_dot_any<1>(M.col, vals, (size_t)off + lane, wdt, x, 0, acc);
+    double acc[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) acc[i] = 0.;
+    slice_dot_any<NC>(M.col, vals, (size_t)off + lane, wdt, x, ldx, acc);
     if (row < M.nRows) {
-      if (MODE == 0) y[row] = acc[0];
-      if (MODE == 1) y[row] = b[row] - acc[0];
-      if (MODE == 2) y[row] = x[row] + w[row] * (b[row] - acc[0]);
-      if (MODE == 3) y[row] += acc[0];
+      const double wr = MODE == 2 ? w[row] : 0.;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const size_t iy = (size_t)i * ldy + row;
+        if (MODE == 0) y[iy] = acc[i];
+        if (MODE == 1) y[iy] = b[iy] - acc[i];
+        if (MODE == 2) y[iy] = x[(size_t)i * ldx + row] + wr * (b[iy] - acc[i]);
+        if (MODE == 3) y[iy] += acc[i];
+      }
     }
   }
 }
 
 // x = w .* b  (first pre-smoothing sweep from a zero guess)
-__global__ void k_amg_scale(int n, const double *__restrict__ w, const double *__restrict__ b,
+__global__ void k_amg_scale(int n, int nc, int ld, const double *__restrict__ w, const double *__restrict__ b,
                             double *__restrict__ x, const KrylovSums *S, int maxIters) {
   if (S && krylov_done(S, maxIters)) return;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = w[i] * b[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double wi = w[i];
+    for (int c = 0; c < nc; ++c) x[(size_t)c * ld + i] = wi * b[(size_t)c * ld + i];
+  }
 }
 
 // coarsest level: x = Ainv b, one warp per row of the dense inverse
-__global__ void k_amg_dense(int n, const double *__restrict__ Ainv, const double *__restrict__ b,
-                            double *__restrict__ x, const KrylovSums *S, int maxIters) {
+__global__ void k_amg_dense(int n, int nc, int ldb, int ldx, const double *__restrict__ Ainv,
+                            const double *__restrict__ b, double *__restrict__ x, const KrylovSums *S, int maxIters) {
   if (S && krylov_done(S, maxIters)) return;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
-  double acc = 0.;
-  for (int k = lane; k < n; k += 32) acc = fma(Ainv[(size_t)row * n + k], b[k], acc);
-  acc = warp_sum(acc);
-  if (lane == 0) x[row] = acc;
+  for (int c = 0; c < nc; ++c) {
+    double acc = 0.;
+    for (int k = lane; k < n; k += 32) acc = fma(Ainv[(size_t)row * n + k], b[(size_t)c * ldb + k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) x[(size_t)c * ldx + row] = acc;
+  }
 }
 
 // max relative deviation of `a` from ratio * ref over the slots, ratio = a[first] / ref[first]
@@ -449,11 +463,15 @@ int grid_rows(const phb_ctx *c, long long rows) {
 }
 
 template <int MODE>
-void launch(phb_solver *s, const SellPattern &P, const double *vals, const double *x, double *y, const double *b,
-            const double *w, bool inLoop) {
+void launch(phb_solver *s, const SellPattern &P, const double *vals, const double *x, int ldx, double *y, int ldy,
+            const double *b, const double *w, bool inLoop) {
   const SellView V = view_of(&P);
-  PHB_LAUNCH(s->ctx, k_amg_spmv<MODE>, grid_rows(s->ctx, (long long)P.nSlices * 32), kThreads, 0, V, vals, x, y, b, w,
-             inLoop ? s->sums.p : nullptr, s->maxIters);
+  const int grid = grid_rows(s->ctx, (long long)P.nSlices * 32);
+  const KrylovSums *S = inLoop ? s->sums.p : nullptr;
+  if (s->nComp == 1)
+    PHB_LAUNCH(s->ctx, (k_amg_spmv<MODE, 1>), grid, kThreads, 0, V, vals, x, ldx, y, ldy, b, w, S, s->maxIters);
+  else
+    PHB_LAUNCH(s->ctx, (k_amg_spmv<MODE, 2>), grid, kThreads, 0, V, vals, x, ldx, y, ldy, b, w, S, s->maxIters);
 }
 
 int upload_mat(phb_ctx *c, const HCsr &H, bool diagFirst, AmgMat &M) {
@@ -492,7 +510,8 @@ int rebuild(phb_solver *s) {
     for (int i = 0; i < L->n; ++i) w[i] = (D.omegaS / h.rho) / h.diag[i];
     PHB_CHECK(L->w.upload(w, c->stream));
     PHB_CUDA(cudaStreamSynchronize(c->stream));
-    const size_t len = l == 0 ? (size_t)P->nCols : (size_t)L->n;  // level 0 vectors carry (zero) ghost entries
+    L->ld = l == 0 ? P->nCols : L->n;                      // level 0 vectors carry (zero) ghost entries
+    const size_t len = (size_t)L->ld * s->nComp;
     PHB_CHECK(L->x.alloc(len)); PHB_CHECK(L->x2.alloc(len)); PHB_CHECK(L->r.alloc(len));
     PHB_CHECK(L->x.zero(c->stream)); PHB_CHECK(L->x2.zero(c->stream)); PHB_CHECK(L->r.zero(c->stream));
     if (l > 0) { PHB_CHECK(L->b.alloc(len)); PHB_CHECK(L->b.zero(c->stream)); }
@@ -506,6 +525,7 @@ int rebuild(phb_solver *s) {
                            c->stream));
   PHB_CUDA(cudaStreamSynchronize(c->stream));
   D.src = P;
+  D.nComp = s->nComp;
   D.built = true;
   D.setups++;
   D.setupMs = H.setupMs;
@@ -526,11 +546,7 @@ namespace phb {
 int amg_prepare(phb_solver *s) {
   phb_ctx *c = s->ctx;
   AmgData &D = s->amg;
-  if (s->nComp != 1) {
-    set_error("preconditioner amg handles scalar equations only (use ilu0 for vector equations)");
-    return PHB_ERR_UNSUPPORTED;
-  }
-  bool need = !D.built || D.src != s->pat || D.refVals.n != (size_t)s->pat->nSlots;
+  bool need = !D.built || D.src != s->pat || D.refVals.n != (size_t)s->pat->nSlots || D.nComp != s->nComp;
   if (!need) {
     PHB_CHECK(D.chk.alloc(2));
     int first = 0;
@@ -570,14 +586,14 @@ double amg_cycle_bytes(const phb_solver *s) {
   double total = 0.;
   for (int l = 0; l < L; ++l) {
     const AmgLevel &V = *D.lev[l];
-    const double n = V.n, a = mat(l == 0 ? *s->pat : V.A.pat);
-    const double jac = a + 40. * n, res = a + 24. * n;  // x gather + x, b, w reads + y write | x, b, y
+    const double k = s->nComp, n = V.n, a = mat(l == 0 ? *s->pat : V.A.pat);
+    const double jac = a + (8. + 32. * k) * n, res = a + 24. * k * n;  // w + (x gather, x, b, y) per component | x, b, y
     if (l + 1 < L) {
       const double nc = D.lev[l + 1]->n;
-      total += 24. * n + (D.nu - 1) * jac + res + (mat(V.R.pat) + 8. * n + 8. * nc) + (mat(V.P.pat) + 8. * nc + 16. * n) +
-               D.nu * jac;
+      total += (8. + 16. * k) * n + (D.nu - 1) * jac + res + (mat(V.R.pat) + 8. * k * (n + nc)) +
+               (mat(V.P.pat) + 8. * k * nc + 16. * k * n) + D.nu * jac;
     } else {
-      total += D.denseCoarse ? 8. * n * n + 16. * n : 24. * n + kCoarseSweeps * jac;
+      total += D.denseCoarse ? 8. * n * n + 16. * k * n : (8. + 16. * k) * n + kCoarseSweeps * jac;
     }
   }
   return total;
@@ -588,7 +604,7 @@ double amg_cycle_bytes(const phb_solver *s) {
 int amg_apply(phb_solver *s, const double *in, double *out, bool inLoop) {
   phb_ctx *c = s->ctx;
   AmgData &D = s->amg;
-  const int L = (int)D.lev.size();
+  const int L = (int)D.lev.size(), nc = s->nComp;
   const KrylovSums *S = inLoop ? s->sums.p : nullptr;
   std::vector<const double *> bOf(L);
   std::vector<double *> xOf(L);
@@ -598,28 +614,31 @@ int amg_apply(phb_solver *s, const double *in, double *out, bool inLoop) {
   auto matVal = [&](int l) -> const double * { return l == 0 ? D.refVals.p : D.lev[l]->A.vals.p; };
   for (int l = 0; l + 1 < L; ++l) {
     AmgLevel &V = *D.lev[l];
+    const int ld = V.ld;
     double *x = V.x.p, *x2 = V.x2.p;
-    PHB_LAUNCH(c, k_amg_scale, grid_rows(c, V.n), kThreads, 0, V.n, V.w.p, bOf[l], x, S, s->maxIters);
+    PHB_LAUNCH(c, k_amg_scale, grid_rows(c, V.n), kThreads, 0, V.n, nc, ld, V.w.p, bOf[l], x, S, s->maxIters);
     for (int k = 1; k < D.nu; ++k) {
-      launch<2>(s, matPat(l), matVal(l), x, x2, bOf[l], V.w.p, inLoop);
+      launch<2>(s, matPat(l), matVal(l), x, ld, x2, ld, bOf[l], V.w.p, inLoop);
       std::swap(x, x2);
     }
-    launch<1>(s, matPat(l), matVal(l), x, V.r.p, bOf[l], nullptr, inLoop);
-    launch<0>(s, V.R.pat, V.R.vals.p, V.r.p, D.lev[l + 1]->b.p, nullptr, nullptr, inLoop);
+    launch<1>(s, matPat(l), matVal(l), x, ld, V.r.p, ld, bOf[l], nullptr, inLoop);
+    launch<0>(s, V.R.pat, V.R.vals.p, V.r.p, ld, D.lev[l + 1]->b.p, D.lev[l + 1]->ld, nullptr, nullptr, inLoop);
     xOf[l] = x;
   }
   {
     AmgLevel &V = *D.lev[L - 1];
+    const int ld = V.ld;
     double *x = V.x.p, *x2 = V.x2.p;
     double *dst = L == 1 ? out : x;
     if (D.denseCoarse) {
-      PHB_LAUNCH(c, k_amg_dense, (V.n + 7) / 8, 256, 0, V.n, D.coarseInv.p, bOf[L - 1], dst, S, s->maxIters);
+      PHB_LAUNCH(c, k_amg_dense, (V.n + 7) / 8, 256, 0, V.n, nc, ld, ld, D.coarseInv.p, bOf[L - 1], dst, S,
+                 s->maxIters);
       xOf[L - 1] = dst;
     } else {
-      PHB_LAUNCH(c, k_amg_scale, grid_rows(c, V.n), kThreads, 0, V.n, V.w.p, bOf[L - 1], x, S, s->maxIters);
+      PHB_LAUNCH(c, k_amg_scale, grid_rows(c, V.n), kThreads, 0, V.n, nc, ld, V.w.p, bOf[L - 1], x, S, s->maxIters);
       for (int k = 0; k < kCoarseSweeps; ++k) {
         double *y = (L == 1 && k == kCoarseSweeps - 1) ? out : x2;
-        launch<2>(s, matPat(L - 1), matVal(L - 1), x, y, bOf[L - 1], V.w.p, inLoop);
+        launch<2>(s, matPat(L - 1), matVal(L - 1), x, ld, y, ld, bOf[L - 1], V.w.p, inLoop);
         x2 = x; x = y;
       }
       xOf[L - 1] = x;
@@ -627,12 +646,13 @@ int amg_apply(phb_solver *s, const double *in, double *out, bool inLoop) {
   }
   for (int l = L - 2; l >= 0; --l) {
     AmgLevel &V = *D.lev[l];
+    const int ld = V.ld;
     double *x = xOf[l];
     double *x2 = x == V.x.p ? V.x2.p : V.x.p;
-    launch<3>(s, V.P.pat, V.P.vals.p, xOf[l + 1], x, nullptr, nullptr, inLoop);
+    launch<3>(s, V.P.pat, V.P.vals.p, xOf[l + 1], D.lev[l + 1]->ld, x, ld, nullptr, nullptr, inLoop);
     for (int k = 0; k < D.nu; ++k) {
       double *y = (l == 0 && k == D.nu - 1) ? out : x2;
-      launch<2>(s, matPat(l), matVal(l), x, y, bOf[l], V.w.p, inLoop);
+      launch<2>(s, matPat(l), matVal(l), x, ld, y, ld, bOf[l], V.w.p, inLoop);
       x2 = x; x = y;
     }
     xOf[l] = x;

@@ -665,6 +665,18 @@ int phb_field_set_bc(phb_field *f, const char *patch, int type, double vx, doubl
   return PHB_OK;
 }
 
+// dir 0: dev[c][cell2dev[i]] = host[c][i]; dir 1: host[c][i] = dev[c][cell2dev[i]]
+__global__ void k_cells_permute(int nCells, int nComp, int nDev, const int *__restrict__ cell2dev,
+                                double *__restrict__ host, double *__restrict__ dev, int dir) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nCells) return;
+  const int d = cell2dev[i];
+  for (int c = 0; c < nComp; ++c) {
+    if (dir == 0) dev[(size_t)c * nDev + d] = host[(size_t)c * nCells + i];
+    else host[(size_t)c * nCells + i] = dev[(size_t)c * nDev + d];
+  }
+}
+
 static int field_part(phb_field *f, const char *part, double **dev, long long *len, bool *isCells) {
   phb_mesh *m = f->m;
   const std::string p(part ? part : "");
@@ -684,11 +696,12 @@ int phb_field_set(phb_field *f, const char *part, const double *v, long long n) 
   PHB_CHECK(field_part(f, part, &dev, &len, &isCells));
   PHB_REQUIRE(n == len, "phb_field_set: size %lld != %lld", n, len);
   phb_mesh *m = f->m;
-  if (isCells) {
-    std::vector<double> tmp((size_t)f->nComp * m->nDev);
-    for (int c = 0; c < f->nComp; ++c)
-      for (int i = 0; i < m->nCells; ++i) tmp[(size_t)c * m->nDev + m->cell2dev[i]] = v[(size_t)c * m->nCells + i];
-    PHB_CUDA(cudaMemcpyAsync(dev, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
+  if (isCells && !m->identityCells) {
+    // host (reference) cell order -> device order, permuted on the device: no pageable staging copy
+    PHB_CHECK(m->dStage.alloc((size_t)2 * m->nCells));
+    PHB_CUDA(cudaMemcpyAsync(m->dStage.p, v, n * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
+    PHB_LAUNCH(m->ctx, k_cells_permute, (m->nCells + 255) / 256, 256, 0, m->nCells, f->nComp, m->nDev,
+               m->dCell2Dev.p, m->dStage.p, dev, 0);
     PHB_CUDA(cudaStreamSynchronize(m->ctx->stream));
   } else {
     PHB_CUDA(cudaMemcpyAsync(dev, v, n * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
@@ -706,12 +719,12 @@ int phb_field_get(const phb_field *cf, const char *part, double *v, long long n)
   PHB_CHECK(field_part(f, part, &dev, &len, &isCells));
   PHB_REQUIRE(n == len, "phb_field_get: size %lld != %lld", n, len);
   phb_mesh *m = f->m;
-  if (isCells) {
-    std::vector<double> tmp((size_t)f->nComp * m->nDev);
-    PHB_CUDA(cudaMemcpyAsync(tmp.data(), dev, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+  if (isCells && !m->identityCells) {
+    PHB_CHECK(m->dStage.alloc((size_t)2 * m->nCells));
+    PHB_LAUNCH(m->ctx, k_cells_permute, (m->nCells + 255) / 256, 256, 0, m->nCells, f->nComp, m->nDev,
+               m->dCell2Dev.p, m->dStage.p, dev, 1);
+    PHB_CUDA(cudaMemcpyAsync(v, m->dStage.p, n * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
     PHB_CUDA(cudaStreamSynchronize(m->ctx->stream));
-    for (int c = 0; c < f->nComp; ++c)
-      for (int i = 0; i < m->nCells; ++i) v[(size_t)c * m->nCells + i] = tmp[(size_t)c * m->nDev + m->cell2dev[i]];
   } else {
     PHB_CUDA(cudaMemcpyAsync(v, dev, n * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
     PHB_CUDA(cudaStreamSynchronize(m->ctx->stream));

@@ -350,6 +350,8 @@ int upload(phb_mesh *m) {
   PHB_CHECK(m->dSendDev.upload(m->hSendDev, st));
   PHB_CHECK(m->dSendBuf.alloc(std::max<size_t>(1, 2 * m->hSendDev.size())));
   PHB_CHECK(m->dCell2Dev.upload(m->cell2dev, st));
+  m->identityCells = m->nDev == m->nCells;
+  for (int i = 0; i < m->nCells && m->identityCells; ++i) m->identityCells = m->cell2dev[i] == i;
   PHB_CUDA(cudaStreamSynchronize(st));
   return PHB_OK;
 }

@@ -69,7 +69,7 @@ struct AmgMat {
   phb::DevBuf<double> vals;
 };
 struct AmgLevel {
-  int n = 0;
+  int n = 0, ld = 0;               // rows, leading dimension of the level vectors
   AmgMat A, P, R;                  // level operator (levels >= 1), prolongator n x n_c, restriction n_c x n
   phb::DevBuf<double> w;           // smoother weight omega / a_ii
   phb::DevBuf<double> x, x2, b, r;
@@ -80,7 +80,7 @@ struct AmgData {
   phb::DevBuf<double> coarseInv, refVals, chk;
   const SellPattern *src = nullptr;
   bool built = false, denseCoarse = false, stale = false, rebuildAlways = false;
-  int nCoarse = 0, nu = 1, coarsest = 400, setups = 0, itersAfterSetup = -1;
+  int nComp = 1, nCoarse = 0, nu = 1, coarsest = 400, setups = 0, itersAfterSetup = -1;
   double theta = 0., omegaS = 4. / 3., setupMs = 0., opComplexity = 1.;
 };
 

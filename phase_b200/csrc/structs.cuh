@@ -63,6 +63,8 @@ struct phb_mesh {
   phb::DevBuf<double> dSendBuf;
   // host<->device field permutation
   phb::DevBuf<int> dCell2Dev;
+  phb::DevBuf<double> dStage;       // staging for phb_field_set/get when cell2dev is not the identity
+  bool identityCells = false;       // cell2dev[i] == i and nDev == nCells: fields copy straight through
   phb::DevBuf<double> dCellC, dCo;  // cell centroids (device order) and Courant scratch, CICSAM only
   // peer-memory halo: where my values land in each peer's vectors (set by the launcher)
   std::vector<int> peerRecvOff, peerLd;

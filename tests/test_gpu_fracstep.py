@@ -76,23 +76,29 @@ def test_cavity_with_ilu0(comm, kind, nx, ny):
     gfs.close(); g.close()
 
 
-@pytest.mark.parametrize("kind,nx,ny", [("rect", 64, 48), ("tri", 24, 20)])
-def test_cavity_with_amg_pressure_solve(comm, kind, nx, ny):
+@pytest.mark.parametrize("kind,nx,ny,upc", [("rect", 64, 48, "ilu0"), ("tri", 24, 20, "ilu0"), ("rect", 48, 64, "amg"),
+                                            ("tri", 20, 24, "amg")])
+def test_cavity_with_amg_pressure_solve(comm, kind, nx, ny, upc):
     """pEqn_ preconditioned by the smoothed-aggregation V-cycle (singular all-Neumann system, hierarchy built once
-    and reused while dt changes), uEqn_ by ILU(0): same parity bar, pressure solve in tens of iterations."""
+    and reused while dt changes), uEqn_ by ILU(0) or by the 2-component V-cycle on a hierarchy that goes stale as the
+    convection term changes: same parity bar, solves in tens of iterations."""
     from phase_b200.api import FiniteVolumeGrid2D as G, lid_driven_cavity
     om, ofs = oracle_cavity(kind, nx, ny, 1.0, 1.0, 1.0, 0.1)
     ofs.use_direct_solver()
     g = (G.rectilinear if kind == "rect" else G.triangulated)(comm, nx, ny, 1.0, 1.0)
-    gfs = lid_driven_cavity(g, 1.0, 0.1, solver=dict(tolerance=1e-11, maxIters=2000),
+    gfs = lid_driven_cavity(g, 1.0, 0.1, solver=dict(tolerance=1e-11, maxIters=2000, preconditioner=upc, amgCoarsest=40),
                             pSolver=dict(preconditioner="amg", amgCoarsest=40))
     dts = [0.5 / nx, 0.5 / nx, 0.4 / nx, 0.3 / nx, 0.3 / nx]
     for dt in dts:
         ofs.step(dt)
         st = gfs.solve(dt)
         assert st["errorP"] <= 1e-10 and st["itersP"] <= 40, st
+        assert st["errorU"] <= 1e-10 and (upc == "ilu0" or st["itersU"] <= 40), st
     info = gfs.pEqn.solver.amgInfo()
     assert info["setups"] == 1 and info["levels"] >= 3, info
+    if upc == "amg":
+        iu = gfs.uEqn.solver.amgInfo()
+        assert iu["setups"] == 1 and iu["stale"] == 1 and iu["levels"] >= 3, iu
     u, p, po = gfs.u.get("cells"), gfs.p.get("cells"), ofs.view("p").copy()
     assert rel_l2(u[0], ofs.view("ux")) < TOL and rel_l2(u[1], ofs.view("uy")) < TOL
     assert rel_l2(p - p.mean(), po - po.mean()) < TOL

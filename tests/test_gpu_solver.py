@@ -226,13 +226,3 @@ def test_amg_singular_neumann_system(comm):
     x, xd = s.x(), O.direct_solve(rp, ci, va, bc)
     assert rel_l2(x - x.mean(), xd - xd.mean()) < 1e-7
     s.close()
-
-
-def test_amg_rejects_vector_equations_loudly(comm):
-    from phase_b200.api import FiniteVolumeGrid2D, lid_driven_cavity, PhaseB200Error
-    g = FiniteVolumeGrid2D.rectilinear(comm, 8, 8, 1.0, 1.0)
-    fs = lid_driven_cavity(g, solver=dict(preconditioner="amg"))
-    with pytest.raises(PhaseB200Error):
-        fs.solve(1e-3)
-    fs.close()
-    g.close()
