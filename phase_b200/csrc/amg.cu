@@ -376,18 +376,40 @@ HCsr csr_from_sell(const SellPattern &S, const std::vector<double> &slotVals) {
 }
 
 // ===================================================================== device cycle
+// The cycle runs in single precision by default (`amgPrecision single`): it is a preconditioner, the
+// Krylov recurrences around it stay fp64, and every kernel here is bound by HBM bytes -- float matrices
+// and vectors halve them.  T = float | double is the type of the level matrices and level vectors;
+// TB / TY are the types of the right-hand side read and of the vector written (double where the cycle
+// touches the Krylov vectors: b on level 0 and the final result).
 constexpr int kThreads = 256;
 constexpr int kBlocksPerSM = 8;
+constexpr int kSubLanes = 8;        // lanes per row in the small-level kernel
+constexpr int kSubRows = 200000;    // levels with at most this many rows use it
+
+template <int MODE, int NC, typename T, typename TB, typename TY>
+__device__ __forceinline__ void amg_epilogue(int row, const T (&acc)[NC], const T *__restrict__ x, int ldx,
+                                             TY *__restrict__ y, int ldy, const TB *__restrict__ b,
+                                             const T *__restrict__ w) {
+  const T wr = MODE == 2 ? w[row] : T(0);
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const size_t iy = (size_t)i * ldy + row;
+    if (MODE == 0) y[iy] = (TY)acc[i];
+    if (MODE == 1) y[iy] = (TY)((T)b[iy] - acc[i]);
+    if (MODE == 2) y[iy] = (TY)(x[(size_t)i * ldx + row] + wr * ((T)b[iy] - acc[i]));
+    if (MODE == 3) y[iy] += (TY)acc[i];
+  }
+}
 
 // MODE 0: y = M x          MODE 1: y = b - M x
 // MODE 2: y = x + w (b - M x)   (damped Jacobi, out of place; w = omega / a_ii)
 // MODE 3: y += M x
 // NC components share the coefficients; x has leading dimension ldx, y and b have ldy.
-template <int MODE, int NC>
+// Streaming variant: warp <-> slice, lane <-> row (large levels, HBM-bound).
+template <int MODE, int NC, typename T, typename TB, typename TY>
 __global__ void __launch_bounds__(kThreads)
-k_amg_spmv(SellView M, const double *__restrict__ vals, const double *__restrict__ x, int ldx,
-           double *__restrict__ y, int ldy, const double *__restrict__ b, const double *__restrict__ w,
-           const KrylovSums *S, int maxIters) {
+k_amg_spmv(SellView M, const T *__restrict__ vals, const T *__restrict__ x, int ldx, TY *__restrict__ y, int ldy,
+           const TB *__restrict__ b, const T *__restrict__ w, const KrylovSums *S, int maxIters) {
   if (S && krylov_done(S, maxIters)) return;
   const int lane = threadIdx.x & 31;
   const int warpsPerBlock = blockDim.x >> 5;
@@ -397,47 +419,87 @@ k_amg_spmv(SellView M, const double *__restrict__ vals, const double *__restrict
     const int off = __ldg(M.sliceOff + slice);
     const int wdt = (__ldg(M.sliceOff + slice + 1) - off) >> 5;
     const int row = slice * 32 + lane;
-    double acc[NC];
+    T acc[NC];
 #pragma unroll
-    for (int i = 0; i < NC; ++i) acc[i] = 0.;
+    for (int i = 0; i < NC; ++i) acc[i] = T(0);
     slice_dot_any<NC>(M.col, vals, (size_t)off + lane, wdt, x, ldx, acc);
-    if (row < M.nRows) {
-      const double wr = MODE == 2 ? w[row] : 0.;
-#pragma unroll
-      for (int i = 0; i < NC; ++i) {
-        const size_t iy = (size_t)i * ldy + row;
-        if (MODE == 0) y[iy] = acc[i];
-        if (MODE == 1) y[iy] = b[iy] - acc[i];
-        if (MODE == 2) y[iy] = x[(size_t)i * ldx + row] + wr * (b[iy] - acc[i]);
-        if (MODE == 3) y[iy] += acc[i];
-      }
-    }
+    if (row < M.nRows) amg_epilogue<MODE, NC, T, TB, TY>(row, acc, x, ldx, y, ldy, b, w);
   }
+}
+
+// Small levels are latency-bound, not bandwidth-bound: kSubLanes lanes share a row, every lane issues its
+// (up to 4) entries at once, partial sums meet in shuffles -- the dependent-load chain no longer grows
+// with the row length (restriction rows hold 20-30 entries).
+template <int MODE, int NC, typename T, typename TB, typename TY>
+__global__ void __launch_bounds__(kThreads)
+k_amg_spmv_sub(SellView M, const T *__restrict__ vals, const T *__restrict__ x, int ldx, TY *__restrict__ y, int ldy,
+               const TB *__restrict__ b, const T *__restrict__ w, const KrylovSums *S, int maxIters) {
+  if (S && krylov_done(S, maxIters)) return;
+  const int g = threadIdx.x & (kSubLanes - 1);
+  const int row = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSubLanes);
+  const bool live = row < M.nRows;
+  int off = 0, wdt = 0;
+  if (live) {
+    off = __ldg(M.sliceOff + (row >> 5));
+    wdt = (__ldg(M.sliceOff + (row >> 5) + 1) - off) >> 5;
+  }
+  const size_t base = (size_t)off + (row & 31);
+  T acc[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) acc[i] = T(0);
+  for (int k0 = 0; k0 < wdt; k0 += 4 * kSubLanes) {
+    int c[4];
+    T a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + j * kSubLanes + g;
+      c[j] = k < wdt ? __ldg(M.col + base + (size_t)k * 32) : -1;
+      a[j] = k < wdt ? __ldg(vals + base + (size_t)k * 32) : T(0);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c[j] >= 0) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) acc[i] = fma(a[j], __ldg(x + (size_t)i * ldx + c[j]), acc[i]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < NC; ++i)
+#pragma unroll
+    for (int o = kSubLanes / 2; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  if (live && g == 0) amg_epilogue<MODE, NC, T, TB, TY>(row, acc, x, ldx, y, ldy, b, w);
 }
 
 // x = w .* b  (first pre-smoothing sweep from a zero guess)
-__global__ void k_amg_scale(int n, int nc, int ld, const double *__restrict__ w, const double *__restrict__ b,
-                            double *__restrict__ x, const KrylovSums *S, int maxIters) {
+template <typename T, typename TB>
+__global__ void k_amg_scale(int n, int nc, int ld, const T *__restrict__ w, const TB *__restrict__ b,
+                            T *__restrict__ x, const KrylovSums *S, int maxIters) {
   if (S && krylov_done(S, maxIters)) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const double wi = w[i];
-    for (int c = 0; c < nc; ++c) x[(size_t)c * ld + i] = wi * b[(size_t)c * ld + i];
+    const T wi = w[i];
+    for (int c = 0; c < nc; ++c) x[(size_t)c * ld + i] = wi * (T)b[(size_t)c * ld + i];
   }
 }
 
-// coarsest level: x = Ainv b, one warp per row of the dense inverse
-__global__ void k_amg_dense(int n, int nc, int ldb, int ldx, const double *__restrict__ Ainv,
-                            const double *__restrict__ b, double *__restrict__ x, const KrylovSums *S, int maxIters) {
+// coarsest level: x = Ainv b, one warp per row of the dense inverse (kept in fp64: it is tiny)
+template <typename TB, typename TY>
+__global__ void k_amg_dense(int n, int nc, int ld, const double *__restrict__ Ainv, const TB *__restrict__ b,
+                            TY *__restrict__ x, const KrylovSums *S, int maxIters) {
   if (S && krylov_done(S, maxIters)) return;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   for (int c = 0; c < nc; ++c) {
     double acc = 0.;
-    for (int k = lane; k < n; k += 32) acc = fma(Ainv[(size_t)row * n + k], b[(size_t)c * ldb + k], acc);
+    for (int k = lane; k < n; k += 32) acc = fma(Ainv[(size_t)row * n + k], (double)b[(size_t)c * ld + k], acc);
     acc = warp_sum(acc);
-    if (lane == 0) x[(size_t)c * ldx + row] = acc;
+    if (lane == 0) x[(size_t)c * ld + row] = (TY)acc;
   }
+}
+
+__global__ void k_amg_to_float(long long n, const double *__restrict__ a, float *__restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (float)a[i];
 }
 
 // max relative deviation of `a` from ratio * ref over the slots, ratio = a[first] / ref[first]
@@ -462,30 +524,57 @@ int grid_rows(const phb_ctx *c, long long rows) {
   return (int)std::max<long long>(1, std::min(g, cap));
 }
 
-template <int MODE>
-void launch(phb_solver *s, const SellPattern &P, const double *vals, const double *x, int ldx, double *y, int ldy,
-            const double *b, const double *w, bool inLoop) {
+template <int MODE, typename T, typename TB, typename TY>
+void launch(phb_solver *s, const SellPattern &P, const T *vals, const T *x, int ldx, TY *y, int ldy, const TB *b,
+            const T *w, bool inLoop) {
   const SellView V = view_of(&P);
-  const int grid = grid_rows(s->ctx, (long long)P.nSlices * 32);
   const KrylovSums *S = inLoop ? s->sums.p : nullptr;
+  if (P.nRows <= kSubRows) {
+    const int grid = (int)(((long long)P.nRows * kSubLanes + kThreads - 1) / kThreads);
+    if (s->nComp == 1)
+      PHB_LAUNCH(s->ctx, (k_amg_spmv_sub<MODE, 1, T, TB, TY>), grid, kThreads, 0, V, vals, x, ldx, y, ldy, b, w, S,
+                 s->maxIters);
+    else
+      PHB_LAUNCH(s->ctx, (k_amg_spmv_sub<MODE, 2, T, TB, TY>), grid, kThreads, 0, V, vals, x, ldx, y, ldy, b, w, S,
+                 s->maxIters);
+    return;
+  }
+  const int grid = grid_rows(s->ctx, (long long)P.nSlices * 32);
   if (s->nComp == 1)
-    PHB_LAUNCH(s->ctx, (k_amg_spmv<MODE, 1>), grid, kThreads, 0, V, vals, x, ldx, y, ldy, b, w, S, s->maxIters);
+    PHB_LAUNCH(s->ctx, (k_amg_spmv<MODE, 1, T, TB, TY>), grid, kThreads, 0, V, vals, x, ldx, y, ldy, b, w, S,
+               s->maxIters);
   else
-    PHB_LAUNCH(s->ctx, (k_amg_spmv<MODE, 2>), grid, kThreads, 0, V, vals, x, ldx, y, ldy, b, w, S, s->maxIters);
+    PHB_LAUNCH(s->ctx, (k_amg_spmv<MODE, 2, T, TB, TY>), grid, kThreads, 0, V, vals, x, ldx, y, ldy, b, w, S,
+               s->maxIters);
 }
 
+// typed views of the byte buffers of a level
+template <typename T> T *as(const phb::DevBuf<double> &b) { return reinterpret_cast<T *>(b.p); }
+template <typename T> int alloc_as(phb::DevBuf<double> &b, size_t count, cudaStream_t st) {
+  PHB_CHECK(b.alloc((count * sizeof(T) + 7) / 8));
+  return b.zero(st);
+}
+template <typename T> int upload_as(phb::DevBuf<double> &b, const std::vector<double> &h, cudaStream_t st) {
+  std::vector<T> t(h.begin(), h.end());
+  PHB_CHECK(b.alloc((t.size() * sizeof(T) + 7) / 8));
+  if (!t.empty()) PHB_CUDA(cudaMemcpyAsync(b.p, t.data(), t.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  PHB_CUDA(cudaStreamSynchronize(st));  // t goes out of scope
+  return PHB_OK;
+}
+
+template <typename T>
 int upload_mat(phb_ctx *c, const HCsr &H, bool diagFirst, AmgMat &M) {
   std::vector<double> slotVals;
   sell_from_csr(H, diagFirst, M.pat, slotVals);
   PHB_CHECK(M.pat.sliceOff.upload(M.pat.hSliceOff, c->stream));
   PHB_CHECK(M.pat.rowLen.upload(M.pat.hRowLen, c->stream));
   PHB_CHECK(M.pat.col.upload(M.pat.hCol, c->stream));
-  PHB_CHECK(M.vals.upload(slotVals, c->stream));
-  PHB_CUDA(cudaStreamSynchronize(c->stream));  // slotVals goes out of scope
+  PHB_CHECK(upload_as<T>(M.vals, slotVals, c->stream));
   return PHB_OK;
 }
 
-int rebuild(phb_solver *s) {
+template <typename T>
+int rebuild_t(phb_solver *s) {
   phb_ctx *c = s->ctx;
   AmgData &D = s->amg;
   const SellPattern *P = s->pat;
@@ -501,31 +590,37 @@ int rebuild(phb_solver *s) {
     std::unique_ptr<AmgLevel> L(new AmgLevel());
     HostLevel &h = H.lev[l];
     L->n = h.A.n;
-    if (l > 0) PHB_CHECK(upload_mat(c, h.A, true, L->A));
+    if (l > 0) PHB_CHECK(upload_mat<T>(c, h.A, true, L->A));
     if (l + 1 < nLev) {
-      PHB_CHECK(upload_mat(c, h.P, false, L->P));
-      PHB_CHECK(upload_mat(c, h.R, false, L->R));
+      PHB_CHECK(upload_mat<T>(c, h.P, false, L->P));
+      PHB_CHECK(upload_mat<T>(c, h.R, false, L->R));
     }
     std::vector<double> w(L->n);
     for (int i = 0; i < L->n; ++i) w[i] = (D.omegaS / h.rho) / h.diag[i];
-    PHB_CHECK(L->w.upload(w, c->stream));
-    PHB_CUDA(cudaStreamSynchronize(c->stream));
+    PHB_CHECK(upload_as<T>(L->w, w, c->stream));
     L->ld = l == 0 ? P->nCols : L->n;                      // level 0 vectors carry (zero) ghost entries
     const size_t len = (size_t)L->ld * s->nComp;
-    PHB_CHECK(L->x.alloc(len)); PHB_CHECK(L->x2.alloc(len)); PHB_CHECK(L->r.alloc(len));
-    PHB_CHECK(L->x.zero(c->stream)); PHB_CHECK(L->x2.zero(c->stream)); PHB_CHECK(L->r.zero(c->stream));
-    if (l > 0) { PHB_CHECK(L->b.alloc(len)); PHB_CHECK(L->b.zero(c->stream)); }
+    PHB_CHECK(alloc_as<T>(L->x, len, c->stream)); PHB_CHECK(alloc_as<T>(L->x2, len, c->stream));
+    PHB_CHECK(alloc_as<T>(L->r, len, c->stream));
+    if (l > 0) PHB_CHECK(alloc_as<T>(L->b, len, c->stream));
     D.lev.push_back(std::move(L));
   }
   D.nCoarse = H.lev.back().A.n;
   D.denseCoarse = !H.coarseInv.empty();
   if (D.denseCoarse) PHB_CHECK(D.coarseInv.upload(H.coarseInv, c->stream));
+  // level 0 operator of the cycle = the matrix the hierarchy was built from (kept in fp64 for the
+  // change test, plus the float image the single-precision cycle streams)
   PHB_CHECK(D.refVals.alloc((size_t)P->nSlots));
   PHB_CUDA(cudaMemcpyAsync(D.refVals.p, s->dVals, (size_t)P->nSlots * sizeof(double), cudaMemcpyDeviceToDevice,
                            c->stream));
+  if (sizeof(T) == 4) {
+    PHB_CHECK(D.refValsF.alloc((size_t)P->nSlots));
+    PHB_LAUNCH(c, k_amg_to_float, grid_rows(c, P->nSlots), kThreads, 0, P->nSlots, D.refVals.p, D.refValsF.p);
+  }
   PHB_CUDA(cudaStreamSynchronize(c->stream));
   D.src = P;
   D.nComp = s->nComp;
+  D.builtSingle = sizeof(T) == 4;
   D.built = true;
   D.setups++;
   D.setupMs = H.setupMs;
@@ -535,6 +630,94 @@ int rebuild(phb_solver *s) {
   if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
   return PHB_OK;
 }
+
+template <typename T> const T *level0_vals(const AmgData &D);
+template <> const float *level0_vals<float>(const AmgData &D) { return D.refValsF.p; }
+template <> const double *level0_vals<double>(const AmgData &D) { return D.refVals.p; }
+
+template <typename T> struct Cycle {
+  phb_solver *s;
+  AmgData &D;
+  bool inLoop;
+  const KrylovSums *S;
+  int nc;
+  const SellPattern &pat(int l) const { return l == 0 ? *s->pat : D.lev[l]->A.pat; }
+  const T *val(int l) const { return l == 0 ? level0_vals<T>(D) : as<T>(D.lev[l]->A.vals); }
+
+  // pre-smoothing from a zero guess, residual, restriction; returns the level's iterate
+  template <typename TB> T *down(int l, const TB *b) {
+    AmgLevel &V = *D.lev[l];
+    const int ld = V.ld;
+    T *x = as<T>(V.x), *x2 = as<T>(V.x2);
+    PHB_LAUNCH(s->ctx, (k_amg_scale<T, TB>), grid_rows(s->ctx, V.n), kThreads, 0, V.n, nc, ld, as<T>(V.w), b, x, S,
+               s->maxIters);
+    for (int k = 1; k < D.nu; ++k) {
+      launch<2>(s, pat(l), val(l), (const T *)x, ld, x2, ld, b, (const T *)as<T>(V.w), inLoop);
+      std::swap(x, x2);
+    }
+    launch<1>(s, pat(l), val(l), (const T *)x, ld, as<T>(V.r), ld, b, (const T *)nullptr, inLoop);
+    AmgLevel &C = *D.lev[l + 1];
+    launch<0>(s, V.R.pat, (const T *)as<T>(V.R.vals), (const T *)as<T>(V.r), ld, as<T>(C.b), C.ld, (const T *)nullptr,
+              (const T *)nullptr, inLoop);
+    return x;
+  }
+  // coarse correction + post-smoothing; the last sweep of level 0 writes the fp64 result
+  template <typename TB> T *up(int l, const TB *b, T *x, const T *xc, double *out) {
+    AmgLevel &V = *D.lev[l];
+    const int ld = V.ld;
+    T *x2 = x == as<T>(V.x) ? as<T>(V.x2) : as<T>(V.x);
+    launch<3>(s, V.P.pat, (const T *)as<T>(V.P.vals), xc, D.lev[l + 1]->ld, x, ld, (const T *)nullptr,
+              (const T *)nullptr, inLoop);
+    for (int k = 0; k < D.nu; ++k) {
+      if (out && k == D.nu - 1) {
+        launch<2>(s, pat(l), val(l), (const T *)x, ld, out, ld, b, (const T *)as<T>(V.w), inLoop);
+        return nullptr;
+      }
+      launch<2>(s, pat(l), val(l), (const T *)x, ld, x2, ld, b, (const T *)as<T>(V.w), inLoop);
+      std::swap(x, x2);
+    }
+    return x;
+  }
+  // coarsest level: dense inverse, or a fixed number of Jacobi sweeps when it is too large for one
+  template <typename TB> T *coarse(int l, const TB *b, double *out) {
+    AmgLevel &V = *D.lev[l];
+    const int ld = V.ld;
+    T *x = as<T>(V.x), *x2 = as<T>(V.x2);
+    if (D.denseCoarse) {
+      if (out)
+        PHB_LAUNCH(s->ctx, (k_amg_dense<TB, double>), (V.n + 7) / 8, 256, 0, V.n, nc, ld, D.coarseInv.p, b, out, S,
+                   s->maxIters);
+      else
+        PHB_LAUNCH(s->ctx, (k_amg_dense<TB, T>), (V.n + 7) / 8, 256, 0, V.n, nc, ld, D.coarseInv.p, b, x, S,
+                   s->maxIters);
+      return x;
+    }
+    PHB_LAUNCH(s->ctx, (k_amg_scale<T, TB>), grid_rows(s->ctx, V.n), kThreads, 0, V.n, nc, ld, as<T>(V.w), b, x, S,
+               s->maxIters);
+    for (int k = 0; k < kCoarseSweeps; ++k) {
+      if (out && k == kCoarseSweeps - 1) {
+        launch<2>(s, pat(l), val(l), (const T *)x, ld, out, ld, b, (const T *)as<T>(V.w), inLoop);
+        return nullptr;
+      }
+      launch<2>(s, pat(l), val(l), (const T *)x, ld, x2, ld, b, (const T *)as<T>(V.w), inLoop);
+      std::swap(x, x2);
+    }
+    return x;
+  }
+
+  int run(const double *in, double *out) {
+    const int L = (int)D.lev.size();
+    if (L == 1) { coarse(0, in, out); return PHB_OK; }
+    std::vector<T *> xOf(L);
+    xOf[0] = down(0, in);
+    for (int l = 1; l + 1 < L; ++l) xOf[l] = down(l, (const T *)as<T>(D.lev[l]->b));
+    xOf[L - 1] = coarse(L - 1, (const T *)as<T>(D.lev[L - 1]->b), nullptr);
+    for (int l = L - 2; l >= 1; --l)
+      xOf[l] = up(l, (const T *)as<T>(D.lev[l]->b), xOf[l], (const T *)xOf[l + 1], nullptr);
+    up(0, in, xOf[0], (const T *)xOf[1], out);
+    return PHB_OK;
+  }
+};
 
 }  // namespace
 
@@ -546,7 +729,8 @@ namespace phb {
 int amg_prepare(phb_solver *s) {
   phb_ctx *c = s->ctx;
   AmgData &D = s->amg;
-  bool need = !D.built || D.src != s->pat || D.refVals.n != (size_t)s->pat->nSlots || D.nComp != s->nComp;
+  bool need = !D.built || D.src != s->pat || D.refVals.n != (size_t)s->pat->nSlots || D.nComp != s->nComp ||
+              D.builtSingle != D.single;
   if (!need) {
     PHB_CHECK(D.chk.alloc(2));
     int first = 0;
@@ -560,7 +744,7 @@ int amg_prepare(phb_solver *s) {
       need = true;
     if (D.rebuildAlways && D.stale) need = true;
   }
-  if (need) PHB_CHECK(rebuild(s));
+  if (need) PHB_CHECK(D.single ? rebuild_t<float>(s) : rebuild_t<double>(s));
   return PHB_OK;
 }
 
@@ -576,24 +760,28 @@ int amg_launches_per_apply(const phb_solver *s) {
   return (L - 1) * perLevel + (D.denseCoarse ? 1 : 1 + kCoarseSweeps);
 }
 
-// algorithmic bytes of one cycle: every matrix streamed once per use (12 B per entry + 4 B per row
-// pointer), vectors 8 B per element read or written
+// algorithmic bytes of one cycle: every matrix streamed once per use (index + value per entry, 4 B per row
+// pointer), vectors read or written once per use; v = bytes of a cycle scalar (4 single, 8 double), the
+// Krylov vectors touched on level 0 (b, result) are fp64
 double amg_cycle_bytes(const phb_solver *s) {
   const AmgData &D = s->amg;
   const int L = (int)D.lev.size();
   if (L == 0) return 0.;
-  auto mat = [](const SellPattern &P) { return 12. * (double)P.nnz + 4. * (P.nRows + 1.); };
+  const double v = D.builtSingle ? 4. : 8.;
+  auto mat = [v](const SellPattern &P) { return (4. + v) * (double)P.nnz + 4. * (P.nRows + 1.); };
   double total = 0.;
   for (int l = 0; l < L; ++l) {
     const AmgLevel &V = *D.lev[l];
     const double k = s->nComp, n = V.n, a = mat(l == 0 ? *s->pat : V.A.pat);
-    const double jac = a + (8. + 32. * k) * n, res = a + 24. * k * n;  // w + (x gather, x, b, y) per component | x, b, y
+    const double vb = l == 0 ? 8. : v;                            // right-hand side of this level
+    const double jac = a + (v + (3. * v + vb) * k) * n;           // w | x gather, x, y, b per component
+    const double res = a + (2. * v + vb) * k * n;                 // x gather, r, b
     if (l + 1 < L) {
       const double nc = D.lev[l + 1]->n;
-      total += (8. + 16. * k) * n + (D.nu - 1) * jac + res + (mat(V.R.pat) + 8. * k * (n + nc)) +
-               (mat(V.P.pat) + 8. * k * nc + 16. * k * n) + D.nu * jac;
+      total += (v + (v + vb) * k) * n + (D.nu - 1) * jac + res + (mat(V.R.pat) + v * k * (n + nc)) +
+               (mat(V.P.pat) + v * k * nc + 2. * v * k * n) + D.nu * jac + (l == 0 ? (8. - v) * k * n : 0.);
     } else {
-      total += D.denseCoarse ? 8. * n * n + 16. * k * n : (8. + 16. * k) * n + kCoarseSweeps * jac;
+      total += D.denseCoarse ? 8. * n * n + 2. * v * k * n : (v + (v + vb) * k) * n + kCoarseSweeps * jac;
     }
   }
   return total;
@@ -602,62 +790,14 @@ double amg_cycle_bytes(const phb_solver *s) {
 // z = M^-1 r : one V(nu, nu) cycle.  All kernels test the device-side convergence flag first, so the
 // tail of a graph after convergence costs launches only.
 int amg_apply(phb_solver *s, const double *in, double *out, bool inLoop) {
-  phb_ctx *c = s->ctx;
   AmgData &D = s->amg;
-  const int L = (int)D.lev.size(), nc = s->nComp;
   const KrylovSums *S = inLoop ? s->sums.p : nullptr;
-  std::vector<const double *> bOf(L);
-  std::vector<double *> xOf(L);
-  bOf[0] = in;
-  for (int l = 1; l < L; ++l) bOf[l] = D.lev[l]->b.p;
-  auto matPat = [&](int l) -> const SellPattern & { return l == 0 ? *s->pat : D.lev[l]->A.pat; };
-  auto matVal = [&](int l) -> const double * { return l == 0 ? D.refVals.p : D.lev[l]->A.vals.p; };
-  for (int l = 0; l + 1 < L; ++l) {
-    AmgLevel &V = *D.lev[l];
-    const int ld = V.ld;
-    double *x = V.x.p, *x2 = V.x2.p;
-    PHB_LAUNCH(c, k_amg_scale, grid_rows(c, V.n), kThreads, 0, V.n, nc, ld, V.w.p, bOf[l], x, S, s->maxIters);
-    for (int k = 1; k < D.nu; ++k) {
-      launch<2>(s, matPat(l), matVal(l), x, ld, x2, ld, bOf[l], V.w.p, inLoop);
-      std::swap(x, x2);
-    }
-    launch<1>(s, matPat(l), matVal(l), x, ld, V.r.p, ld, bOf[l], nullptr, inLoop);
-    launch<0>(s, V.R.pat, V.R.vals.p, V.r.p, ld, D.lev[l + 1]->b.p, D.lev[l + 1]->ld, nullptr, nullptr, inLoop);
-    xOf[l] = x;
+  if (D.builtSingle) {
+    Cycle<float> cy{s, D, inLoop, S, s->nComp};
+    return cy.run(in, out);
   }
-  {
-    AmgLevel &V = *D.lev[L - 1];
-    const int ld = V.ld;
-    double *x = V.x.p, *x2 = V.x2.p;
-    double *dst = L == 1 ? out : x;
-    if (D.denseCoarse) {
-      PHB_LAUNCH(c, k_amg_dense, (V.n + 7) / 8, 256, 0, V.n, nc, ld, ld, D.coarseInv.p, bOf[L - 1], dst, S,
-                 s->maxIters);
-      xOf[L - 1] = dst;
-    } else {
-      PHB_LAUNCH(c, k_amg_scale, grid_rows(c, V.n), kThreads, 0, V.n, nc, ld, V.w.p, bOf[L - 1], x, S, s->maxIters);
-      for (int k = 0; k < kCoarseSweeps; ++k) {
-        double *y = (L == 1 && k == kCoarseSweeps - 1) ? out : x2;
-        launch<2>(s, matPat(L - 1), matVal(L - 1), x, ld, y, ld, bOf[L - 1], V.w.p, inLoop);
-        x2 = x; x = y;
-      }
-      xOf[L - 1] = x;
-    }
-  }
-  for (int l = L - 2; l >= 0; --l) {
-    AmgLevel &V = *D.lev[l];
-    const int ld = V.ld;
-    double *x = xOf[l];
-    double *x2 = x == V.x.p ? V.x2.p : V.x.p;
-    launch<3>(s, V.P.pat, V.P.vals.p, xOf[l + 1], D.lev[l + 1]->ld, x, ld, nullptr, nullptr, inLoop);
-    for (int k = 0; k < D.nu; ++k) {
-      double *y = (l == 0 && k == D.nu - 1) ? out : x2;
-      launch<2>(s, matPat(l), matVal(l), x, ld, y, ld, bOf[l], V.w.p, inLoop);
-      x2 = x; x = y;
-    }
-    xOf[l] = x;
-  }
-  return PHB_OK;
+  Cycle<double> cy{s, D, inLoop, S, s->nComp};
+  return cy.run(in, out);
 }
 
 }  // namespace phb

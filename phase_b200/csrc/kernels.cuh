@@ -26,6 +26,7 @@ __device__ __forceinline__ double warp_max(double v) {
 // streaming (read-once) loads: keep them out of L1 and first in line for L2 eviction
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
+__device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
 
 constexpr int kMaxBlockWarps = 32;
 
@@ -94,12 +95,12 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NS], double *partials, u
   return false;
 }
 
-template <int NC, int W>
-__device__ __forceinline__ void slice_dot(const int *__restrict__ col, const double *__restrict__ vals,
-                                          size_t base, const double *__restrict__ x, int ld,
-                                          double (&acc)[NC]) {
+// T = double for the Krylov SpMV, float inside a single-precision multigrid cycle
+template <int NC, int W, typename T>
+__device__ __forceinline__ void slice_dot(const int *__restrict__ col, const T *__restrict__ vals,
+                                          size_t base, const T *__restrict__ x, int ld, T (&acc)[NC]) {
   int c[W];
-  double a[W];
+  T a[W];
 #pragma unroll
   for (int k = 0; k < W; ++k) {
     c[k] = ld_stream(col + base + (size_t)k * 32);
@@ -112,20 +113,19 @@ __device__ __forceinline__ void slice_dot(const int *__restrict__ col, const dou
   }
 }
 
-template <int NC>
-__device__ __forceinline__ void slice_dot_any(const int *__restrict__ col, const double *__restrict__ vals,
-                                              size_t base, int w, const double *__restrict__ x, int ld,
-                                              double (&acc)[NC]) {
+template <int NC, typename T>
+__device__ __forceinline__ void slice_dot_any(const int *__restrict__ col, const T *__restrict__ vals,
+                                              size_t base, int w, const T *__restrict__ x, int ld, T (&acc)[NC]) {
   switch (w) {
-    case 3: slice_dot<NC, 3>(col, vals, base, x, ld, acc); break;
-    case 4: slice_dot<NC, 4>(col, vals, base, x, ld, acc); break;
-    case 5: slice_dot<NC, 5>(col, vals, base, x, ld, acc); break;
-    case 6: slice_dot<NC, 6>(col, vals, base, x, ld, acc); break;
-    case 7: slice_dot<NC, 7>(col, vals, base, x, ld, acc); break;
+    case 3: slice_dot<NC, 3, T>(col, vals, base, x, ld, acc); break;
+    case 4: slice_dot<NC, 4, T>(col, vals, base, x, ld, acc); break;
+    case 5: slice_dot<NC, 5, T>(col, vals, base, x, ld, acc); break;
+    case 6: slice_dot<NC, 6, T>(col, vals, base, x, ld, acc); break;
+    case 7: slice_dot<NC, 7, T>(col, vals, base, x, ld, acc); break;
     default: {
       int k = 0;
-      for (; k + 4 <= w; k += 4) slice_dot<NC, 4>(col, vals, base + (size_t)k * 32, x, ld, acc);
-      for (; k < w; ++k) slice_dot<NC, 1>(col, vals, base + (size_t)k * 32, x, ld, acc);
+      for (; k + 4 <= w; k += 4) slice_dot<NC, 4, T>(col, vals, base + (size_t)k * 32, x, ld, acc);
+      for (; k < w; ++k) slice_dot<NC, 1, T>(col, vals, base + (size_t)k * 32, x, ld, acc);
     }
   }
 }

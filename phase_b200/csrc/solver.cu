@@ -683,6 +683,9 @@ int phb_solver_setup(phb_solver *s, const char *key, const char *value) {
   } else if (k == "amgSmootherWeight") {
     s->amg.omegaS = std::stod(v); s->amg.built = false;
     PHB_REQUIRE(s->amg.omegaS > 0. && s->amg.omegaS < 2., "amgSmootherWeight must lie in (0, 2)");
+  } else if (k == "amgPrecision") {
+    PHB_REQUIRE(lv == "single" || lv == "double" || lv == "float", "amgPrecision must be \"single\" or \"double\"");
+    s->amg.single = lv != "double";
   } else if (k == "amgRebuild") {
     PHB_REQUIRE(lv == "auto" || lv == "always", "amgRebuild must be \"auto\" or \"always\"");
     s->amg.rebuildAlways = lv == "always";

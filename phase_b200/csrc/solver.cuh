@@ -66,7 +66,7 @@ struct IluData {
 // smoothed-aggregation AMG hierarchy (amg.cu)
 struct AmgMat {
   SellPattern pat;
-  phb::DevBuf<double> vals;
+  phb::DevBuf<double> vals;        // bytes: float or double values per `amgPrecision`
 };
 struct AmgLevel {
   int n = 0, ld = 0;               // rows, leading dimension of the level vectors
@@ -78,6 +78,8 @@ constexpr int kCoarseSweeps = 8;   // Jacobi sweeps on a coarsest level too larg
 struct AmgData {
   std::vector<std::unique_ptr<AmgLevel>> lev;
   phb::DevBuf<double> coarseInv, refVals, chk;
+  phb::DevBuf<float> refValsF;
+  bool single = true, builtSingle = true;   // cycle precision (`amgPrecision single|double`)
   const SellPattern *src = nullptr;
   bool built = false, denseCoarse = false, stale = false, rebuildAlways = false;
   int nComp = 1, nCoarse = 0, nu = 1, coarsest = 400, setups = 0, itersAfterSetup = -1;

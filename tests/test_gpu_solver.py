@@ -173,13 +173,14 @@ def test_variable_coefficient_iteration_counts_match_oracle(comm):
 
 
 # ------------------------------------------------------------------ smoothed-aggregation AMG (`preconditioner amg`)
+@pytest.mark.parametrize("prec", ["single", "double"])
 @pytest.mark.parametrize("kind,nx,ny,coarsest", [("rect", 48, 40, 40), ("tri", 30, 26, 40), ("rect", 12, 9, 400)])
-def test_amg_vs_direct(comm, kind, nx, ny, coarsest):
+def test_amg_vs_direct(comm, kind, nx, ny, coarsest, prec):
     from phase_b200.api import SparseMatrixSolver
     rp, ci, va, b = poisson_system(kind, nx, ny)
     xd = O.direct_solve(rp, ci, va, b)
     s = SparseMatrixSolver(comm).setup(dict(solver="BICGSTAB", maxIters=200, tolerance=1e-11, preconditioner="amg",
-                                            amgCoarsest=coarsest))
+                                            amgCoarsest=coarsest, amgPrecision=prec))
     s.setRank(len(b))
     s.set(rp, ci, va)
     s.setRhs(b)
