@@ -227,9 +227,9 @@ def main():
     ap.add_argument("--side", dest="n", type=int, default=2000, help="cells per side per GPU (2000 -> 4M cells)")
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--max-iters", type=int, default=20000)
-    ap.add_argument("--precond", default="ilu0", choices=["ilu0", "jacobi", "none", "amg"],
+    ap.add_argument("--precond", default="amg", choices=["ilu0", "jacobi", "none", "amg"],
                     help="amg = smoothed-aggregation V-cycle on pEqn_; uEqn_ per --u-precond")
-    ap.add_argument("--u-precond", default="ilu0", choices=["ilu0", "amg"], help="uEqn_ preconditioner when --precond amg")
+    ap.add_argument("--u-precond", default="amg", choices=["ilu0", "amg"], help="uEqn_ preconditioner when --precond amg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--mesh", default="quad", choices=["quad", "tri"],
                     help="quad: side x side quads; tri: the same cell count as triangles (each quad of a "
