@@ -207,6 +207,20 @@ int phb_amg_host_level_csr(const phb_amg_host *h, int level, int which, int *row
                            double *vals);
 int phb_amg_host_coarse_inverse(const phb_amg_host *h, double *inv);
 int phb_amg_host_destroy(phb_amg_host *h);
+/* The distributed setup used when nProcs > 1 (`amgScope global`): aggregates are rank-local, the Galerkin
+ * operators keep the couplings between ranks, the level with <= tailRows global rows is gathered and the
+ * rest of the hierarchy replicated.  Test hook: the ranks run as threads of this process, `part[i]` is
+ * the owner of global row i.  Matrices come back with GLOBAL ids of their level (which: 0 = A_l, 1 = P_l). */
+typedef struct phb_amg_dist phb_amg_dist;
+int phb_amg_dist_build(int nRanks, int n, const int *rowPtr, const int *colInd, const double *vals,
+                       const int *part, double theta, int coarsest, long long tailRows, phb_amg_dist **out);
+int phb_amg_dist_info(const phb_amg_dist *h, int *nDistLevels, int *nTailLevels, int *singular);
+const phb_amg_host *phb_amg_dist_tail(const phb_amg_dist *h, int rank);
+int phb_amg_dist_matrix_size(const phb_amg_dist *h, int rank, int level, int which, int *nRows, long long *nnz);
+int phb_amg_dist_matrix(const phb_amg_dist *h, int rank, int level, int which, int *rowPtr, int *colGid,
+                        double *vals, int *rowGid);
+int phb_amg_dist_halo(const phb_amg_dist *h, int rank, int level, int *sendPtr, int *sendIdx, int *recvPtr);
+int phb_amg_dist_destroy(phb_amg_dist *h);
 
 /* ---------------------------------------------------------- fields, equations
  * Seam 2.  Device mirrors of FiniteVolumeField<T> (cells + faces, BC table,

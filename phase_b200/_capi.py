@@ -67,6 +67,13 @@ SIGNATURES = {
     "phb_amg_host_level_csr": (ci, [vp, ci, ci, pi, pi, pd]),
     "phb_amg_host_coarse_inverse": (ci, [vp, pd]),
     "phb_amg_host_destroy": (ci, [vp]),
+    "phb_amg_dist_build": (ci, [ci, ci, pi, pi, pd, pi, cd, ci, cll, pvp]),
+    "phb_amg_dist_info": (ci, [vp, pi, pi, pi]),
+    "phb_amg_dist_tail": (vp, [vp, ci]),
+    "phb_amg_dist_matrix_size": (ci, [vp, ci, ci, ci, pi, C.POINTER(cll)]),
+    "phb_amg_dist_matrix": (ci, [vp, ci, ci, ci, pi, pi, pd, pi]),
+    "phb_amg_dist_halo": (ci, [vp, ci, ci, pi, pi, pi]),
+    "phb_amg_dist_destroy": (ci, [vp]),
     "phb_field_create": (ci, [vp, ci, cs, pvp]),
     "phb_field_destroy": (ci, [vp]),
     "phb_field_set_bc": (ci, [vp, cs, ci, cd, cd]),

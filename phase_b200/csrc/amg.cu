@@ -18,7 +18,11 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
 #include <numeric>
+#include <thread>
 
 #include "kernels.cuh"
 #include "solver.cuh"
@@ -107,7 +111,8 @@ int aggregate(const HCsr &A, const std::vector<double> &d, double theta, std::ve
     for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) {
       const int j = A.ci[k];
       const double a = A.v[k];
-      strong[k] = (j != i && a != 0. && a * a >= theta * theta * std::fabs(d[i] * d[j])) ? 1 : 0;
+      // columns >= n are ghosts (rows of another rank): aggregates and prolongator smoothing stay rank-local
+      strong[k] = (j != i && j < n && a != 0. && a * a >= theta * theta * std::fabs(d[i] * d[j])) ? 1 : 0;
     }
   agg.assign(n, -1);
   int nc = 0;
@@ -155,6 +160,12 @@ struct HostHierarchy {
 
 constexpr int kDenseMax = 1024;
 
+}  // namespace
+struct phb_amg_host {
+  HostHierarchy H;
+};
+namespace {
+
 bool dense_inverse(std::vector<double> &M, int n) {
   // Gauss-Jordan with partial pivoting on [M | I]
   std::vector<double> I((size_t)n * n, 0.);
@@ -184,98 +195,112 @@ bool dense_inverse(std::vector<double> &M, int n) {
   return true;
 }
 
+double gershgorin(const HCsr &A, const std::vector<double> &d) {
+  double rho = 0.;
+  for (int i = 0; i < A.n; ++i) {
+    double s = 0.;
+    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) s += std::fabs(A.v[k]);
+    rho = std::max(rho, s / std::fabs(d[i]));
+  }
+  return rho;
+}
+
+// One coarsening step on the rows of A (A.n owned rows; columns >= A.n are ghosts): fills the smoother data of
+// L and the prolongator P = (I - (omegaP / rho) Df^-1 Af) T with T(i, agg[i]) = 1 and Af the operator with weak
+// and ghost couplings lumped onto the diagonal (so that P reproduces the constant whenever A does).
+// Returns 1 when the level cannot be coarsened any further, 0 on success, < 0 on error.
+int make_prolongator(const HCsr &A, double theta, double omegaP, int level, HostLevel &L, HCsr &P, int &nc,
+                     bool allowStall = false) {
+  const int n = A.n;
+  std::vector<double> d = diagonal(A);
+  for (int i = 0; i < n; ++i)
+    if (d[i] == 0.) { set_error("amg: zero diagonal in row %d of level %d", i, level); return PHB_ERR_BREAKDOWN; }
+  L.diag = d;
+  L.rho = gershgorin(A, d);
+  std::vector<int> agg;
+  std::vector<char> strong;
+  nc = aggregate(A, d, theta, agg, strong);
+  if (!allowStall && (nc >= n || (long long)nc * 10 > (long long)n * 9)) return 1;
+  std::vector<double> df(d);
+  for (int i = 0; i < n; ++i)
+    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
+      if (!strong[k] && A.ci[k] != i) df[i] += A.v[k];
+  for (int i = 0; i < n; ++i)
+    if (df[i] == 0. || (df[i] > 0.) != (d[i] > 0.)) df[i] = d[i];
+  double rho = 0.;
+  for (int i = 0; i < n; ++i) {
+    double s = std::fabs(df[i]);
+    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
+      if (strong[k]) s += std::fabs(A.v[k]);
+    rho = std::max(rho, s / std::fabs(df[i]));
+  }
+  P = HCsr();
+  P.n = n; P.m = nc;
+  P.rp.assign(n + 1, 0);
+  std::vector<std::pair<int, double>> row;
+  const double w = omegaP / rho;
+  for (int i = 0; i < n; ++i) {
+    row.clear();
+    row.push_back({agg[i], 1. - w});  // diagonal term of Af: df/df = 1
+    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) {
+      if (!strong[k]) continue;
+      const int c = agg[A.ci[k]];
+      const double val = -w * A.v[k] / df[i];
+      bool hit = false;
+      for (auto &e : row)
+        if (e.first == c) { e.second += val; hit = true; break; }
+      if (!hit) row.push_back({c, val});
+    }
+    std::sort(row.begin(), row.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) {
+      return x.first < y.first;
+    });
+    for (auto &e : row) { P.ci.push_back(e.first); P.v.push_back(e.second); }
+    P.rp[i + 1] = (int)P.ci.size();
+  }
+  return 0;
+}
+
+bool rows_sum_to_zero(const HCsr &A) {
+  double maxRow = 0., maxDiag = 0.;
+  for (int i = 0; i < A.n; ++i) {
+    double sum = 0.;
+    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) {
+      sum += A.v[k];
+      if (A.ci[k] == i) maxDiag = std::max(maxDiag, std::fabs(A.v[k]));
+    }
+    maxRow = std::max(maxRow, std::fabs(sum));
+  }
+  return maxRow <= 1e-10 * maxDiag;
+}
+
 int build_hierarchy(HCsr A0, double theta, int coarsest, double omegaP, HostHierarchy &H) {
   const auto t0 = std::chrono::steady_clock::now();
   H.lev.clear();
   // singular with the constant in the null space? (all-Neumann pressure: every row sums to zero)
-  {
-    double maxRow = 0., maxDiag = 0.;
-    for (int i = 0; i < A0.n; ++i) {
-      double sum = 0.;
-      for (int k = A0.rp[i]; k < A0.rp[i + 1]; ++k) {
-        sum += A0.v[k];
-        if (A0.ci[k] == i) maxDiag = std::max(maxDiag, std::fabs(A0.v[k]));
-      }
-      maxRow = std::max(maxRow, std::fabs(sum));
-    }
-    H.singular = maxRow <= 1e-10 * maxDiag;
-  }
+  H.singular = rows_sum_to_zero(A0);
   const long long nnz0 = std::max<long long>(1, A0.nnz());
   long long nnzAll = 0;
   HCsr A = std::move(A0);
   for (int level = 0;; ++level) {
     HostLevel L;
     const int n = A.n;
-    std::vector<double> d = diagonal(A);
-    for (int i = 0; i < n; ++i)
-      if (d[i] == 0.) { set_error("amg: zero diagonal in row %d of level %d", i, level); return PHB_ERR_BREAKDOWN; }
     nnzAll += A.nnz();
     const bool last = n <= coarsest || level >= 15;
-    std::vector<int> agg;
-    std::vector<char> strong;
-    int nc = 0;
-    if (!last) nc = aggregate(A, d, theta, agg, strong);
-    if (last || nc >= n || nc * 10 > n * 9) {  // coarsest level (or coarsening stalled)
-      L.diag = d;
-      double rho = 0.;
-      for (int i = 0; i < n; ++i) {
-        double s = 0.;
-        for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) s += std::fabs(A.v[k]);
-        rho = std::max(rho, s / std::fabs(d[i]));
-      }
-      L.rho = rho;
+    HCsr P;
+    int nc = 0, rc = 1;
+    if (last) {
+      L.diag = diagonal(A);
+      for (int i = 0; i < n; ++i)
+        if (L.diag[i] == 0.) { set_error("amg: zero diagonal in row %d of level %d", i, level); return PHB_ERR_BREAKDOWN; }
+      L.rho = gershgorin(A, L.diag);
+    } else {
+      rc = make_prolongator(A, theta, omegaP, level, L, P, nc);
+      if (rc < 0) return rc;
+    }
+    if (rc == 1) {  // coarsest level (or coarsening stalled)
       L.A = std::move(A);
       H.lev.push_back(std::move(L));
       break;
-    }
-    // filtered operator: weak off-diagonals lumped onto the diagonal (identity when theta = 0)
-    std::vector<double> df(d);
-    for (int i = 0; i < n; ++i)
-      for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
-        if (!strong[k] && A.ci[k] != i) df[i] += A.v[k];
-    for (int i = 0; i < n; ++i)
-      if (df[i] == 0. || (df[i] > 0.) != (d[i] > 0.)) df[i] = d[i];
-    double rho = 0.;
-    for (int i = 0; i < n; ++i) {
-      double s = std::fabs(df[i]);
-      for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
-        if (strong[k]) s += std::fabs(A.v[k]);
-      rho = std::max(rho, s / std::fabs(df[i]));
-    }
-    // smoother data uses the full operator
-    {
-      double r2 = 0.;
-      for (int i = 0; i < n; ++i) {
-        double s = 0.;
-        for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) s += std::fabs(A.v[k]);
-        r2 = std::max(r2, s / std::fabs(d[i]));
-      }
-      L.rho = r2;
-      L.diag = d;
-    }
-    // P = (I - (omegaP / rho) Df^-1 Af) T,  T(i, agg[i]) = 1
-    HCsr P;
-    P.n = n; P.m = nc;
-    P.rp.assign(n + 1, 0);
-    std::vector<std::pair<int, double>> row;
-    const double w = omegaP / rho;
-    for (int i = 0; i < n; ++i) {
-      row.clear();
-      row.push_back({agg[i], 1. - w});  // diagonal term of Af: df/df = 1
-      for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) {
-        if (!strong[k]) continue;
-        const int c = agg[A.ci[k]];
-        const double val = -w * A.v[k] / df[i];
-        bool hit = false;
-        for (auto &e : row)
-          if (e.first == c) { e.second += val; hit = true; break; }
-        if (!hit) row.push_back({c, val});
-      }
-      std::sort(row.begin(), row.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) {
-        return x.first < y.first;
-      });
-      for (auto &e : row) { P.ci.push_back(e.first); P.v.push_back(e.second); }
-      P.rp[i + 1] = (int)P.ci.size();
     }
     L.R = transpose(P);
     HCsr AP = spgemm(A, P);
@@ -305,6 +330,240 @@ int build_hierarchy(HCsr A0, double theta, int coarsest, double omegaP, HostHier
   H.setupMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return PHB_OK;
 }
+
+// ===================================================================== distributed setup (nProcs > 1)
+// Aggregates and prolongator smoothing are rank-local (P is block diagonal over the ranks), the Galerkin
+// operators keep the couplings between ranks: A_c(rows of r) = P_r^T [A_rr P_r | A_rq P_q(ghost rows)], which
+// needs the P rows of the ghost cells (one neighbour exchange per level) and gives every coarse level its
+// own ghost columns and halo lists.  Once the global row count is small (`tailRows`) the level is gathered
+// on every rank and the rest of the hierarchy is the serial one, replicated: no communication below it.
+struct Exchanger {
+  int rank = 0, nProcs = 1;
+  virtual ~Exchanger() {}
+  virtual int allgatherv(const std::vector<char> &mine, std::vector<std::vector<char>> &all) = 0;
+};
+
+struct Halo {
+  std::vector<int> sendPtr, sendIdx;  // per destination rank: owned rows whose values it needs
+  std::vector<int> recvPtr;           // per source rank: ghost k of rank q is column n + recvPtr[q] + k
+};
+
+struct DistLevel {
+  HostLevel L;            // A: n x (n + g), P: n x nc (local coarse ids), R = P^T
+  Halo halo;
+  std::vector<int> gid;   // global id (within this level) of every column, owned then ghosts
+  int n = 0, g = 0;
+};
+
+struct DistHierarchy {
+  std::vector<DistLevel> dist;
+  std::vector<int> tailOff;   // nProcs + 1: rank segments of the first replicated level
+  phb_amg_host tail;
+  bool singular = false;
+  double setupMs = 0.;
+};
+
+template <typename T> void put(std::vector<char> &b, const T &v) {
+  const char *p = reinterpret_cast<const char *>(&v);
+  b.insert(b.end(), p, p + sizeof(T));
+}
+template <typename T> T take(const char *&p) {
+  T v;
+  memcpy(&v, p, sizeof(T));
+  p += sizeof(T);
+  return v;
+}
+
+int build_dist_hierarchy(Exchanger &ex, HCsr A, Halo halo, std::vector<int> gid, double theta, int coarsest,
+                         long long tailRows, double omegaP, DistHierarchy &H) {
+  const auto t0 = std::chrono::steady_clock::now();
+  const int NP = ex.nProcs, me = ex.rank;
+  H.dist.clear();
+  int localSingular = rows_sum_to_zero(A) ? 1 : 0;
+  std::vector<std::vector<char>> all;
+  for (int level = 0;; ++level) {
+    DistLevel D;
+    D.n = A.n; D.g = A.m - A.n;
+    D.halo = halo;
+    D.gid = gid;
+    HCsr P;
+    int nc = 0;
+    int rc = make_prolongator(A, theta, omegaP, level, D.L, P, nc, true);
+    // ---- exchange 1: coarse sizes + the P rows of the cells my neighbours hold as ghosts
+    std::vector<char> blob;
+    put<int>(blob, rc < 0 ? -1 : nc);
+    put<int>(blob, localSingular);
+    for (int q = 0; q < NP; ++q) {
+      const int cnt = rc < 0 ? 0 : halo.sendPtr[q + 1] - halo.sendPtr[q];
+      put<int>(blob, cnt);
+      for (int k = 0; k < cnt; ++k) {
+        const int i = halo.sendIdx[halo.sendPtr[q] + k];
+        put<int>(blob, P.rp[i + 1] - P.rp[i]);
+        for (int e = P.rp[i]; e < P.rp[i + 1]; ++e) { put<int>(blob, P.ci[e]); put<double>(blob, P.v[e]); }
+      }
+    }
+    PHB_CHECK(ex.allgatherv(blob, all));
+    std::vector<int> ncAll(NP), off(NP + 1, 0);
+    bool failed = false, singular = true;
+    for (int q = 0; q < NP; ++q) {
+      const char *p = all[q].data();
+      ncAll[q] = take<int>(p);
+      if (ncAll[q] < 0) failed = true;
+      if (!take<int>(p)) singular = false;
+    }
+    if (failed) {
+      if (rc >= 0) set_error("amg: the hierarchy setup failed on another rank");
+      return PHB_ERR_BREAKDOWN;
+    }
+    if (level == 0) H.singular = singular;
+    for (int q = 0; q < NP; ++q) off[q + 1] = off[q] + ncAll[q];
+    // P rows of my ghosts, coarse ghost numbering (grouped by owner, ascending coarse id)
+    std::vector<std::vector<std::pair<int, double>>> ghostRow(D.g);
+    std::vector<std::vector<int>> need(NP);   // coarse ids of rank q that appear in my ghost rows
+    for (int q = 0; q < NP; ++q) {
+      if (q == me) continue;
+      const char *p = all[q].data();
+      take<int>(p); take<int>(p);
+      for (int dst = 0; dst < NP; ++dst) {
+        const int cnt = take<int>(p);
+        for (int k = 0; k < cnt; ++k) {
+          const int len = take<int>(p);
+          for (int e = 0; e < len; ++e) {
+            const int cid = take<int>(p);
+            const double val = take<double>(p);
+            if (dst == me) {
+              ghostRow[halo.recvPtr[q] + k].push_back({cid, val});
+              need[q].push_back(cid);
+            }
+          }
+        }
+        if (dst == me && cnt != halo.recvPtr[q + 1] - halo.recvPtr[q]) {
+          set_error("amg: halo lists of ranks %d and %d disagree on level %d", me, q, level);
+          return PHB_ERR_STATE;
+        }
+      }
+    }
+    Halo ch;
+    ch.recvPtr.assign(NP + 1, 0);
+    for (int q = 0; q < NP; ++q) {
+      std::sort(need[q].begin(), need[q].end());
+      need[q].erase(std::unique(need[q].begin(), need[q].end()), need[q].end());
+      ch.recvPtr[q + 1] = ch.recvPtr[q] + (int)need[q].size();
+    }
+    const int gc = ch.recvPtr[NP];
+    // extended prolongator: owned rows then ghost rows, columns = own coarse ids then coarse ghosts
+    HCsr Pe;
+    Pe.n = D.n + D.g; Pe.m = nc + gc;
+    Pe.rp.assign(Pe.n + 1, 0);
+    Pe.ci = P.ci; Pe.v = P.v;
+    for (int i = 0; i < D.n; ++i) Pe.rp[i + 1] = P.rp[i + 1];
+    for (int q = 0; q < NP; ++q)
+      for (int k = halo.recvPtr[q]; k < halo.recvPtr[q + 1]; ++k) {
+        for (auto &e : ghostRow[k]) {
+          const int pos = (int)(std::lower_bound(need[q].begin(), need[q].end(), e.first) - need[q].begin());
+          Pe.ci.push_back(nc + ch.recvPtr[q] + pos);
+          Pe.v.push_back(e.second);
+        }
+        Pe.rp[D.n + k + 1] = (int)Pe.ci.size();
+      }
+    D.L.R = transpose(P);
+    HCsr AP = spgemm(A, Pe);
+    HCsr Ac = spgemm(D.L.R, AP);   // nc x (nc + gc)
+    // ---- exchange 2: tell every neighbour which of its coarse rows I hold as ghosts
+    blob.clear();
+    for (int q = 0; q < NP; ++q) {
+      put<int>(blob, (int)need[q].size());
+      for (int cid : need[q]) put<int>(blob, cid);
+    }
+    PHB_CHECK(ex.allgatherv(blob, all));
+    ch.sendPtr.assign(NP + 1, 0);
+    for (int q = 0; q < NP; ++q) {
+      const char *p = all[q].data();
+      for (int dst = 0; dst < NP; ++dst) {
+        const int cnt = take<int>(p);
+        for (int k = 0; k < cnt; ++k) {
+          const int cid = take<int>(p);
+          if (dst == me && q != me) ch.sendIdx.push_back(cid);
+        }
+      }
+      ch.sendPtr[q + 1] = (int)ch.sendIdx.size();
+    }
+    std::vector<int> cgid(nc + gc);
+    for (int i = 0; i < nc; ++i) cgid[i] = off[me] + i;
+    for (int q = 0; q < NP; ++q)
+      for (size_t k = 0; k < need[q].size(); ++k) cgid[nc + ch.recvPtr[q] + k] = off[q] + need[q][k];
+    D.L.P = std::move(P);
+    D.L.A = std::move(A);
+    H.dist.push_back(std::move(D));
+    A = std::move(Ac);
+    halo = std::move(ch);
+    gid = std::move(cgid);
+    localSingular = 1;
+    if ((long long)off[NP] <= tailRows || level + 1 >= 10) { H.tailOff = off; break; }
+  }
+  // ---- replicated tail: gather the level on every rank (rows in rank order, global column ids)
+  std::vector<char> blob;
+  put<int>(blob, A.n);
+  put<int>(blob, (int)A.nnz());
+  for (int i = 0; i <= A.n; ++i) put<int>(blob, A.rp[i]);
+  for (long long k = 0; k < A.nnz(); ++k) put<int>(blob, gid[A.ci[k]]);
+  for (long long k = 0; k < A.nnz(); ++k) put<double>(blob, A.v[k]);
+  PHB_CHECK(ex.allgatherv(blob, all));
+  HCsr G;
+  G.n = G.m = H.tailOff[NP];
+  G.rp.assign(1, 0);
+  std::vector<std::pair<int, double>> row;
+  for (int q = 0; q < NP; ++q) {
+    const char *p = all[q].data();
+    const int nr = take<int>(p), nz = take<int>(p);
+    const int *rp = reinterpret_cast<const int *>(p);
+    const int *ci = rp + nr + 1;
+    const char *vp = reinterpret_cast<const char *>(ci + nz);
+    for (int i = 0; i < nr; ++i) {
+      row.clear();
+      for (int k = rp[i]; k < rp[i + 1]; ++k) {
+        double v;
+        memcpy(&v, vp + (size_t)k * sizeof(double), sizeof(double));
+        row.push_back({ci[k], v});
+      }
+      std::sort(row.begin(), row.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) {
+        return x.first < y.first;
+      });
+      for (auto &e : row) { G.ci.push_back(e.first); G.v.push_back(e.second); }
+      G.rp.push_back((int)G.ci.size());
+    }
+  }
+  PHB_CHECK(build_hierarchy(std::move(G), theta, coarsest, omegaP, H.tail.H));
+  H.setupMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return PHB_OK;
+}
+
+// in-process exchanger: the ranks are threads of one process (CPU tests of the distributed setup)
+struct ThreadBoard {
+  std::mutex m;
+  std::condition_variable cv;
+  int arrived = 0;
+  long gen = 0;
+  std::vector<std::vector<char>> slots, published;
+};
+struct ThreadExchanger : Exchanger {
+  ThreadBoard *B = nullptr;
+  int allgatherv(const std::vector<char> &mine, std::vector<std::vector<char>> &all) override {
+    std::unique_lock<std::mutex> lk(B->m);
+    B->slots[rank] = mine;
+    if (++B->arrived == nProcs) {
+      B->published = B->slots;
+      B->arrived = 0;
+      B->gen++;
+      B->cv.notify_all();
+    } else {
+      const long g = B->gen;
+      B->cv.wait(lk, [&] { return B->gen != g; });
+    }
+    all = B->published;
+    return PHB_OK;
+  }
+};
 
 // sliced-ELL image of a host CSR matrix (diagonal moved to entry 0 when square)
 void sell_from_csr(const HCsr &A, bool diagFirst, SellPattern &S, std::vector<double> &slotVals) {
@@ -803,11 +1062,161 @@ int amg_apply(phb_solver *s, const double *in, double *out, bool inLoop) {
 }  // namespace phb
 
 // ===================================================================== C ABI (inspection / tests)
-struct phb_amg_host {
-  HostHierarchy H;
+struct phb_amg_dist {
+  int nRanks = 0;
+  std::vector<DistHierarchy> H;   // one per (virtual) rank
 };
 
 extern "C" {
+
+// Distributed setup with the ranks as threads of this process: `part[i]` = owner of global row i.
+// Local numbering as on the device: owned rows in ascending global order, ghosts grouped by owner.
+int phb_amg_dist_build(int nRanks, int n, const int *rowPtr, const int *colInd, const double *vals, const int *part,
+                       double theta, int coarsest, long long tailRows, phb_amg_dist **out) {
+  PHB_TRY_BEGIN
+  PHB_REQUIRE(nRanks >= 1 && nRanks <= 64 && n > 0 && rowPtr && colInd && vals && part && out,
+              "phb_amg_dist_build: bad argument");
+  std::vector<std::vector<int>> owned(nRanks);
+  std::vector<int> local(n);
+  for (int i = 0; i < n; ++i) {
+    PHB_REQUIRE(part[i] >= 0 && part[i] < nRanks, "phb_amg_dist_build: part[%d] out of range", i);
+    local[i] = (int)owned[part[i]].size();
+    owned[part[i]].push_back(i);
+  }
+  // ghosts of every rank: columns of its rows owned elsewhere, grouped by owner, ascending global id
+  std::vector<std::vector<std::vector<int>>> ghosts(nRanks, std::vector<std::vector<int>>(nRanks));
+  for (int r = 0; r < nRanks; ++r) {
+    for (int i : owned[r])
+      for (int k = rowPtr[i]; k < rowPtr[i + 1]; ++k)
+        if (colInd[k] >= 0 && part[colInd[k]] != r) ghosts[r][part[colInd[k]]].push_back(colInd[k]);
+    for (auto &g : ghosts[r]) {
+      std::sort(g.begin(), g.end());
+      g.erase(std::unique(g.begin(), g.end()), g.end());
+    }
+  }
+  std::vector<HCsr> A(nRanks);
+  std::vector<Halo> halo(nRanks);
+  std::vector<std::vector<int>> gid(nRanks);
+  for (int r = 0; r < nRanks; ++r) {
+    const int nl = (int)owned[r].size();
+    Halo &h = halo[r];
+    h.recvPtr.assign(nRanks + 1, 0);
+    h.sendPtr.assign(nRanks + 1, 0);
+    gid[r] = owned[r];
+    for (int q = 0; q < nRanks; ++q) {
+      h.recvPtr[q + 1] = h.recvPtr[q] + (int)ghosts[r][q].size();
+      for (int g : ghosts[r][q]) gid[r].push_back(g);
+      for (int g : ghosts[q][r]) h.sendIdx.push_back(local[g]);
+      h.sendPtr[q + 1] = (int)h.sendIdx.size();
+    }
+    HCsr &M = A[r];
+    M.n = nl; M.m = nl + h.recvPtr[nRanks];
+    M.rp.assign(1, 0);
+    std::vector<std::pair<int, double>> row;
+    for (int i : owned[r]) {
+      row.clear();
+      for (int k = rowPtr[i]; k < rowPtr[i + 1]; ++k) {
+        const int c = colInd[k];
+        if (c < 0) continue;
+        int lc;
+        if (part[c] == r) lc = local[c];
+        else {
+          const auto &g = ghosts[r][part[c]];
+          lc = nl + h.recvPtr[part[c]] + (int)(std::lower_bound(g.begin(), g.end(), c) - g.begin());
+        }
+        row.push_back({lc, vals[k]});
+      }
+      std::sort(row.begin(), row.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) {
+        return x.first < y.first;
+      });
+      for (auto &e : row) { M.ci.push_back(e.first); M.v.push_back(e.second); }
+      M.rp.push_back((int)M.ci.size());
+    }
+  }
+  std::unique_ptr<phb_amg_dist> h(new phb_amg_dist());
+  h->nRanks = nRanks;
+  h->H.resize(nRanks);
+  ThreadBoard board;
+  board.slots.resize(nRanks);
+  std::vector<int> rc(nRanks, PHB_OK);
+  std::vector<std::string> err(nRanks);
+  std::vector<std::thread> th;
+  for (int r = 0; r < nRanks; ++r)
+    th.emplace_back([&, r] {
+      ThreadExchanger ex;
+      ex.rank = r; ex.nProcs = nRanks; ex.B = &board;
+      rc[r] = build_dist_hierarchy(ex, std::move(A[r]), std::move(halo[r]), std::move(gid[r]), theta,
+                                   coarsest > 0 ? coarsest : 400, tailRows, 4. / 3., h->H[r]);
+      if (rc[r] != PHB_OK) err[r] = phb_last_error();
+    });
+  for (auto &t : th) t.join();
+  for (int r = 0; r < nRanks; ++r)
+    if (rc[r] != PHB_OK) { set_error("rank %d: %s", r, err[r].c_str()); return rc[r]; }
+  *out = h.release();
+  return PHB_OK;
+  PHB_TRY_END
+}
+
+int phb_amg_dist_info(const phb_amg_dist *h, int *nDistLevels, int *nTailLevels, int *singular) {
+  PHB_REQUIRE(h && nDistLevels && nTailLevels, "phb_amg_dist_info: NULL argument");
+  *nDistLevels = (int)h->H[0].dist.size();
+  *nTailLevels = (int)h->H[0].tail.H.lev.size();
+  if (singular) *singular = h->H[0].singular ? 1 : 0;
+  return PHB_OK;
+}
+
+// the replicated part of rank `rank` as a serial hierarchy (borrowed: do not destroy)
+const phb_amg_host *phb_amg_dist_tail(const phb_amg_dist *h, int rank) {
+  if (!h || rank < 0 || rank >= h->nRanks) return nullptr;
+  return &h->H[rank].tail;
+}
+
+// which: 0 = A_l (global column ids of level l), 1 = P_l (global column ids of level l + 1);
+// rows are the rank's owned rows, rowGid their global ids within level l
+int phb_amg_dist_matrix_size(const phb_amg_dist *h, int rank, int level, int which, int *nRows, long long *nnz) {
+  PHB_REQUIRE(h && nRows && nnz && rank >= 0 && rank < h->nRanks && level >= 0 &&
+              level < (int)h->H[rank].dist.size() && (which == 0 || which == 1), "phb_amg_dist_matrix_size: bad argument");
+  const DistLevel &D = h->H[rank].dist[level];
+  const HCsr &M = which == 0 ? D.L.A : D.L.P;
+  *nRows = M.n; *nnz = M.nnz();
+  return PHB_OK;
+}
+
+int phb_amg_dist_matrix(const phb_amg_dist *h, int rank, int level, int which, int *rowPtr, int *colGid,
+                        double *vals, int *rowGid) {
+  PHB_REQUIRE(h && rowPtr && colGid && vals && rowGid && rank >= 0 && rank < h->nRanks && level >= 0 &&
+              level < (int)h->H[rank].dist.size() && (which == 0 || which == 1), "phb_amg_dist_matrix: bad argument");
+  const DistHierarchy &H = h->H[rank];
+  const DistLevel &D = H.dist[level];
+  const HCsr &M = which == 0 ? D.L.A : D.L.P;
+  std::copy(M.rp.begin(), M.rp.end(), rowPtr);
+  std::copy(M.v.begin(), M.v.end(), vals);
+  for (int i = 0; i < D.n; ++i) rowGid[i] = D.gid[i];
+  if (which == 0) {
+    for (long long k = 0; k < M.nnz(); ++k) colGid[k] = D.gid[M.ci[k]];
+  } else {  // own coarse ids -> global: first owned id of the next level (or the rank's tail segment)
+    const int base = level + 1 < (int)H.dist.size() ? H.dist[level + 1].gid[0] : H.tailOff[rank];
+    for (long long k = 0; k < M.nnz(); ++k) colGid[k] = base + M.ci[k];
+  }
+  return PHB_OK;
+}
+
+// halo lists of a distributed level: sendPtr/recvPtr hold nRanks + 1 entries
+int phb_amg_dist_halo(const phb_amg_dist *h, int rank, int level, int *sendPtr, int *sendIdx, int *recvPtr) {
+  PHB_REQUIRE(h && sendPtr && sendIdx && recvPtr && rank >= 0 && rank < h->nRanks && level >= 0 &&
+              level < (int)h->H[rank].dist.size(), "phb_amg_dist_halo: bad argument");
+  const Halo &a = h->H[rank].dist[level].halo;
+  std::copy(a.sendPtr.begin(), a.sendPtr.end(), sendPtr);
+  std::copy(a.sendIdx.begin(), a.sendIdx.end(), sendIdx);
+  std::copy(a.recvPtr.begin(), a.recvPtr.end(), recvPtr);
+  return PHB_OK;
+}
+
+int phb_amg_dist_destroy(phb_amg_dist *h) {
+  delete h;
+  return PHB_OK;
+}
+
 
 int phb_amg_host_build(int n, const int *rowPtr, const int *colInd, const double *vals, double theta,
                        int coarsest, phb_amg_host **out) {

@@ -174,3 +174,130 @@ def test_tiny_matrix_is_one_dense_level():
     assert H.nLevels == 1 and H.dense
     assert np.abs(H.coarse_inverse() @ A.toarray() - np.eye(30)).max() < 1e-10
     H.close()
+
+
+# ------------------------------------------------------------------ distributed setup (ranks as threads)
+class DistAmg:
+    def __init__(self, A, part, theta=0.0, coarsest=40, tail_rows=150):
+        self.L = _capi.lib()
+        A = A.tocsr()
+        A.sort_indices()
+        self.n, self.nRanks = A.shape[0], int(part.max()) + 1
+        rp, ci, v = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64)
+        pt = np.ascontiguousarray(part, np.int32)
+        h = C.c_void_p()
+        rc = self.L.phb_amg_dist_build(self.nRanks, self.n, rp.ctypes.data_as(_capi.pi), ci.ctypes.data_as(_capi.pi),
+                                       v.ctypes.data_as(_capi.pd), pt.ctypes.data_as(_capi.pi), theta, coarsest,
+                                       tail_rows, C.byref(h))
+        assert rc == 0, self.L.phb_last_error()
+        self.h = h
+        a, b, s = C.c_int(), C.c_int(), C.c_int()
+        assert self.L.phb_amg_dist_info(h, C.byref(a), C.byref(b), C.byref(s)) == 0
+        self.nDist, self.nTail, self.singular = a.value, b.value, bool(s.value)
+
+    def rank_matrix(self, rank, level, which):
+        nr, nnz = C.c_int(), C.c_longlong()
+        assert self.L.phb_amg_dist_matrix_size(self.h, rank, level, which, C.byref(nr), C.byref(nnz)) == 0
+        rp, ci, v = np.zeros(nr.value + 1, np.int32), np.zeros(nnz.value, np.int32), np.zeros(nnz.value)
+        gid = np.zeros(nr.value, np.int32)
+        assert self.L.phb_amg_dist_matrix(self.h, rank, level, which, rp.ctypes.data_as(_capi.pi),
+                                          ci.ctypes.data_as(_capi.pi), v.ctypes.data_as(_capi.pd),
+                                          gid.ctypes.data_as(_capi.pi)) == 0
+        return rp, ci, v, gid
+
+    def global_matrix(self, level, which, shape):
+        """rows of all ranks stacked by their global ids"""
+        I, J, V = [], [], []
+        for r in range(self.nRanks):
+            rp, ci, v, gid = self.rank_matrix(r, level, which)
+            I.append(np.repeat(gid, np.diff(rp)))
+            J.append(ci)
+            V.append(v)
+        return sp.csr_matrix((np.concatenate(V), (np.concatenate(I), np.concatenate(J))), shape=shape)
+
+    def halo(self, rank, level, n_send_max):
+        sp_, si, rp_ = np.zeros(self.nRanks + 1, np.int32), np.zeros(n_send_max, np.int32), np.zeros(self.nRanks + 1, np.int32)
+        assert self.L.phb_amg_dist_halo(self.h, rank, level, sp_.ctypes.data_as(_capi.pi), si.ctypes.data_as(_capi.pi),
+                                        rp_.ctypes.data_as(_capi.pi)) == 0
+        return sp_, si[:sp_[-1]], rp_
+
+    def tail(self, rank):
+        t = HostAmg.__new__(HostAmg)
+        t.L = self.L
+        t.h = C.c_void_p(self.L.phb_amg_dist_tail(self.h, rank))
+        n, s, d = C.c_int(), C.c_int(), C.c_int()
+        assert self.L.phb_amg_host_levels(t.h, C.byref(n), C.byref(s), C.byref(d)) == 0
+        t.nLevels, t.singular, t.dense = n.value, bool(s.value), bool(d.value)
+        return t
+
+    def close(self):
+        self.L.phb_amg_dist_destroy(self.h)
+
+
+def block_partition(nx, ny, px, py):
+    j, i = np.divmod(np.arange(nx * ny), nx)
+    return (np.minimum(j * py // ny, py - 1) * px + np.minimum(i * px // nx, px - 1)).astype(np.int32)
+
+
+@pytest.mark.parametrize("px,py,fixed", [(2, 1, False), (2, 2, True), (1, 3, False)])
+def test_distributed_hierarchy_is_the_global_galerkin_hierarchy(px, py, fixed):
+    nx, ny = 48, 36
+    A = neumann_laplacian(nx, ny, fixed_left=fixed)
+    part = block_partition(nx, ny, px, py)
+    H = DistAmg(A, part)
+    assert H.nDist >= 2 and H.nTail >= 1 and H.singular == (not fixed)
+    sizes = [A.shape[0]]
+    Al = H.global_matrix(0, 0, A.shape)
+    assert abs(Al - A).max() == 0.0
+    levels = []
+    for l in range(H.nDist):
+        # coarse size = sum of the ranks' aggregate counts = columns of the stacked P
+        ncs = [H.rank_matrix(r, l, 1)[1].max() + 1 if len(H.rank_matrix(r, l, 1)[1]) else 0 for r in range(H.nRanks)]
+        nc = int(max(ncs))
+        P = H.global_matrix(l, 1, (sizes[-1], nc))
+        assert np.all(np.diff(P.indptr) >= 1)
+        if not fixed:
+            assert np.abs(P @ np.ones(nc) - 1.0).max() < 1e-12          # constant reproduced across rank boundaries
+        G = (P.T @ Al @ P).tocsr()
+        if l + 1 < H.nDist:
+            An = H.global_matrix(l + 1, 0, (nc, nc))
+        else:
+            An = H.tail(0).mat(0, 0)[0]                                   # gathered level, replicated on every rank
+            for r in range(1, H.nRanks):
+                assert abs(H.tail(r).mat(0, 0)[0] - An).max() == 0.0
+        assert An.shape == G.shape and abs(G - An).max() <= 1e-12 * abs(An).max()
+        levels.append((Al, P))
+        sizes.append(nc)
+        Al = An
+    # halo lists: what r sends to q is what q expects from r, level by level (checked through gids)
+    for l in range(H.nDist):
+        for r in range(H.nRanks):
+            sp_r, si_r, rp_r = H.halo(r, l, 100000)
+            gid_r = H.rank_matrix(r, l, 0)[3]
+            for q in range(H.nRanks):
+                if q == r:
+                    continue
+                sent = gid_r[si_r[sp_r[q]:sp_r[q + 1]]]
+                rp_q = H.halo(q, l, 100000)[2]
+                # ghost gids of q from r: columns n_q + recvPtr[r] .. of q's matrix -> recover from its column gids
+                rpq, ciq, vq, gidq = H.rank_matrix(q, l, 0)
+                assert rp_q[r + 1] - rp_q[r] == len(sent)
+                assert set(sent.tolist()) <= set(ciq.tolist())
+    # a V(1,1) cycle over the global levels + the replicated tail preconditions BiCGStab like the serial one
+    tail = H.tail(0).cycle()
+
+    def cyc(l, b):
+        if l == H.nDist:
+            return tail(b)
+        A_, P_ = levels[l]
+        rho = np.abs(sp.diags(1.0 / A_.diagonal()) @ A_).sum(axis=1).max()
+        w = (4.0 / 3.0 / rho) / A_.diagonal()
+        x = w * b
+        x = x + P_ @ cyc(l + 1, P_.T @ (b - A_ @ x))
+        return x + w * (b - A_ @ x)
+    b = np.random.default_rng(2).standard_normal(A.shape[0])
+    if not fixed:
+        b -= b.mean()
+    its, rel = bicgstab_iters(A, lambda v: cyc(0, v), b)
+    assert rel < 2e-8 and its <= 16, its
+    H.close()
