@@ -24,6 +24,7 @@
 #include <numeric>
 #include <thread>
 
+#include "comm.cuh"
 #include "kernels.cuh"
 #include "solver.cuh"
 
@@ -608,9 +609,10 @@ void sell_from_csr(const HCsr &A, bool diagFirst, SellPattern &S, std::vector<do
 }
 
 // local block (owned rows x owned columns) of a sliced-ELL matrix as host CSR
-HCsr csr_from_sell(const SellPattern &S, const std::vector<double> &slotVals) {
+HCsr csr_from_sell(const SellPattern &S, const std::vector<double> &slotVals, bool keepGhosts = false) {
   HCsr A;
   A.n = A.m = S.nRows;
+  if (keepGhosts) A.m = S.nCols;
   A.rp.assign(A.n + 1, 0);
   std::vector<std::pair<int, double>> row;
   for (int r = 0; r < A.n; ++r) {
@@ -619,7 +621,7 @@ HCsr csr_from_sell(const SellPattern &S, const std::vector<double> &slotVals) {
     for (int k = 0; k < S.hRowLen[r]; ++k) {
       const size_t slot = (size_t)S.hSliceOff[sl] + (size_t)k * 32 + lane;
       const int c = S.hCol[slot];
-      if (c >= A.n) continue;  // ghost column: rank-local preconditioner
+      if (c >= A.m) continue;  // ghost column dropped: rank-local preconditioner
       bool hit = false;
       for (auto &e : row)
         if (e.first == c) { e.second += slotVals[slot]; hit = true; break; }
@@ -761,6 +763,17 @@ __global__ void k_amg_to_float(long long n, const double *__restrict__ a, float 
     out[i] = (float)a[i];
 }
 
+// send list of a distributed level -> contiguous buffer [comp][nSend]
+template <typename T>
+__global__ void k_amg_pack(int nSend, int nc, int ld, const int *__restrict__ sendIdx, const T *__restrict__ x,
+                           T *__restrict__ buf, const KrylovSums *S, int maxIters) {
+  if (S && krylov_done(S, maxIters)) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nSend) return;
+  const int src = sendIdx[i];
+  for (int c = 0; c < nc; ++c) buf[(size_t)c * nSend + i] = x[(size_t)c * ld + src];
+}
+
 // max relative deviation of `a` from ratio * ref over the slots, ratio = a[first] / ref[first]
 __global__ void __launch_bounds__(kThreads)
 k_amg_changed(long long nSlots, const double *__restrict__ a, const double *__restrict__ ref, int first,
@@ -844,6 +857,7 @@ int rebuild_t(phb_solver *s) {
   HostHierarchy H;
   PHB_CHECK(build_hierarchy(csr_from_sell(*P, slotVals), D.theta, D.coarsest, 4. / 3., H));
   D.lev.clear();
+  D.nDist = 0;
   const int nLev = (int)H.lev.size();
   for (int l = 0; l < nLev; ++l) {
     std::unique_ptr<AmgLevel> L(new AmgLevel());
@@ -890,6 +904,119 @@ int rebuild_t(phb_solver *s) {
   return PHB_OK;
 }
 
+struct NcclExchanger : Exchanger {
+  phb_ctx *c = nullptr;
+  int allgatherv(const std::vector<char> &mine, std::vector<std::vector<char>> &all) override {
+    return comm_allgatherv_host(c, mine, all);
+  }
+};
+
+template <typename T>
+int finish_level(phb_solver *s, AmgLevel &L, const HostLevel &h, int ld, bool hasCoarse, bool uploadA) {
+  phb_ctx *c = s->ctx;
+  AmgData &D = s->amg;
+  L.n = h.A.n;
+  if (uploadA) PHB_CHECK(upload_mat<T>(c, h.A, true, L.A));
+  if (hasCoarse) {
+    PHB_CHECK(upload_mat<T>(c, h.P, false, L.P));
+    PHB_CHECK(upload_mat<T>(c, h.R, false, L.R));
+  }
+  std::vector<double> w(L.n);
+  for (int i = 0; i < L.n; ++i) w[i] = (D.omegaS / h.rho) / h.diag[i];
+  PHB_CHECK(upload_as<T>(L.w, w, c->stream));
+  L.ld = ld;
+  const size_t len = (size_t)ld * s->nComp;
+  PHB_CHECK(alloc_as<T>(L.x, len, c->stream)); PHB_CHECK(alloc_as<T>(L.x2, len, c->stream));
+  PHB_CHECK(alloc_as<T>(L.r, len, c->stream)); PHB_CHECK(alloc_as<T>(L.b, len, c->stream));
+  return PHB_OK;
+}
+
+// hierarchy spanning the ranks: level 0 = the solver's matrix with its ghost columns and the mesh's halo lists
+template <typename T>
+int rebuild_dist_t(phb_solver *s) {
+  phb_ctx *c = s->ctx;
+  AmgData &D = s->amg;
+  const SellPattern *P = s->pat;
+  const phb_mesh *m = s->halo;
+  const int NP = c->nProcs, me = c->rank;
+  std::vector<double> slotVals((size_t)P->nSlots);
+  PHB_CUDA(cudaMemcpyAsync(slotVals.data(), s->dVals, slotVals.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                           c->stream));
+  PHB_CUDA(cudaStreamSynchronize(c->stream));
+  HCsr A0 = csr_from_sell(*P, slotVals, true);
+  Halo h0;
+  h0.sendPtr.assign(NP + 1, 0);
+  h0.recvPtr.assign(NP + 1, 0);
+  for (int q = 0; q < NP; ++q) {
+    h0.sendPtr[q + 1] = h0.sendPtr[q] + m->hSendCnt[q];
+    h0.recvPtr[q + 1] = h0.recvPtr[q] + m->hRecvCnt[q];
+    PHB_REQUIRE(m->hSendOff[q] == h0.sendPtr[q] && (m->hRecvCnt[q] == 0 || m->hRecvOff[q] == P->nRows + h0.recvPtr[q]),
+                "amg: unexpected halo layout of the mesh (peer %d)", q);
+  }
+  h0.sendIdx = m->hSendDev;
+  std::vector<int> gid(A0.m);
+  std::iota(gid.begin(), gid.end(), 0);
+  NcclExchanger ex;
+  ex.rank = me; ex.nProcs = NP; ex.c = c;
+  DistHierarchy H;
+  PHB_CHECK(build_dist_hierarchy(ex, std::move(A0), std::move(h0), std::move(gid), D.theta, D.coarsest, D.tailRows,
+                                 4. / 3., H));
+  D.lev.clear();
+  D.nDist = (int)H.dist.size();
+  for (int l = 0; l < D.nDist; ++l) {
+    std::unique_ptr<AmgLevel> L(new AmgLevel());
+    DistLevel &d = H.dist[l];
+    PHB_CHECK(finish_level<T>(s, *L, d.L, d.n + d.g, true, l > 0));
+    L->dist = true;
+    L->sendOff.assign(NP, 0); L->sendCnt.assign(NP, 0); L->recvOff.assign(NP, 0); L->recvCnt.assign(NP, 0);
+    for (int q = 0; q < NP; ++q) {
+      L->sendOff[q] = d.halo.sendPtr[q]; L->sendCnt[q] = d.halo.sendPtr[q + 1] - d.halo.sendPtr[q];
+      L->recvOff[q] = d.n + d.halo.recvPtr[q]; L->recvCnt[q] = d.halo.recvPtr[q + 1] - d.halo.recvPtr[q];
+    }
+    L->nSend = (int)d.halo.sendIdx.size();
+    if (L->nSend) PHB_CHECK(L->sendIdx.upload(d.halo.sendIdx, c->stream));
+    PHB_CHECK(alloc_as<T>(L->sendBuf, (size_t)std::max(1, L->nSend) * s->nComp, c->stream));
+    PHB_CUDA(cudaStreamSynchronize(c->stream));
+    D.lev.push_back(std::move(L));
+  }
+  HostHierarchy &TH = H.tail.H;
+  const int nTail = (int)TH.lev.size();
+  for (int l = 0; l < nTail; ++l) {
+    std::unique_ptr<AmgLevel> L(new AmgLevel());
+    PHB_CHECK(finish_level<T>(s, *L, TH.lev[l], TH.lev[l].A.n, l + 1 < nTail, true));
+    D.lev.push_back(std::move(L));
+  }
+  D.tailOff = H.tailOff;
+  D.tailCnt.assign(NP, 0); D.tailSendOff.assign(NP, 0); D.tailSendCnt.assign(NP, 0);
+  for (int q = 0; q < NP; ++q) {
+    D.tailCnt[q] = H.tailOff[q + 1] - H.tailOff[q];
+    D.tailSendOff[q] = H.tailOff[me];
+    D.tailSendCnt[q] = H.tailOff[me + 1] - H.tailOff[me];
+  }
+  D.nCoarse = TH.lev.back().A.n;
+  D.denseCoarse = !TH.coarseInv.empty();
+  if (D.denseCoarse) PHB_CHECK(D.coarseInv.upload(TH.coarseInv, c->stream));
+  PHB_CHECK(D.refVals.alloc((size_t)P->nSlots));
+  PHB_CUDA(cudaMemcpyAsync(D.refVals.p, s->dVals, (size_t)P->nSlots * sizeof(double), cudaMemcpyDeviceToDevice,
+                           c->stream));
+  if (sizeof(T) == 4) {
+    PHB_CHECK(D.refValsF.alloc((size_t)P->nSlots));
+    PHB_LAUNCH(c, k_amg_to_float, grid_rows(c, P->nSlots), kThreads, 0, P->nSlots, D.refVals.p, D.refValsF.p);
+  }
+  PHB_CUDA(cudaStreamSynchronize(c->stream));
+  D.src = P;
+  D.nComp = s->nComp;
+  D.builtSingle = sizeof(T) == 4;
+  D.built = true;
+  D.setups++;
+  D.setupMs = H.setupMs;
+  D.opComplexity = TH.opComplexity;
+  D.itersAfterSetup = -1;
+  D.stale = false;
+  if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
+  return PHB_OK;
+}
+
 template <typename T> const T *level0_vals(const AmgData &D);
 template <> const float *level0_vals<float>(const AmgData &D) { return D.refValsF.p; }
 template <> const double *level0_vals<double>(const AmgData &D) { return D.refVals.p; }
@@ -900,8 +1027,33 @@ template <typename T> struct Cycle {
   bool inLoop;
   const KrylovSums *S;
   int nc;
+  bool failed = false;
   const SellPattern &pat(int l) const { return l == 0 ? *s->pat : D.lev[l]->A.pat; }
   const T *val(int l) const { return l == 0 ? level0_vals<T>(D) : as<T>(D.lev[l]->A.vals); }
+
+  // ghost refresh of a distributed level's vector (no-op on replicated / single-rank levels)
+  int halo(int l, T *x) {
+    AmgLevel &V = *D.lev[l];
+    if (!V.dist) return PHB_OK;
+    phb_ctx *c = s->ctx;
+    T *buf = as<T>(V.sendBuf);
+    if (V.nSend)
+      PHB_LAUNCH(c, (k_amg_pack<T>), (V.nSend + 255) / 256, 256, 0, V.nSend, nc, V.ld, V.sendIdx.p, (const T *)x, buf, S,
+                 s->maxIters);
+    for (int k = 0; k < nc; ++k)
+      PHB_CHECK(comm_exchange_bytes(c, buf + (size_t)k * V.nSend, V.sendOff.data(), V.sendCnt.data(),
+                                    x + (size_t)k * V.ld, V.recvOff.data(), V.recvCnt.data(), sizeof(T)));
+    return PHB_OK;
+  }
+  // first replicated level: every rank contributes its segment of the right-hand side
+  int gather_tail(T *b) {
+    AmgLevel &V = *D.lev[D.nDist];
+    for (int k = 0; k < nc; ++k)
+      PHB_CHECK(comm_exchange_bytes(s->ctx, b + (size_t)k * V.ld, D.tailSendOff.data(), D.tailSendCnt.data(),
+                                    b + (size_t)k * V.ld, D.tailOff.data(), D.tailCnt.data(), sizeof(T)));
+    return PHB_OK;
+  }
+  int mySeg(int l) const { return (D.nDist > 0 && l == D.nDist) ? D.tailOff[s->ctx->rank] : 0; }
 
   // pre-smoothing from a zero guess, residual, restriction; returns the level's iterate
   template <typename TB> T *down(int l, const TB *b) {
@@ -911,13 +1063,16 @@ template <typename T> struct Cycle {
     PHB_LAUNCH(s->ctx, (k_amg_scale<T, TB>), grid_rows(s->ctx, V.n), kThreads, 0, V.n, nc, ld, as<T>(V.w), b, x, S,
                s->maxIters);
     for (int k = 1; k < D.nu; ++k) {
+      if (halo(l, x) != PHB_OK) { failed = true; return x; }
       launch<2>(s, pat(l), val(l), (const T *)x, ld, x2, ld, b, (const T *)as<T>(V.w), inLoop);
       std::swap(x, x2);
     }
+    if (halo(l, x) != PHB_OK) { failed = true; return x; }
     launch<1>(s, pat(l), val(l), (const T *)x, ld, as<T>(V.r), ld, b, (const T *)nullptr, inLoop);
     AmgLevel &C = *D.lev[l + 1];
-    launch<0>(s, V.R.pat, (const T *)as<T>(V.R.vals), (const T *)as<T>(V.r), ld, as<T>(C.b), C.ld, (const T *)nullptr,
-              (const T *)nullptr, inLoop);
+    launch<0>(s, V.R.pat, (const T *)as<T>(V.R.vals), (const T *)as<T>(V.r), ld, as<T>(C.b) + mySeg(l + 1), C.ld,
+              (const T *)nullptr, (const T *)nullptr, inLoop);
+    if (D.nDist > 0 && l + 1 == D.nDist && gather_tail(as<T>(C.b)) != PHB_OK) failed = true;
     return x;
   }
   // coarse correction + post-smoothing; the last sweep of level 0 writes the fp64 result
@@ -925,9 +1080,10 @@ template <typename T> struct Cycle {
     AmgLevel &V = *D.lev[l];
     const int ld = V.ld;
     T *x2 = x == as<T>(V.x) ? as<T>(V.x2) : as<T>(V.x);
-    launch<3>(s, V.P.pat, (const T *)as<T>(V.P.vals), xc, D.lev[l + 1]->ld, x, ld, (const T *)nullptr,
+    launch<3>(s, V.P.pat, (const T *)as<T>(V.P.vals), xc + mySeg(l + 1), D.lev[l + 1]->ld, x, ld, (const T *)nullptr,
               (const T *)nullptr, inLoop);
     for (int k = 0; k < D.nu; ++k) {
+      if (halo(l, x) != PHB_OK) { failed = true; return x; }
       if (out && k == D.nu - 1) {
         launch<2>(s, pat(l), val(l), (const T *)x, ld, out, ld, b, (const T *)as<T>(V.w), inLoop);
         return nullptr;
@@ -974,7 +1130,7 @@ template <typename T> struct Cycle {
     for (int l = L - 2; l >= 1; --l)
       xOf[l] = up(l, (const T *)as<T>(D.lev[l]->b), xOf[l], (const T *)xOf[l + 1], nullptr);
     up(0, in, xOf[0], (const T *)xOf[1], out);
-    return PHB_OK;
+    return failed ? PHB_ERR_COMM : PHB_OK;
   }
 };
 
@@ -1003,7 +1159,20 @@ int amg_prepare(phb_solver *s) {
       need = true;
     if (D.rebuildAlways && D.stale) need = true;
   }
-  if (need) PHB_CHECK(D.single ? rebuild_t<float>(s) : rebuild_t<double>(s));
+  const bool dist = c->nProcs > 1 && s->halo && D.global;
+  if (c->nProcs > 1) {  // the setup talks to the other ranks: everybody rebuilds or nobody does
+    PHB_CHECK(D.chk.alloc(2));
+    const double flag[2] = {need ? 1. : 0., 0.};
+    PHB_CUDA(cudaMemcpyAsync(D.chk.p, flag, sizeof(flag), cudaMemcpyHostToDevice, c->stream));
+    PHB_CHECK(comm_allreduce_max(c, D.chk.p, 1));
+    PHB_CUDA(cudaMemcpyAsync(c->pinned, D.chk.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PHB_CUDA(cudaStreamSynchronize(c->stream));
+    need = c->pinned[0] > 0.5;
+  }
+  if (need) {
+    if (dist) PHB_CHECK(D.single ? rebuild_dist_t<float>(s) : rebuild_dist_t<double>(s));
+    else PHB_CHECK(D.single ? rebuild_t<float>(s) : rebuild_t<double>(s));
+  }
   return PHB_OK;
 }
 
@@ -1016,7 +1185,10 @@ int amg_launches_per_apply(const phb_solver *s) {
   const int L = (int)D.lev.size();
   if (L == 0) return 0;
   const int perLevel = 1 + (D.nu - 1) + 2 + 1 + D.nu;  // scale, extra pre, residual + restrict, prolong, post
-  return (L - 1) * perLevel + (D.denseCoarse ? 1 : 1 + kCoarseSweeps);
+  int packs = 0;                                       // one pack kernel per ghost refresh of a distributed level
+  for (int l = 0; l < D.nDist; ++l)
+    if (D.lev[l]->nSend) packs += 2 * D.nu;
+  return (L - 1) * perLevel + (D.denseCoarse ? 1 : 1 + kCoarseSweeps) + packs;
 }
 
 // algorithmic bytes of one cycle: every matrix streamed once per use (index + value per entry, 4 B per row

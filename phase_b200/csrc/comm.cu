@@ -4,6 +4,9 @@
 // libnccl is dlopen'ed (the torch-bundled libnccl.so.2 is already mapped in a
 // torchrun rank; a single-GPU process never touches it).
 #include <dlfcn.h>
+
+#include <algorithm>
+#include <vector>
 #include <nccl.h>
 
 #include "comm.cuh"
@@ -17,6 +20,7 @@ struct Nccl {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -46,6 +50,7 @@ int load() {
   SYM(CommInitRank, "ncclCommInitRank")
   SYM(CommDestroy, "ncclCommDestroy")
   SYM(AllReduce, "ncclAllReduce")
+  SYM(AllGather, "ncclAllGather")
   SYM(Send, "ncclSend")
   SYM(Recv, "ncclRecv")
   SYM(GroupStart, "ncclGroupStart")
@@ -118,6 +123,50 @@ int comm_exchange(phb_ctx *c, const double *sendBuf, const int *sendOff, const i
       PHB_NCCL(g.Recv(recvBuf + recvOff[q], recvCnt[q], ncclDouble, q, (ncclComm_t)c->comm, c->stream));
   }
   PHB_NCCL(g.GroupEnd());
+  return PHB_OK;
+}
+
+int comm_exchange_bytes(phb_ctx *c, const void *sendBuf, const int *sendOff, const int *sendCnt, void *recvBuf,
+                        const int *recvOff, const int *recvCnt, size_t elem) {
+  if (c->nProcs == 1) return PHB_OK;
+  PHB_NCCL(g.GroupStart());
+  for (int q = 0; q < c->nProcs; ++q) {
+    if (q == c->rank) continue;
+    if (sendCnt[q])
+      PHB_NCCL(g.Send((const char *)sendBuf + (size_t)sendOff[q] * elem, (size_t)sendCnt[q] * elem, ncclChar, q,
+                      (ncclComm_t)c->comm, c->stream));
+    if (recvCnt[q])
+      PHB_NCCL(g.Recv((char *)recvBuf + (size_t)recvOff[q] * elem, (size_t)recvCnt[q] * elem, ncclChar, q,
+                      (ncclComm_t)c->comm, c->stream));
+  }
+  PHB_NCCL(g.GroupEnd());
+  return PHB_OK;
+}
+
+int comm_allgatherv_host(phb_ctx *c, const std::vector<char> &mine, std::vector<std::vector<char>> &all) {
+  const int P = c->nProcs;
+  all.assign(P, std::vector<char>());
+  if (P == 1) { all[0] = mine; return PHB_OK; }
+  long long *dSizes = nullptr;
+  PHB_CUDA(cudaMalloc((void **)&dSizes, P * sizeof(long long)));
+  const long long my = (long long)mine.size();
+  std::vector<long long> sizes(P, 0);
+  PHB_CUDA(cudaMemcpyAsync(dSizes + c->rank, &my, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  PHB_NCCL(g.AllGather(dSizes + c->rank, dSizes, 1, ncclInt64, (ncclComm_t)c->comm, c->stream));
+  PHB_CUDA(cudaMemcpyAsync(sizes.data(), dSizes, P * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  PHB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(dSizes);
+  size_t slot = 16;
+  for (long long sz : sizes) slot = std::max(slot, ((size_t)sz + 15) / 16 * 16);
+  char *dBuf = nullptr;
+  PHB_CUDA(cudaMalloc((void **)&dBuf, slot * P));
+  if (my) PHB_CUDA(cudaMemcpyAsync(dBuf + slot * c->rank, mine.data(), (size_t)my, cudaMemcpyHostToDevice, c->stream));
+  PHB_NCCL(g.AllGather(dBuf + slot * c->rank, dBuf, slot, ncclChar, (ncclComm_t)c->comm, c->stream));
+  std::vector<char> host(slot * P);
+  PHB_CUDA(cudaMemcpyAsync(host.data(), dBuf, slot * P, cudaMemcpyDeviceToHost, c->stream));
+  PHB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(dBuf);
+  for (int q = 0; q < P; ++q) all[q].assign(host.begin() + slot * q, host.begin() + slot * q + (size_t)sizes[q]);
   return PHB_OK;
 }
 }  // namespace phb

@@ -1,6 +1,8 @@
 // comm.cuh -- NCCL plumbing (loaded at run time from the torch-bundled libnccl so
 // that a single-GPU process never needs it).
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace phb {
@@ -14,6 +16,12 @@ int comm_allreduce_max(phb_ctx *c, double *dev, int n);
 // for each peer q: send sendBuf[sendOff[q] .. +sendCnt[q]) , recv into recvBuf[recvOff[q] .. +recvCnt[q])
 int comm_exchange(phb_ctx *c, const double *sendBuf, const int *sendOff, const int *sendCnt,
                   double *recvBuf, const int *recvOff, const int *recvCnt);
+
+// the same with elements of `elem` bytes (offsets and counts in elements): single-precision level vectors
+int comm_exchange_bytes(phb_ctx *c, const void *sendBuf, const int *sendOff, const int *sendCnt, void *recvBuf,
+                        const int *recvOff, const int *recvCnt, size_t elem);
+// all-gather of one host byte blob per rank (setup-time metadata exchange; staged through device memory)
+int comm_allgatherv_host(phb_ctx *c, const std::vector<char> &mine, std::vector<std::vector<char>> &all);
 
 // ---- peer-memory path (peer.cu)
 struct PeerHalo {             // per-mesh halo description for the peer kernels

@@ -686,6 +686,12 @@ int phb_solver_setup(phb_solver *s, const char *key, const char *value) {
   } else if (k == "amgPrecision") {
     PHB_REQUIRE(lv == "single" || lv == "double" || lv == "float", "amgPrecision must be \"single\" or \"double\"");
     s->amg.single = lv != "double";
+  } else if (k == "amgScope") {
+    PHB_REQUIRE(lv == "global" || lv == "local", "amgScope must be \"global\" or \"local\"");
+    s->amg.global = lv == "global"; s->amg.built = false;
+  } else if (k == "amgTailRows") {
+    s->amg.tailRows = std::stoll(v); s->amg.built = false;
+    PHB_REQUIRE(s->amg.tailRows >= 1, "amgTailRows must be positive");
   } else if (k == "amgRebuild") {
     PHB_REQUIRE(lv == "auto" || lv == "always", "amgRebuild must be \"auto\" or \"always\"");
     s->amg.rebuildAlways = lv == "always";

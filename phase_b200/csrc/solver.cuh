@@ -73,6 +73,13 @@ struct AmgLevel {
   AmgMat A, P, R;                  // level operator (levels >= 1), prolongator n x n_c, restriction n_c x n
   phb::DevBuf<double> w;           // smoother weight omega / a_ii
   phb::DevBuf<double> x, x2, b, r;
+  // distributed levels (nProcs > 1, `amgScope global`): the operator has ghost columns, refreshed by a
+  // neighbour exchange before every residual / smoothing sweep
+  bool dist = false;
+  int nSend = 0;
+  std::vector<int> sendOff, sendCnt, recvOff, recvCnt;   // per rank; recvOff = index into the level vector
+  phb::DevBuf<int> sendIdx;
+  phb::DevBuf<double> sendBuf;
 };
 constexpr int kCoarseSweeps = 8;   // Jacobi sweeps on a coarsest level too large for a dense inverse
 struct AmgData {
@@ -80,6 +87,10 @@ struct AmgData {
   phb::DevBuf<double> coarseInv, refVals, chk;
   phb::DevBuf<float> refValsF;
   bool single = true, builtSingle = true;   // cycle precision (`amgPrecision single|double`)
+  bool global = true;                       // nProcs > 1: hierarchy spans the ranks (else rank-local blocks)
+  int nDist = 0;                            // leading distributed levels; level nDist is gathered on every rank
+  long long tailRows = 200000;
+  std::vector<int> tailOff, tailCnt, tailSendOff, tailSendCnt;
   const SellPattern *src = nullptr;
   bool built = false, denseCoarse = false, stale = false, rebuildAlways = false;
   int nComp = 1, nCoarse = 0, nu = 1, coarsest = 400, setups = 0, itersAfterSetup = -1;

@@ -22,6 +22,8 @@ def _ngpus():
 @pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
 @pytest.mark.parametrize("args", [["--peer", "--precond", "ilu0"], ["--peer", "--fused", "--precond", "jacobi"],
                                   ["--kind", "tri", "--nx", "30", "--ny", "26"],
+                                  ["--peer", "--precond", "amg", "--nx", "64", "--ny", "48"],
+                                  ["--precond", "amg", "--kind", "tri", "--nx", "30", "--ny", "26", "--amg-scope", "local"],
                                   ["--peer", "--strip", "--nx", "40", "--ny", "64", "--precond", "jacobi"]])
 def test_two_rank_parity(args):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",

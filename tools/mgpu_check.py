@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--strip", action="store_true")
     ap.add_argument("--precond", default="jacobi")
+    ap.add_argument("--amg-scope", default="global", choices=["global", "local"])
+    ap.add_argument("--amg-tail-rows", type=int, default=200)
     ap.add_argument("--peer", action="store_true", help="NVLink peer-memory exchanges inside the Krylov loop")
     ap.add_argument("--fused", action="store_true", help="peer pushes/waits inside the compute kernels")
     a = ap.parse_args()
@@ -56,7 +58,8 @@ def main():
     fs = lid_driven_cavity(gl, 1.0, 0.1, solver=dict(tolerance=1e-11, maxIters=50000,
                                                      preconditioner="ilu0" if amg else a.precond,
                                                      peerFusion=1 if a.fused else 0),
-                           pSolver=dict(preconditioner="amg", amgCoarsest=40) if amg else None)
+                           pSolver=dict(preconditioner="amg", amgCoarsest=40, amgScope=a.amg_scope,
+                                        amgTailRows=a.amg_tail_rows) if amg else None)
     om = (O.Mesh.rectilinear if a.kind == "rect" else O.Mesh.triangulated)(a.nx, a.ny, 1.0, 1.0)
     ofs = O.cavity(om, 1.0, 0.1)
     ofs.use_direct_solver()
