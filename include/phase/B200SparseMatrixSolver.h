@@ -5,8 +5,8 @@
 //
 // Contract honoured: rows local / columns global / -1 trailing
 // padding skipped; setRhs receives -rhs_ and copies it; x(i) is a host getter valid
-// after solve(); setup() reads solver / maxIters / tolerance / preconditioner /
-// iluFill; one instance lives as long as its equation, so the device copy of the
+// after solve(); setup() reads solver / maxIters / tolerance / preconditioner (jacobi | ilu0 | amg) /
+// iluFill and the amg* keys; one instance lives as long as its equation, so the device copy of the
 // pattern, the CUDA graph of the iteration and all work vectors are cached in
 // the C-side solver across time steps.
 #ifndef PHASE_B200_B200_SPARSE_MATRIX_SOLVER_H
@@ -72,7 +72,11 @@ public:
   // keys of LinearAlgebra.<eqn> (reference: M/TrilinosBelosSparseMatrixSolver.cpp:44-86)
   void setup(const boost::property_tree::ptree &p) override {
     static const char *keys[] = {"solver", "maxIters", "tolerance", "preconditioner", "iluFill",
-                                 "innerPreconditioner", "schwarzIters", "schwarzCombineMode", "schwarzOverlap"};
+                                 "innerPreconditioner", "schwarzIters", "schwarzCombineMode", "schwarzOverlap",
+                                 "ordering", "nullSpace", "itersPerGraph",
+                                 // preconditioner amg (the reference's `lib muelu` role)
+                                 "amgTheta", "amgCoarsest", "amgSweeps", "amgSmootherWeight", "amgPrecision",
+                                 "amgRebuild", "amgScope", "amgTailRows"};
     for (const char *k : keys) {
       const boost::property_tree::ptree *c = p.get_child_optional(k);
       if (c) phase::check(phb_solver_setup(s_, k, c->data().c_str()), "B200SparseMatrixSolver", "setup");

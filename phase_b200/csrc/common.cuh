@@ -125,7 +125,13 @@ struct phb_ctx {
   // pinned scratch for small device->host reads
   double *pinned = nullptr;
   PeerComm peer;
+  // live solvers: their CUDA graphs may hold NCCL nodes, which must be gone before the communicator is
+  std::vector<struct phb_solver *> solvers;
 };
+
+namespace phb {
+void solver_drop_graph(struct phb_solver *s);   // solver.cu
+}
 
 #define PHB_LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
   do {                                                                         \

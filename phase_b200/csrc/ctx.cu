@@ -55,6 +55,9 @@ int phb_ctx_destroy(phb_ctx *c) {
     return PHB_OK;
   }
   cudaSetDevice(c->device);
+  // a captured graph with NCCL nodes keeps the communicator alive: ncclCommDestroy would wait for it forever
+  for (phb_solver *s : c->solvers) phb::solver_drop_graph(s);
+  cudaStreamSynchronize(c->stream);
   phb::peer_destroy(c);
   phb::comm_destroy(c);
   if (c->stream) cudaStreamDestroy(c->stream);

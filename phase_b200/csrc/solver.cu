@@ -425,6 +425,10 @@ int ensure_vectors(phb_solver *s) {
 
 namespace phb {
 
+void solver_drop_graph(phb_solver *s) {
+  if (s && s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
+}
+
 int solver_bind(phb_solver *s, const SellPattern *pat, const double *dVals, int nComp, const phb_mesh *halo) {
   PHB_REQUIRE(nComp == 1 || nComp == 2, "solver: nComp must be 1 or 2");
   const bool resized = (s->pat != pat) || s->nComp != nComp || s->ld != pat->nCols;
@@ -633,12 +637,15 @@ int phb_solver_create(phb_ctx *ctx, phb_solver **out) {
   phb_solver *s = new phb_solver();
   s->ctx = ctx;
   if (getenv("PHB_NO_GRAPH")) s->useGraph = false;
+  ctx->solvers.push_back(s);
   *out = s;
   return PHB_OK;
 }
 
 int phb_solver_destroy(phb_solver *s) {
   if (!s) return PHB_OK;
+  auto &live = s->ctx->solvers;
+  live.erase(std::remove(live.begin(), live.end(), s), live.end());
   if (s->graphExec) cudaGraphExecDestroy(s->graphExec);
   delete s;
   return PHB_OK;

@@ -64,8 +64,13 @@ def main():
     ofs = O.cavity(om, 1.0, 0.1)
     ofs.use_direct_solver()
     dt = 0.5 / a.nx
-    for _ in range(a.steps):
+    if os.environ.get("PHB_CHECK_TRACE"):
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["PHB_CHECK_TRACE"]), exit=True)
+    trace = lambda *m: print("[rank %d]" % rank, *m, flush=True) if os.environ.get("PHB_CHECK_TRACE") else None
+    for k in range(a.steps):
         st = fs.solve(dt)
+        trace("step", k, st)
         ofs.step(dt)
     owner, gid = gl.i32("owner"), gl.i32("globalId")
     mine = owner == rank
@@ -87,7 +92,9 @@ def main():
     s1 = SparseMatrixSolver(comm).setup(dict(tolerance=1e-11, maxIters=50000, preconditioner=a.precond,
                                              nullSpace="constant"))
     s1.setHalo(gl)
+    trace("seam1 set")
     s1.setRank(len(rhs)); s1.set(rp, ci, va); s1.setRhs(-rhs); s1.solve()
+    trace("seam1 solved", s1.nIters())
     x1 = s1.x()
     fs.pEqn.solver.setup(dict(tolerance=1e-11))
     fs.p.fill(0.0)
@@ -104,7 +111,7 @@ def main():
            "OK" if ok else "FAIL"), flush=True)
     t = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(t)
-    fs.close(); gl.close(); comm.close()
+    s1.close(); fs.close(); gl.close(); comm.close()
     dist.destroy_process_group()
     sys.exit(int(t.item() != 0))
 
