@@ -207,10 +207,11 @@ int phb_amg_host_level_csr(const phb_amg_host *h, int level, int which, int *row
                            double *vals);
 int phb_amg_host_coarse_inverse(const phb_amg_host *h, double *inv);
 int phb_amg_host_destroy(phb_amg_host *h);
-/* The distributed setup used when nProcs > 1 (`amgScope global`): aggregates are rank-local, the Galerkin
- * operators keep the couplings between ranks, the level with <= tailRows global rows is gathered and the
+/* The distributed setup used when nProcs > 1 (`amgScope global`): aggregates are rank-local, the prolongator
+ * is smoothed across the rank boundaries, the Galerkin operators R A P keep the couplings between ranks, the level with <= tailRows global rows is gathered and the
  * rest of the hierarchy replicated.  Test hook: the ranks run as threads of this process, `part[i]` is
- * the owner of global row i.  Matrices come back with GLOBAL ids of their level (which: 0 = A_l, 1 = P_l). */
+ * the owner of global row i.  Matrices come back with GLOBAL ids of their level (which: 0 = A_l, 1 = P_l,
+ * 2 = R_l: the restriction is the part of P_l^T inside the rank, so it needs no communication). */
 typedef struct phb_amg_dist phb_amg_dist;
 int phb_amg_dist_build(int nRanks, int n, const int *rowPtr, const int *colInd, const double *vals,
                        const int *part, double theta, int coarsest, long long tailRows, phb_amg_dist **out);

@@ -382,26 +382,35 @@ int build_dist_hierarchy(Exchanger &ex, HCsr A, Halo halo, std::vector<int> gid,
   H.dist.clear();
   int localSingular = rows_sum_to_zero(A) ? 1 : 0;
   std::vector<std::vector<char>> all;
+  typedef std::pair<int, double> Entry;
+  auto byCol = [](const Entry &x, const Entry &y) { return x.first < y.first; };
   for (int level = 0;; ++level) {
     DistLevel D;
-    D.n = A.n; D.g = A.m - A.n;
+    const int n = A.n, g = A.m - A.n;
+    D.n = n; D.g = g;
     D.halo = halo;
     D.gid = gid;
-    HCsr P;
+    // ---- rank-local aggregation (ghost columns are never strong, so aggregates stay inside the rank)
+    std::vector<double> d = diagonal(A);
+    int bad = 0;
+    for (int i = 0; i < n; ++i)
+      if (d[i] == 0.) { set_error("amg: zero diagonal in row %d of level %d", i, level); bad = 1; break; }
+    std::vector<int> agg;
+    std::vector<char> strong;
     int nc = 0;
-    int rc = make_prolongator(A, theta, omegaP, level, D.L, P, nc, true);
-    // ---- exchange 1: coarse sizes + the P rows of the cells my neighbours hold as ghosts
+    if (!bad) {
+      D.L.diag = d;
+      D.L.rho = gershgorin(A, d);
+      nc = aggregate(A, d, theta, agg, strong);
+    }
+    // ---- exchange 0: coarse sizes + the aggregate of every cell a neighbour holds as a ghost
     std::vector<char> blob;
-    put<int>(blob, rc < 0 ? -1 : nc);
+    put<int>(blob, bad ? -1 : nc);
     put<int>(blob, localSingular);
     for (int q = 0; q < NP; ++q) {
-      const int cnt = rc < 0 ? 0 : halo.sendPtr[q + 1] - halo.sendPtr[q];
+      const int cnt = bad ? 0 : halo.sendPtr[q + 1] - halo.sendPtr[q];
       put<int>(blob, cnt);
-      for (int k = 0; k < cnt; ++k) {
-        const int i = halo.sendIdx[halo.sendPtr[q] + k];
-        put<int>(blob, P.rp[i + 1] - P.rp[i]);
-        for (int e = P.rp[i]; e < P.rp[i + 1]; ++e) { put<int>(blob, P.ci[e]); put<double>(blob, P.v[e]); }
-      }
+      for (int k = 0; k < cnt; ++k) put<int>(blob, agg[halo.sendIdx[halo.sendPtr[q] + k]]);
     }
     PHB_CHECK(ex.allgatherv(blob, all));
     std::vector<int> ncAll(NP), off(NP + 1, 0);
@@ -413,64 +422,137 @@ int build_dist_hierarchy(Exchanger &ex, HCsr A, Halo halo, std::vector<int> gid,
       if (!take<int>(p)) singular = false;
     }
     if (failed) {
-      if (rc >= 0) set_error("amg: the hierarchy setup failed on another rank");
+      if (!bad) set_error("amg: the hierarchy setup failed on another rank");
       return PHB_ERR_BREAKDOWN;
     }
     if (level == 0) H.singular = singular;
     for (int q = 0; q < NP; ++q) off[q + 1] = off[q] + ncAll[q];
-    // P rows of my ghosts, coarse ghost numbering (grouped by owner, ascending coarse id)
-    std::vector<std::vector<std::pair<int, double>>> ghostRow(D.g);
-    std::vector<std::vector<int>> need(NP);   // coarse ids of rank q that appear in my ghost rows
+    const bool lastDist = (long long)off[NP] <= tailRows || level + 1 >= 10;
+    std::vector<int> ghostAgg(g, -1);  // GLOBAL coarse id of the aggregate of every ghost cell
     for (int q = 0; q < NP; ++q) {
       if (q == me) continue;
       const char *p = all[q].data();
       take<int>(p); take<int>(p);
       for (int dst = 0; dst < NP; ++dst) {
         const int cnt = take<int>(p);
-        for (int k = 0; k < cnt; ++k) {
-          const int len = take<int>(p);
-          for (int e = 0; e < len; ++e) {
-            const int cid = take<int>(p);
-            const double val = take<double>(p);
-            if (dst == me) {
-              ghostRow[halo.recvPtr[q] + k].push_back({cid, val});
-              need[q].push_back(cid);
-            }
-          }
-        }
         if (dst == me && cnt != halo.recvPtr[q + 1] - halo.recvPtr[q]) {
           set_error("amg: halo lists of ranks %d and %d disagree on level %d", me, q, level);
           return PHB_ERR_STATE;
         }
+        for (int k = 0; k < cnt; ++k) {
+          const int cid = take<int>(p);
+          if (dst == me) ghostAgg[halo.recvPtr[q] + k] = off[q] + cid;
+        }
       }
     }
+    // ---- prolongator rows of the owned cells, GLOBAL coarse ids: P = (I - w Df^-1 Af) T where Af keeps
+    // the couplings to other ranks (smooth basis functions across the interfaces) and lumps weak local ones
+    std::vector<double> df(d);
+    for (int i = 0; i < n; ++i)
+      for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
+        if (!strong[k] && A.ci[k] != i && A.ci[k] < n) df[i] += A.v[k];
+    for (int i = 0; i < n; ++i)
+      if (df[i] == 0. || (df[i] > 0.) != (d[i] > 0.)) df[i] = d[i];
+    double rho = 0.;
+    for (int i = 0; i < n; ++i) {
+      double sum = std::fabs(df[i]);
+      for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
+        if (strong[k] || A.ci[k] >= n) sum += std::fabs(A.v[k]);
+      rho = std::max(rho, sum / std::fabs(df[i]));
+    }
+    const double w = omegaP / std::max(rho, 1e-300);
+    std::vector<std::vector<Entry>> Prow(n + g);
+    for (int i = 0; i < n; ++i) {
+      std::vector<Entry> &row = Prow[i];
+      row.push_back({off[me] + agg[i], 1. - w});
+      for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) {
+        const int j = A.ci[k];
+        if (!(strong[k] || (j >= n && A.v[k] != 0.))) continue;
+        const int c = j < n ? off[me] + agg[j] : ghostAgg[j - n];
+        const double val = -w * A.v[k] / df[i];
+        bool hit = false;
+        for (auto &e : row)
+          if (e.first == c) { e.second += val; hit = true; break; }
+        if (!hit) row.push_back({c, val});
+      }
+      std::sort(row.begin(), row.end(), byCol);
+    }
+    // ---- exchange 1: the P rows of the cells my neighbours hold as ghosts
+    blob.clear();
+    for (int q = 0; q < NP; ++q) {
+      const int cnt = halo.sendPtr[q + 1] - halo.sendPtr[q];
+      put<int>(blob, cnt);
+      for (int k = 0; k < cnt; ++k) {
+        const std::vector<Entry> &row = Prow[halo.sendIdx[halo.sendPtr[q] + k]];
+        put<int>(blob, (int)row.size());
+        for (auto &e : row) { put<int>(blob, e.first); put<double>(blob, e.second); }
+      }
+    }
+    PHB_CHECK(ex.allgatherv(blob, all));
+    for (int q = 0; q < NP; ++q) {
+      if (q == me) continue;
+      const char *p = all[q].data();
+      for (int dst = 0; dst < NP; ++dst) {
+        const int cnt = take<int>(p);
+        for (int k = 0; k < cnt; ++k) {
+          const int len = take<int>(p);
+          for (int e = 0; e < len; ++e) {
+            const int c = take<int>(p);
+            const double val = take<double>(p);
+            if (dst == me) Prow[n + halo.recvPtr[q] + k].push_back({c, val});
+          }
+        }
+      }
+    }
+    // coarse ghosts: every coarse id of another rank seen in these rows, grouped by owner (ascending global id)
+    std::vector<int> cg;
+    for (auto &row : Prow)
+      for (auto &e : row)
+        if (e.first < off[me] || e.first >= off[me + 1]) cg.push_back(e.first);
+    std::sort(cg.begin(), cg.end());
+    cg.erase(std::unique(cg.begin(), cg.end()), cg.end());
+    const int gc = (int)cg.size();
     Halo ch;
     ch.recvPtr.assign(NP + 1, 0);
-    for (int q = 0; q < NP; ++q) {
-      std::sort(need[q].begin(), need[q].end());
-      need[q].erase(std::unique(need[q].begin(), need[q].end()), need[q].end());
-      ch.recvPtr[q + 1] = ch.recvPtr[q] + (int)need[q].size();
+    std::vector<std::vector<int>> need(NP);
+    for (int c : cg) {
+      const int q = (int)(std::upper_bound(off.begin(), off.end(), c) - off.begin()) - 1;
+      need[q].push_back(c - off[q]);
     }
-    const int gc = ch.recvPtr[NP];
-    // extended prolongator: owned rows then ghost rows, columns = own coarse ids then coarse ghosts
-    HCsr Pe;
-    Pe.n = D.n + D.g; Pe.m = nc + gc;
-    Pe.rp.assign(Pe.n + 1, 0);
-    Pe.ci = P.ci; Pe.v = P.v;
-    for (int i = 0; i < D.n; ++i) Pe.rp[i + 1] = P.rp[i + 1];
-    for (int q = 0; q < NP; ++q)
-      for (int k = halo.recvPtr[q]; k < halo.recvPtr[q + 1]; ++k) {
-        for (auto &e : ghostRow[k]) {
-          const int pos = (int)(std::lower_bound(need[q].begin(), need[q].end(), e.first) - need[q].begin());
-          Pe.ci.push_back(nc + ch.recvPtr[q] + pos);
-          Pe.v.push_back(e.second);
-        }
-        Pe.rp[D.n + k + 1] = (int)Pe.ci.size();
+    for (int q = 0; q < NP; ++q) ch.recvPtr[q + 1] = ch.recvPtr[q] + (int)need[q].size();
+    auto localCol = [&](int c) {
+      if (c >= off[me] && c < off[me + 1]) return c - off[me];
+      return nc + (int)(std::lower_bound(cg.begin(), cg.end(), c) - cg.begin());
+    };
+    // Pe: all rows, local column numbering (own coarse ids, then coarse ghosts) -> Galerkin product
+    // P : owned rows; on the last distributed level its columns index the gathered (global) coarse vector
+    // R : transpose of the part of P inside this rank (restriction needs no communication)
+    HCsr Pe, P, Ploc;
+    Pe.n = n + g; Pe.m = nc + gc; Pe.rp.assign(1, 0);
+    P.n = n; P.m = lastDist ? off[NP] : nc + gc; P.rp.assign(1, 0);
+    Ploc.n = n; Ploc.m = nc; Ploc.rp.assign(1, 0);
+    std::vector<Entry> tmp;
+    for (int i = 0; i < n + g; ++i) {
+      tmp.clear();
+      for (auto &e : Prow[i]) tmp.push_back({localCol(e.first), e.second});
+      std::sort(tmp.begin(), tmp.end(), byCol);
+      for (auto &e : tmp) { Pe.ci.push_back(e.first); Pe.v.push_back(e.second); }
+      Pe.rp.push_back((int)Pe.ci.size());
+      if (i >= n) continue;
+      if (lastDist) {
+        for (auto &e : Prow[i]) { P.ci.push_back(e.first); P.v.push_back(e.second); }  // sorted by global id
+      } else {
+        for (auto &e : tmp) { P.ci.push_back(e.first); P.v.push_back(e.second); }
       }
-    D.L.R = transpose(P);
+      P.rp.push_back((int)P.ci.size());
+      for (auto &e : tmp)
+        if (e.first < nc) { Ploc.ci.push_back(e.first); Ploc.v.push_back(e.second); }
+      Ploc.rp.push_back((int)Ploc.ci.size());
+    }
+    D.L.R = transpose(Ploc);
     HCsr AP = spgemm(A, Pe);
     HCsr Ac = spgemm(D.L.R, AP);   // nc x (nc + gc)
-    // ---- exchange 2: tell every neighbour which of its coarse rows I hold as ghosts
+    // ---- exchange 2: tell every rank which of its coarse rows I hold as ghosts
     blob.clear();
     for (int q = 0; q < NP; ++q) {
       put<int>(blob, (int)need[q].size());
@@ -491,8 +573,7 @@ int build_dist_hierarchy(Exchanger &ex, HCsr A, Halo halo, std::vector<int> gid,
     }
     std::vector<int> cgid(nc + gc);
     for (int i = 0; i < nc; ++i) cgid[i] = off[me] + i;
-    for (int q = 0; q < NP; ++q)
-      for (size_t k = 0; k < need[q].size(); ++k) cgid[nc + ch.recvPtr[q] + k] = off[q] + need[q][k];
+    for (int k = 0; k < gc; ++k) cgid[nc + k] = cg[k];
     D.L.P = std::move(P);
     D.L.A = std::move(A);
     H.dist.push_back(std::move(D));
@@ -500,7 +581,7 @@ int build_dist_hierarchy(Exchanger &ex, HCsr A, Halo halo, std::vector<int> gid,
     halo = std::move(ch);
     gid = std::move(cgid);
     localSingular = 1;
-    if ((long long)off[NP] <= tailRows || level + 1 >= 10) { H.tailOff = off; break; }
+    if (lastDist) { H.tailOff = off; break; }
   }
   // ---- replicated tail: gather the level on every rank (rows in rank order, global column ids)
   std::vector<char> blob;
@@ -513,7 +594,7 @@ int build_dist_hierarchy(Exchanger &ex, HCsr A, Halo halo, std::vector<int> gid,
   HCsr G;
   G.n = G.m = H.tailOff[NP];
   G.rp.assign(1, 0);
-  std::vector<std::pair<int, double>> row;
+  std::vector<Entry> row;
   for (int q = 0; q < NP; ++q) {
     const char *p = all[q].data();
     const int nr = take<int>(p), nz = take<int>(p);
@@ -527,9 +608,7 @@ int build_dist_hierarchy(Exchanger &ex, HCsr A, Halo halo, std::vector<int> gid,
         memcpy(&v, vp + (size_t)k * sizeof(double), sizeof(double));
         row.push_back({ci[k], v});
       }
-      std::sort(row.begin(), row.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) {
-        return x.first < y.first;
-      });
+      std::sort(row.begin(), row.end(), byCol);
       for (auto &e : row) { G.ci.push_back(e.first); G.v.push_back(e.second); }
       G.rp.push_back((int)G.ci.size());
     }
@@ -1080,7 +1159,10 @@ template <typename T> struct Cycle {
     AmgLevel &V = *D.lev[l];
     const int ld = V.ld;
     T *x2 = x == as<T>(V.x) ? as<T>(V.x2) : as<T>(V.x);
-    launch<3>(s, V.P.pat, (const T *)as<T>(V.P.vals), xc + mySeg(l + 1), D.lev[l + 1]->ld, x, ld, (const T *)nullptr,
+    // the smoothed prolongator reaches into the neighbours' aggregates: refresh the ghosts of x_c first (on the
+    // last distributed level its columns index the gathered coarse vector, which every rank holds in full)
+    if (halo(l + 1, const_cast<T *>(xc)) != PHB_OK) { failed = true; return x; }
+    launch<3>(s, V.P.pat, (const T *)as<T>(V.P.vals), xc, D.lev[l + 1]->ld, x, ld, (const T *)nullptr,
               (const T *)nullptr, inLoop);
     for (int k = 0; k < D.nu; ++k) {
       if (halo(l, x) != PHB_OK) { failed = true; return x; }
@@ -1187,7 +1269,7 @@ int amg_launches_per_apply(const phb_solver *s) {
   const int perLevel = 1 + (D.nu - 1) + 2 + 1 + D.nu;  // scale, extra pre, residual + restrict, prolong, post
   int packs = 0;                                       // one pack kernel per ghost refresh of a distributed level
   for (int l = 0; l < D.nDist; ++l)
-    if (D.lev[l]->nSend) packs += 2 * D.nu;
+    if (D.lev[l]->nSend) packs += 2 * D.nu + (l > 0 ? 1 : 0);
   return (L - 1) * perLevel + (D.denseCoarse ? 1 : 1 + kCoarseSweeps) + packs;
 }
 
@@ -1343,13 +1425,15 @@ const phb_amg_host *phb_amg_dist_tail(const phb_amg_dist *h, int rank) {
   return &h->H[rank].tail;
 }
 
-// which: 0 = A_l (global column ids of level l), 1 = P_l (global column ids of level l + 1);
-// rows are the rank's owned rows, rowGid their global ids within level l
+// which: 0 = A_l (rows = the rank's cells of level l, global column ids of level l),
+//        1 = P_l (same rows, global column ids of level l + 1),
+//        2 = R_l (rows = the rank's cells of level l + 1, global column ids of level l)
+static const HCsr &dist_pick(const DistLevel &D, int which) { return which == 0 ? D.L.A : which == 1 ? D.L.P : D.L.R; }
+
 int phb_amg_dist_matrix_size(const phb_amg_dist *h, int rank, int level, int which, int *nRows, long long *nnz) {
   PHB_REQUIRE(h && nRows && nnz && rank >= 0 && rank < h->nRanks && level >= 0 &&
-              level < (int)h->H[rank].dist.size() && (which == 0 || which == 1), "phb_amg_dist_matrix_size: bad argument");
-  const DistLevel &D = h->H[rank].dist[level];
-  const HCsr &M = which == 0 ? D.L.A : D.L.P;
+              level < (int)h->H[rank].dist.size() && which >= 0 && which <= 2, "phb_amg_dist_matrix_size: bad argument");
+  const HCsr &M = dist_pick(h->H[rank].dist[level], which);
   *nRows = M.n; *nnz = M.nnz();
   return PHB_OK;
 }
@@ -1357,18 +1441,26 @@ int phb_amg_dist_matrix_size(const phb_amg_dist *h, int rank, int level, int whi
 int phb_amg_dist_matrix(const phb_amg_dist *h, int rank, int level, int which, int *rowPtr, int *colGid,
                         double *vals, int *rowGid) {
   PHB_REQUIRE(h && rowPtr && colGid && vals && rowGid && rank >= 0 && rank < h->nRanks && level >= 0 &&
-              level < (int)h->H[rank].dist.size() && (which == 0 || which == 1), "phb_amg_dist_matrix: bad argument");
+              level < (int)h->H[rank].dist.size() && which >= 0 && which <= 2, "phb_amg_dist_matrix: bad argument");
   const DistHierarchy &H = h->H[rank];
   const DistLevel &D = H.dist[level];
-  const HCsr &M = which == 0 ? D.L.A : D.L.P;
+  const HCsr &M = dist_pick(D, which);
+  const bool last = level + 1 == (int)H.dist.size();
   std::copy(M.rp.begin(), M.rp.end(), rowPtr);
   std::copy(M.v.begin(), M.v.end(), vals);
+  auto coarseGid = [&](int c) { return last ? H.tailOff[rank] + c : H.dist[level + 1].gid[c]; };
+  if (which == 2) {
+    for (int i = 0; i < M.n; ++i) rowGid[i] = coarseGid(i);
+    for (long long k = 0; k < M.nnz(); ++k) colGid[k] = D.gid[M.ci[k]];
+    return PHB_OK;
+  }
   for (int i = 0; i < D.n; ++i) rowGid[i] = D.gid[i];
   if (which == 0) {
     for (long long k = 0; k < M.nnz(); ++k) colGid[k] = D.gid[M.ci[k]];
-  } else {  // own coarse ids -> global: first owned id of the next level (or the rank's tail segment)
-    const int base = level + 1 < (int)H.dist.size() ? H.dist[level + 1].gid[0] : H.tailOff[rank];
-    for (long long k = 0; k < M.nnz(); ++k) colGid[k] = base + M.ci[k];
+  } else if (last) {   // columns already index the gathered coarse vector
+    for (long long k = 0; k < M.nnz(); ++k) colGid[k] = M.ci[k];
+  } else {
+    for (long long k = 0; k < M.nnz(); ++k) colGid[k] = H.dist[level + 1].gid[M.ci[k]];
   }
   return PHB_OK;
 }

@@ -246,19 +246,21 @@ def test_distributed_hierarchy_is_the_global_galerkin_hierarchy(px, py, fixed):
     part = block_partition(nx, ny, px, py)
     H = DistAmg(A, part)
     assert H.nDist >= 2 and H.nTail >= 1 and H.singular == (not fixed)
-    sizes = [A.shape[0]]
     Al = H.global_matrix(0, 0, A.shape)
     assert abs(Al - A).max() == 0.0
     levels = []
     for l in range(H.nDist):
-        # coarse size = sum of the ranks' aggregate counts = columns of the stacked P
-        ncs = [H.rank_matrix(r, l, 1)[1].max() + 1 if len(H.rank_matrix(r, l, 1)[1]) else 0 for r in range(H.nRanks)]
-        nc = int(max(ncs))
-        P = H.global_matrix(l, 1, (sizes[-1], nc))
+        nc = sum(H.rank_matrix(r, l, 2)[0].shape[0] - 1 for r in range(H.nRanks))    # coarse rows of all ranks
+        P = H.global_matrix(l, 1, (Al.shape[0], nc))
+        R = H.global_matrix(l, 2, (nc, Al.shape[0]))
         assert np.all(np.diff(P.indptr) >= 1)
         if not fixed:
             assert np.abs(P @ np.ones(nc) - 1.0).max() < 1e-12          # constant reproduced across rank boundaries
-        G = (P.T @ Al @ P).tocsr()
+        # R = the part of P^T inside the rank that owns the coarse row; P itself reaches across rank boundaries
+        D = (P.T - R).tocoo()
+        D.eliminate_zeros()
+        assert R.nnz > 0 and D.nnz > 0 and abs(R - R.multiply(P.T != 0)).max() == 0.0
+        G = (R @ Al @ P).tocsr()
         if l + 1 < H.nDist:
             An = H.global_matrix(l + 1, 0, (nc, nc))
         else:
@@ -266,10 +268,9 @@ def test_distributed_hierarchy_is_the_global_galerkin_hierarchy(px, py, fixed):
             for r in range(1, H.nRanks):
                 assert abs(H.tail(r).mat(0, 0)[0] - An).max() == 0.0
         assert An.shape == G.shape and abs(G - An).max() <= 1e-12 * abs(An).max()
-        levels.append((Al, P))
-        sizes.append(nc)
+        levels.append((Al, P, R))
         Al = An
-    # halo lists: what r sends to q is what q expects from r, level by level (checked through gids)
+    # halo lists: what r sends to q is what q expects from r, level by level
     for l in range(H.nDist):
         for r in range(H.nRanks):
             sp_r, si_r, rp_r = H.halo(r, l, 100000)
@@ -279,25 +280,22 @@ def test_distributed_hierarchy_is_the_global_galerkin_hierarchy(px, py, fixed):
                     continue
                 sent = gid_r[si_r[sp_r[q]:sp_r[q + 1]]]
                 rp_q = H.halo(q, l, 100000)[2]
-                # ghost gids of q from r: columns n_q + recvPtr[r] .. of q's matrix -> recover from its column gids
-                rpq, ciq, vq, gidq = H.rank_matrix(q, l, 0)
                 assert rp_q[r + 1] - rp_q[r] == len(sent)
-                assert set(sent.tolist()) <= set(ciq.tolist())
     # a V(1,1) cycle over the global levels + the replicated tail preconditions BiCGStab like the serial one
     tail = H.tail(0).cycle()
 
     def cyc(l, b):
         if l == H.nDist:
             return tail(b)
-        A_, P_ = levels[l]
+        A_, P_, R_ = levels[l]
         rho = np.abs(sp.diags(1.0 / A_.diagonal()) @ A_).sum(axis=1).max()
         w = (4.0 / 3.0 / rho) / A_.diagonal()
         x = w * b
-        x = x + P_ @ cyc(l + 1, P_.T @ (b - A_ @ x))
+        x = x + P_ @ cyc(l + 1, R_ @ (b - A_ @ x))
         return x + w * (b - A_ @ x)
     b = np.random.default_rng(2).standard_normal(A.shape[0])
     if not fixed:
         b -= b.mean()
     its, rel = bicgstab_iters(A, lambda v: cyc(0, v), b)
-    assert rel < 2e-8 and its <= 16, its
+    assert rel < 2e-8 and its <= 14, its
     H.close()
