@@ -348,6 +348,24 @@ def main():
     except Exception:
         pass
 
+    # ---- the pressure solve alone (pEqn_ as assembled by the last step, zero initial guess): whole-solve
+    # algorithmic throughput = iterations x bytes per iteration (2 SpMV + 2 preconditioner applies + vector passes)
+    fs.pEqn.solve(warmStart=False)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        pe0.record()
+    fs.pEqn.solve(warmStart=False)
+    with torch.cuda.stream(stream):
+        pe1.record()
+    barrier()
+    p_ms, p_its = pe0.elapsed_time(pe1), fs.pEqn.solver.nIters()
+    pressure_solve = {"what": "pEqn_ of the last step solved from a zero guess, CUDA events around phb_eqn_solve",
+                      "iterations": p_its, "ms": p_ms, "relres": fs.pEqn.solver.error(),
+                      "algorithmic_bytes_per_iteration": b_iter,
+                      "achieved_GBps_per_gpu": p_its * b_iter / (p_ms * 1e-3) / 1e9,
+                      "frac_of_measured_peak": p_its * b_iter / (p_ms * 1e-3) / 1e9 / peak}
+
     # ---- e2e: the same step through the public API with HOST state in pinned memory:
     # H2D of the step's input state, the step, D2H of the resulting u and p
     host = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k, n in
@@ -415,6 +433,7 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "frac_of_8TBs_nominal": achieved / 8000.0, "traffic": traffic,
                          "algorithmic_bytes_per_launch": b_spmv, "ms_per_launch": spmv_ms, "peak_source": peak_src},
+            "pressure_solve": pressure_solve,
             "bicgstab": {"bytes_per_iteration": b_iter,
                          "note": "whole-solve GB/s = iters * bytes_per_iteration / solve time; see profiles/"},
             "e2e": {"value": (world if args.scaling == "weak" else 1) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_all,
