@@ -767,17 +767,24 @@ k_amg_spmv(SellView M, const T *__restrict__ vals, const T *__restrict__ x, int 
   }
 }
 
-// dot product of one row with x, shared by kSubLanes lanes (all 32 lanes of the warp must call it).
-// COHERENT: x was written earlier in the SAME kernel (fused tail) -> read it through L2, not the read-only path.
-template <int NC, typename T, bool COHERENT>
-__device__ __forceinline__ void sub_row_dot(const SellView &M, const T *__restrict__ vals, const T *x, int ldx, int row,
-                                            bool live, int g, T (&acc)[NC]) {
+// Small levels are latency-bound, not bandwidth-bound: kSubLanes lanes share a row, every lane issues its
+// (up to 4) entries at once, partial sums meet in shuffles -- the dependent-load chain no longer grows
+// with the row length (restriction rows hold 20-30 entries).
+template <int MODE, int NC, typename T, typename TB, typename TY>
+__global__ void __launch_bounds__(kThreads)
+k_amg_spmv_sub(SellView M, const T *__restrict__ vals, const T *__restrict__ x, int ldx, TY *__restrict__ y, int ldy,
+               const TB *__restrict__ b, const T *__restrict__ w, const KrylovSums *S, int maxIters) {
+  if (S && krylov_done(S, maxIters)) return;
+  const int g = threadIdx.x & (kSubLanes - 1);
+  const int row = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSubLanes);
+  const bool live = row < M.nRows;
   int off = 0, wdt = 0;
   if (live) {
     off = __ldg(M.sliceOff + (row >> 5));
     wdt = (__ldg(M.sliceOff + (row >> 5) + 1) - off) >> 5;
   }
   const size_t base = (size_t)off + (row & 31);
+  T acc[NC];
 #pragma unroll
   for (int i = 0; i < NC; ++i) acc[i] = T(0);
   for (int k0 = 0; k0 < wdt; k0 += 4 * kSubLanes) {
@@ -793,31 +800,13 @@ __device__ __forceinline__ void sub_row_dot(const SellView &M, const T *__restri
     for (int j = 0; j < 4; ++j)
       if (c[j] >= 0) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i) {
-          const T xv = COHERENT ? __ldcg(x + (size_t)i * ldx + c[j]) : __ldg(x + (size_t)i * ldx + c[j]);
-          acc[i] = fma(a[j], xv, acc[i]);
-        }
+        for (int i = 0; i < NC; ++i) acc[i] = fma(a[j], __ldg(x + (size_t)i * ldx + c[j]), acc[i]);
       }
   }
 #pragma unroll
   for (int i = 0; i < NC; ++i)
 #pragma unroll
     for (int o = kSubLanes / 2; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-}
-
-// Small levels are latency-bound, not bandwidth-bound: kSubLanes lanes share a row, every lane issues its
-// (up to 4) entries at once, partial sums meet in shuffles -- the dependent-load chain no longer grows
-// with the row length (restriction rows hold 20-30 entries).
-template <int MODE, int NC, typename T, typename TB, typename TY>
-__global__ void __launch_bounds__(kThreads)
-k_amg_spmv_sub(SellView M, const T *__restrict__ vals, const T *__restrict__ x, int ldx, TY *__restrict__ y, int ldy,
-               const TB *__restrict__ b, const T *__restrict__ w, const KrylovSums *S, int maxIters) {
-  if (S && krylov_done(S, maxIters)) return;
-  const int g = threadIdx.x & (kSubLanes - 1);
-  const int row = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSubLanes);
-  const bool live = row < M.nRows;
-  T acc[NC];
-  sub_row_dot<NC, T, false>(M, vals, x, ldx, row, live, g, acc);
   if (live && g == 0) amg_epilogue<MODE, NC, T, TB, TY>(row, acc, x, ldx, y, ldy, b, w);
 }
 
@@ -845,103 +834,6 @@ __global__ void k_amg_dense(int n, int nc, int ld, const double *__restrict__ Ai
     for (int k = lane; k < n; k += 32) acc = fma(Ainv[(size_t)row * n + k], (double)b[(size_t)c * ld + k], acc);
     acc = warp_sum(acc);
     if (lane == 0) x[(size_t)c * ld + row] = (TY)acc;
-  }
-}
-
-// ---- fused tail: every level with <= kTailRows rows (down sweep, dense coarsest solve, up sweep) in ONE launch of one
-// CTA.  These levels hold a few thousand rows: their 5 launches per level were pure launch + dependent-load latency.
-constexpr int kTailRows = 16384, kTailMax = 8, kTailThreads = 1024;
-struct TailLevel {
-  SellView A, P, R;
-  const void *aVals, *pVals, *rVals, *w;
-  void *x, *x2, *b, *r;
-  int n, ld;
-};
-struct TailArgs {
-  TailLevel lev[kTailMax];
-  int nLev, nu;
-  const double *Ainv;
-};
-
-// MODE as k_amg_spmv; every vector may have been written earlier in this kernel -> coherent loads
-template <int MODE, int NC, typename T>
-__device__ __forceinline__ void tail_spmv(const SellView &M, const T *__restrict__ vals, const T *x, int ldx, T *y,
-                                          int ldy, const T *b, const T *__restrict__ w) {
-  const int g = threadIdx.x & (kSubLanes - 1), grp = threadIdx.x / kSubLanes, nGrp = blockDim.x / kSubLanes;
-  for (int row0 = 0; row0 < M.nRows; row0 += nGrp) {   // block-uniform trip count (shuffles inside)
-    const int row = row0 + grp;
-    const bool live = row < M.nRows;
-    T acc[NC];
-    sub_row_dot<NC, T, true>(M, vals, x, ldx, row, live, g, acc);
-    if (live && g == 0) {
-      const T wr = MODE == 2 ? __ldg(w + row) : T(0);
-#pragma unroll
-      for (int i = 0; i < NC; ++i) {
-        const size_t iy = (size_t)i * ldy + row;
-        if (MODE == 0) y[iy] = acc[i];
-        if (MODE == 1) y[iy] = __ldcg(b + iy) - acc[i];
-        if (MODE == 2) y[iy] = __ldcg(x + (size_t)i * ldx + row) + wr * (__ldcg(b + iy) - acc[i]);
-        if (MODE == 3) y[iy] = __ldcg(y + iy) + acc[i];
-      }
-    }
-  }
-}
-
-template <int NC, typename T>
-__global__ void __launch_bounds__(kTailThreads) k_amg_tail(TailArgs a, const KrylovSums *S, int maxIters) {
-  if (S && krylov_done(S, maxIters)) return;
-  const int L = a.nLev;
-  T *xs[kTailMax];
-  for (int l = 0; l + 1 < L; ++l) {   // ---- down
-    const TailLevel &V = a.lev[l];
-    T *x = (T *)V.x, *x2 = (T *)V.x2, *r = (T *)V.r;
-    const T *b = (const T *)V.b, *w = (const T *)V.w, *av = (const T *)V.aVals;
-    for (int i = threadIdx.x; i < V.n; i += blockDim.x) {
-      const T wi = __ldg(w + i);
-      for (int c = 0; c < NC; ++c) x[(size_t)c * V.ld + i] = wi * __ldcg(b + (size_t)c * V.ld + i);
-    }
-    __syncthreads();
-    for (int k = 1; k < a.nu; ++k) {
-      tail_spmv<2, NC, T>(V.A, av, x, V.ld, x2, V.ld, b, w);
-      __syncthreads();
-      T *t = x; x = x2; x2 = t;
-    }
-    tail_spmv<1, NC, T>(V.A, av, x, V.ld, r, V.ld, b, w);
-    __syncthreads();
-    const TailLevel &C = a.lev[l + 1];
-    tail_spmv<0, NC, T>(V.R, (const T *)V.rVals, r, V.ld, (T *)C.b, C.ld, (const T *)nullptr, w);
-    __syncthreads();
-    xs[l] = x;
-  }
-  {   // ---- coarsest: dense inverse, one warp per row
-    const TailLevel &V = a.lev[L - 1];
-    const T *b = (const T *)V.b;
-    T *x = (T *)V.x;
-    const int lane = threadIdx.x & 31, nW = blockDim.x >> 5;
-    for (int row = threadIdx.x >> 5; row < V.n; row += nW)
-      for (int c = 0; c < NC; ++c) {
-        double acc = 0.;
-        for (int k = lane; k < V.n; k += 32)
-          acc = fma(__ldg(a.Ainv + (size_t)row * V.n + k), (double)__ldcg(b + (size_t)c * V.ld + k), acc);
-        acc = warp_sum(acc);
-        if (lane == 0) x[(size_t)c * V.ld + row] = (T)acc;
-      }
-    __syncthreads();
-    xs[L - 1] = x;
-  }
-  for (int l = L - 2; l >= 0; --l) {   // ---- up
-    const TailLevel &V = a.lev[l];
-    T *x = xs[l];
-    T *x2 = x == (T *)V.x ? (T *)V.x2 : (T *)V.x;
-    const T *b = (const T *)V.b, *w = (const T *)V.w, *av = (const T *)V.aVals;
-    tail_spmv<3, NC, T>(V.P, (const T *)V.pVals, xs[l + 1], a.lev[l + 1].ld, x, V.ld, (const T *)nullptr, w);
-    __syncthreads();
-    for (int k = 0; k < a.nu; ++k) {
-      tail_spmv<2, NC, T>(V.A, av, x, V.ld, x2, V.ld, b, w);
-      __syncthreads();
-      T *t = x; x = x2; x2 = t;
-    }
-    xs[l] = x;
   }
 }
 
@@ -1208,19 +1100,6 @@ template <typename T> const T *level0_vals(const AmgData &D);
 template <> const float *level0_vals<float>(const AmgData &D) { return D.refValsF.p; }
 template <> const double *level0_vals<double>(const AmgData &D) { return D.refVals.p; }
 
-// first level of the fused tail (= number of levels when there is none): replicated levels of at most kTailRows
-// rows below level 0, at least two of them, ending in the dense coarsest solve
-int amg_tail_start(const AmgData &D) {
-  const int L = (int)D.lev.size();
-  if (!D.fusedTail || !D.denseCoarse) return L;
-  int cand = L;
-  for (int l = L - 1; l >= std::max(1, D.nDist); --l) {
-    if (D.lev[l]->n > kTailRows || D.lev[l]->dist) break;
-    cand = l;
-  }
-  return (L - cand >= 2 && L - cand <= kTailMax) ? cand : L;
-}
-
 template <typename T> struct Cycle {
   phb_solver *s;
   AmgData &D;
@@ -1323,42 +1202,14 @@ template <typename T> struct Cycle {
     return x;
   }
 
-  // levels [lt, L) in one launch of one CTA; the iterate of level lt ends in its x2 buffer (2 nu - 1 swaps)
-  T *tail(int lt) {
-    const int L = (int)D.lev.size();
-    TailArgs a;
-    memset(&a, 0, sizeof(a));
-    a.nLev = L - lt;
-    a.nu = D.nu;
-    a.Ainv = D.coarseInv.p;
-    for (int j = lt; j < L; ++j) {
-      AmgLevel &V = *D.lev[j];
-      TailLevel &t = a.lev[j - lt];
-      t.A = view_of(&V.A.pat);
-      t.aVals = V.A.vals.p;
-      if (j + 1 < L) {
-        t.P = view_of(&V.P.pat); t.R = view_of(&V.R.pat);
-        t.pVals = V.P.vals.p; t.rVals = V.R.vals.p;
-      }
-      t.w = V.w.p; t.x = V.x.p; t.x2 = V.x2.p; t.b = V.b.p; t.r = V.r.p;
-      t.n = V.n; t.ld = V.ld;
-    }
-    if (nc == 1) PHB_LAUNCH(s->ctx, (k_amg_tail<1, T>), 1, kTailThreads, 0, a, S, s->maxIters);
-    else PHB_LAUNCH(s->ctx, (k_amg_tail<2, T>), 1, kTailThreads, 0, a, S, s->maxIters);
-    return as<T>(D.lev[lt]->x2);
-  }
-
   int run(const double *in, double *out) {
     const int L = (int)D.lev.size();
     if (L == 1) { coarse(0, in, out); return PHB_OK; }
-    const int lt = amg_tail_start(D);
     std::vector<T *> xOf(L);
     xOf[0] = down(0, in);
-    for (int l = 1; l < lt && l + 1 < L; ++l) xOf[l] = down(l, (const T *)as<T>(D.lev[l]->b));
-    int top;   // coarsest level handled level by level above the tail
-    if (lt < L) { xOf[lt] = tail(lt); top = lt; }
-    else { xOf[L - 1] = coarse(L - 1, (const T *)as<T>(D.lev[L - 1]->b), nullptr); top = L - 1; }
-    for (int l = top - 1; l >= 1; --l)
+    for (int l = 1; l + 1 < L; ++l) xOf[l] = down(l, (const T *)as<T>(D.lev[l]->b));
+    xOf[L - 1] = coarse(L - 1, (const T *)as<T>(D.lev[L - 1]->b), nullptr);
+    for (int l = L - 2; l >= 1; --l)
       xOf[l] = up(l, (const T *)as<T>(D.lev[l]->b), xOf[l], (const T *)xOf[l + 1], nullptr);
     up(0, in, xOf[0], (const T *)xOf[1], out);
     return failed ? PHB_ERR_COMM : PHB_OK;
@@ -1419,8 +1270,6 @@ int amg_launches_per_apply(const phb_solver *s) {
   int packs = 0;                                       // one pack kernel per ghost refresh of a distributed level
   for (int l = 0; l < D.nDist; ++l)
     if (D.lev[l]->nSend) packs += 2 * D.nu + (l > 0 ? 1 : 0);
-  const int lt = amg_tail_start(D);
-  if (lt < L) return lt * perLevel + 1 + packs;        // levels [lt, L) are one launch
   return (L - 1) * perLevel + (D.denseCoarse ? 1 : 1 + kCoarseSweeps) + packs;
 }
 

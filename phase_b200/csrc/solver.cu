@@ -693,9 +693,6 @@ int phb_solver_setup(phb_solver *s, const char *key, const char *value) {
   } else if (k == "amgPrecision") {
     PHB_REQUIRE(lv == "single" || lv == "double" || lv == "float", "amgPrecision must be \"single\" or \"double\"");
     s->amg.single = lv != "double";
-  } else if (k == "amgFusedTail") {
-    s->amg.fusedTail = std::stoi(v) != 0;
-    if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
   } else if (k == "amgScope") {
     PHB_REQUIRE(lv == "global" || lv == "local", "amgScope must be \"global\" or \"local\"");
     s->amg.global = lv == "global"; s->amg.built = false;

@@ -87,7 +87,6 @@ struct AmgData {
   phb::DevBuf<double> coarseInv, refVals, chk;
   phb::DevBuf<float> refValsF;
   bool single = true, builtSingle = true;   // cycle precision (`amgPrecision single|double`)
-  bool fusedTail = true;                    // small replicated levels in one single-CTA launch (`amgFusedTail`)
   bool global = true;                       // nProcs > 1: hierarchy spans the ranks (else rank-local blocks)
   int nDist = 0;                            // leading distributed levels; level nDist is gathered on every rank
   long long tailRows = 200000;
