@@ -231,6 +231,8 @@ def main():
                     help="amg = smoothed-aggregation V-cycle on pEqn_; uEqn_ per --u-precond")
     ap.add_argument("--u-precond", default="amg", choices=["ilu0", "amg"], help="uEqn_ preconditioner when --precond amg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--solver-key", action="append", default=[], metavar="KEY=VALUE",
+                    help="extra LinearAlgebra key for both equations (e.g. amgPrecision=double, amgSweeps=2)")
     ap.add_argument("--mesh", default="quad", choices=["quad", "tri"],
                     help="quad: side x side quads; tri: the same cell count as triangles (each quad of a "
                          "side/sqrt(2) lattice split along alternating diagonals, unstructured connectivity)")
@@ -288,6 +290,9 @@ def main():
     amg = args.precond == "amg"
     cfg = dict(solver="BICGSTAB", maxIters=args.max_iters, tolerance=args.tol,
                preconditioner=args.u_precond if amg else args.precond, peerFusion=1 if args.comm == "peer-fused" else 0)
+    for kv in args.solver_key:
+        k, v = kv.split("=", 1)
+        cfg[k] = v
     fs = lid_driven_cavity(grid, 1.0, 0.1, solver=cfg, pSolver=dict(preconditioner="amg") if amg else None)
     fs.setup(guessOrder=args.guess_order)
     dt = 0.5 / nx                                            # maxCo 0.5 with the unit lid speed, h = 1/nx
