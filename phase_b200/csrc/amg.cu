@@ -58,39 +58,83 @@ HCsr transpose(const HCsr &A) {
   return T;
 }
 
-// C = A B (Gustavson, marker array); rows of C sorted by column
+// ---- host threads for the row-parallel parts of the setup (results do not depend on the thread count)
+int g_hostRanks = 1;   // ranks sharing this host (set by the distributed setup)
+int host_threads() {
+  if (const char *e = getenv("PHB_HOST_THREADS")) return std::max(1, atoi(e));
+  const int hw = (int)std::thread::hardware_concurrency();
+  return std::max(1, std::min(16, hw / std::max(1, g_hostRanks)));
+}
+// f(begin, end, chunk) over [0, n) in contiguous chunks, one thread each; returns the number of chunks
+template <typename F> int parallel_chunks(int n, F f) {
+  const int T = std::max(1, std::min(host_threads(), n / 8192));
+  const int chunk = (n + T - 1) / T;
+  if (T == 1) { f(0, n, 0); return 1; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; ++t) th.emplace_back(f, std::min(n, t * chunk), std::min(n, (t + 1) * chunk), t);
+  for (auto &x : th) x.join();
+  return T;
+}
+int chunk_count(int n) { return std::max(1, std::min(host_threads(), n / 8192)); }
+
+// rows computed chunk by chunk into private arrays, then stitched: C.rp holds row lengths on entry
+void stitch(HCsr &C, std::vector<std::vector<int>> &ci, std::vector<std::vector<double>> &v,
+            const std::vector<int> &chunkBegin) {
+  for (int i = 0; i < C.n; ++i) C.rp[i + 1] += C.rp[i];
+  C.ci.resize(C.rp[C.n]);
+  C.v.resize(C.rp[C.n]);
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < ci.size(); ++t)
+    th.emplace_back([&, t] {
+      std::copy(ci[t].begin(), ci[t].end(), C.ci.begin() + C.rp[chunkBegin[t]]);
+      std::copy(v[t].begin(), v[t].end(), C.v.begin() + C.rp[chunkBegin[t]]);
+    });
+  for (auto &x : th) x.join();
+}
+
+// C = A B (Gustavson, marker array); rows of C sorted by column; row-parallel
 HCsr spgemm(const HCsr &A, const HCsr &B) {
   HCsr C;
   C.n = A.n; C.m = B.m;
   C.rp.assign(C.n + 1, 0);
-  std::vector<long long> marker(B.m, -1);
-  std::vector<std::pair<int, double>> row;
-  for (int i = 0; i < A.n; ++i) {
-    const long long start = (long long)C.ci.size();
-    for (int ka = A.rp[i]; ka < A.rp[i + 1]; ++ka) {
-      const int j = A.ci[ka];
-      const double a = A.v[ka];
-      for (int kb = B.rp[j]; kb < B.rp[j + 1]; ++kb) {
-        const int c = B.ci[kb];
-        if (marker[c] < start) {
-          marker[c] = (long long)C.ci.size();
-          C.ci.push_back(c);
-          C.v.push_back(a * B.v[kb]);
-        } else {
-          C.v[marker[c]] += a * B.v[kb];
+  const int T = chunk_count(A.n);
+  std::vector<std::vector<int>> ci(T);
+  std::vector<std::vector<double>> v(T);
+  std::vector<int> chunkBegin(T, 0);
+  parallel_chunks(A.n, [&](int begin, int end, int t) {
+    chunkBegin[t] = begin;
+    std::vector<int> marker(B.m, -1);
+    std::vector<int> &cc = ci[t];
+    std::vector<double> &cv = v[t];
+    std::vector<std::pair<int, double>> row;
+    for (int i = begin; i < end; ++i) {
+      const int start = (int)cc.size();
+      for (int ka = A.rp[i]; ka < A.rp[i + 1]; ++ka) {
+        const int j = A.ci[ka];
+        const double a = A.v[ka];
+        for (int kb = B.rp[j]; kb < B.rp[j + 1]; ++kb) {
+          const int c = B.ci[kb];
+          if (marker[c] < start) {
+            marker[c] = (int)cc.size();
+            cc.push_back(c);
+            cv.push_back(a * B.v[kb]);
+          } else {
+            cv[marker[c]] += a * B.v[kb];
+          }
         }
       }
+      const int stop = (int)cc.size();
+      row.clear();
+      for (int k = start; k < stop; ++k) row.push_back({cc[k], cv[k]});
+      std::sort(row.begin(), row.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) {
+        return x.first < y.first;
+      });
+      for (int k = start; k < stop; ++k) { cc[k] = row[k - start].first; cv[k] = row[k - start].second; }
+      for (int k = start; k < stop; ++k) marker[cc[k]] = -1;  // positions moved: forget them
+      C.rp[i + 1] = stop - start;
     }
-    const long long end = (long long)C.ci.size();
-    row.clear();
-    for (long long k = start; k < end; ++k) row.push_back({C.ci[k], C.v[k]});
-    std::sort(row.begin(), row.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) {
-      return x.first < y.first;
-    });
-    for (long long k = start; k < end; ++k) { C.ci[k] = row[k - start].first; C.v[k] = row[k - start].second; }
-    for (long long k = start; k < end; ++k) marker[C.ci[k]] = -1;  // positions moved: forget them
-    C.rp[i + 1] = (int)end;
-  }
+  });
+  stitch(C, ci, v, chunkBegin);
   return C;
 }
 
@@ -238,26 +282,34 @@ int make_prolongator(const HCsr &A, double theta, double omegaP, int level, Host
   P = HCsr();
   P.n = n; P.m = nc;
   P.rp.assign(n + 1, 0);
-  std::vector<std::pair<int, double>> row;
   const double w = omegaP / rho;
-  for (int i = 0; i < n; ++i) {
-    row.clear();
-    row.push_back({agg[i], 1. - w});  // diagonal term of Af: df/df = 1
-    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) {
-      if (!strong[k]) continue;
-      const int c = agg[A.ci[k]];
-      const double val = -w * A.v[k] / df[i];
-      bool hit = false;
-      for (auto &e : row)
-        if (e.first == c) { e.second += val; hit = true; break; }
-      if (!hit) row.push_back({c, val});
+  const int T = chunk_count(n);
+  std::vector<std::vector<int>> pci(T);
+  std::vector<std::vector<double>> pv(T);
+  std::vector<int> chunkBegin(T, 0);
+  parallel_chunks(n, [&](int begin, int end, int t) {
+    chunkBegin[t] = begin;
+    std::vector<std::pair<int, double>> row;
+    for (int i = begin; i < end; ++i) {
+      row.clear();
+      row.push_back({agg[i], 1. - w});  // diagonal term of Af: df/df = 1
+      for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) {
+        if (!strong[k]) continue;
+        const int c = agg[A.ci[k]];
+        const double val = -w * A.v[k] / df[i];
+        bool hit = false;
+        for (auto &e : row)
+          if (e.first == c) { e.second += val; hit = true; break; }
+        if (!hit) row.push_back({c, val});
+      }
+      std::sort(row.begin(), row.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) {
+        return x.first < y.first;
+      });
+      for (auto &e : row) { pci[t].push_back(e.first); pv[t].push_back(e.second); }
+      P.rp[i + 1] = (int)row.size();
     }
-    std::sort(row.begin(), row.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) {
-      return x.first < y.first;
-    });
-    for (auto &e : row) { P.ci.push_back(e.first); P.v.push_back(e.second); }
-    P.rp[i + 1] = (int)P.ci.size();
-  }
+  });
+  stitch(P, pci, pv, chunkBegin);
   return 0;
 }
 
@@ -285,6 +337,7 @@ int build_hierarchy(HCsr A0, double theta, int coarsest, double omegaP, HostHier
   for (int level = 0;; ++level) {
     HostLevel L;
     const int n = A.n;
+    const auto tL = std::chrono::steady_clock::now();
     nnzAll += A.nnz();
     const bool last = n <= coarsest || level >= 15;
     HCsr P;
@@ -303,9 +356,20 @@ int build_hierarchy(HCsr A0, double theta, int coarsest, double omegaP, HostHier
       H.lev.push_back(std::move(L));
       break;
     }
+    const auto t1 = std::chrono::steady_clock::now();
     L.R = transpose(P);
+    const auto t2 = std::chrono::steady_clock::now();
     HCsr AP = spgemm(A, P);
+    const auto t3 = std::chrono::steady_clock::now();
     HCsr Ac = spgemm(L.R, AP);
+    const auto t4 = std::chrono::steady_clock::now();
+    if (getenv("PHB_AMG_TIMING")) {
+      auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+      };
+      fprintf(stderr, "amg setup level %d (%d rows): prolongator %.0f ms, transpose %.0f, A*P %.0f, R*(AP) %.0f\n", level, n,
+              ms(tL, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
+    }
     L.P = std::move(P);
     L.A = std::move(A);
     H.lev.push_back(std::move(L));
@@ -1037,6 +1101,7 @@ int rebuild_dist_t(phb_solver *s) {
   std::iota(gid.begin(), gid.end(), 0);
   NcclExchanger ex;
   ex.rank = me; ex.nProcs = NP; ex.c = c;
+  g_hostRanks = NP;   // the ranks of one node share its cores
   DistHierarchy H;
   PHB_CHECK(build_dist_hierarchy(ex, std::move(A0), std::move(h0), std::move(gid), D.theta, D.coarsest, D.tailRows,
                                  4. / 3., H));

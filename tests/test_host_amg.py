@@ -299,3 +299,38 @@ def test_distributed_hierarchy_is_the_global_galerkin_hierarchy(px, py, fixed):
     its, rel = bicgstab_iters(A, lambda v: cyc(0, v), b)
     assert rel < 2e-8 and its <= 14, its
     H.close()
+
+
+def test_nonsymmetric_momentum_like_matrix():
+    """uEqn_-type operator: V/dt I + upwind convection - nu Laplacian (non-symmetric, strictly diagonally dominant);
+    restriction = P^T is still a good transfer and the cycle preconditions BiCGStab into a handful of iterations"""
+    nx = ny = 96
+    h = 1.0 / nx
+    L = neumann_laplacian(nx, ny, sign=1.0)                    # positive semi-definite 5-point operator (unit weights)
+    idx = np.arange(nx * ny).reshape(ny, nx)
+    # upwind convection with u = (1, 0.5): flux h*u through each face, donor = upstream cell
+    I, J, V = [], [], []
+    for (a, b, f) in ((idx[:, :-1].ravel(), idx[:, 1:].ravel(), 1.0 * h), (idx[:-1, :].ravel(), idx[1:, :].ravel(), 0.5 * h)):
+        I += [a, b]; J += [a, a]; V += [np.full(len(a), f), np.full(len(a), -f)]   # outflow of a = inflow of b
+    Cv = sp.csr_matrix((np.concatenate(V), (np.concatenate(I), np.concatenate(J))), shape=L.shape)
+    A = (sp.eye(nx * ny) * (h * h / (0.5 * h)) + 0.5 * Cv + 0.05 * L).tocsr()
+    assert abs(A - A.T).max() > 0
+    H = HostAmg(A, coarsest=60)
+    assert not H.singular and H.nLevels >= 3
+    b = np.random.default_rng(3).standard_normal(nx * ny)
+    its, rel = bicgstab_iters(A, H.cycle(), b)
+    assert rel < 2e-8 and its <= 12, its
+    H.close()
+
+
+def test_setup_does_not_depend_on_the_thread_count(monkeypatch):
+    A = neumann_laplacian(150, 120)
+    mats = []
+    for t in ("1", "5"):
+        monkeypatch.setenv("PHB_HOST_THREADS", t)
+        H = HostAmg(A, coarsest=50)
+        mats.append([H.mat(l, w)[0] for l in range(H.nLevels - 1) for w in (0, 1, 2)])
+        H.close()
+    assert len(mats[0]) == len(mats[1])
+    for a, b in zip(*mats):
+        assert a.shape == b.shape and abs(a - b).max() == 0.0
