@@ -329,6 +329,10 @@ bool rows_sum_to_zero(const HCsr &A) {
 int build_hierarchy(HCsr A0, double theta, int coarsest, double omegaP, HostHierarchy &H) {
   const auto t0 = std::chrono::steady_clock::now();
   H.lev.clear();
+  if (A0.nnz() > 1200000000LL) {  // row pointers of the products are 32-bit
+    set_error("amg: %lld entries are too many for the host setup (32-bit row pointers)", A0.nnz());
+    return PHB_ERR_UNSUPPORTED;
+  }
   // singular with the constant in the null space? (all-Neumann pressure: every row sums to zero)
   H.singular = rows_sum_to_zero(A0);
   const long long nnz0 = std::max<long long>(1, A0.nnz());
@@ -1154,7 +1158,12 @@ int rebuild_dist_t(phb_solver *s) {
   D.built = true;
   D.setups++;
   D.setupMs = H.setupMs;
-  D.opComplexity = TH.opComplexity;
+  {  // work per rank relative to its level-0 rows: own part of the distributed levels + the replicated tail
+    double nnzAll = 0.;
+    for (auto &d : H.dist) nnzAll += (double)d.L.A.nnz();
+    for (auto &t : TH.lev) nnzAll += (double)t.A.nnz();
+    D.opComplexity = nnzAll / std::max(1., (double)H.dist[0].L.A.nnz());
+  }
   D.itersAfterSetup = -1;
   D.stale = false;
   if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
