@@ -221,6 +221,7 @@ int phb_amg_dist_matrix_size(const phb_amg_dist *h, int rank, int level, int whi
 int phb_amg_dist_matrix(const phb_amg_dist *h, int rank, int level, int which, int *rowPtr, int *colGid,
                         double *vals, int *rowGid);
 int phb_amg_dist_halo(const phb_amg_dist *h, int rank, int level, int *sendPtr, int *sendIdx, int *recvPtr);
+int phb_amg_dist_ghost_gids(const phb_amg_dist *h, int rank, int level, int *out);
 int phb_amg_dist_destroy(phb_amg_dist *h);
 
 /* ---------------------------------------------------------- fields, equations

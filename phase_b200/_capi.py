@@ -73,6 +73,7 @@ SIGNATURES = {
     "phb_amg_dist_matrix_size": (ci, [vp, ci, ci, ci, pi, C.POINTER(cll)]),
     "phb_amg_dist_matrix": (ci, [vp, ci, ci, ci, pi, pi, pd, pi]),
     "phb_amg_dist_halo": (ci, [vp, ci, ci, pi, pi, pi]),
+    "phb_amg_dist_ghost_gids": (ci, [vp, ci, ci, pi]),
     "phb_amg_dist_destroy": (ci, [vp]),
     "phb_field_create": (ci, [vp, ci, cs, pvp]),
     "phb_field_destroy": (ci, [vp]),

@@ -1550,6 +1550,15 @@ int phb_amg_dist_halo(const phb_amg_dist *h, int rank, int level, int *sendPtr, 
   return PHB_OK;
 }
 
+// global ids (within the level) of the rank's ghost columns, in ghost order: recvPtr[nRanks] entries
+int phb_amg_dist_ghost_gids(const phb_amg_dist *h, int rank, int level, int *out) {
+  PHB_REQUIRE(h && out && rank >= 0 && rank < h->nRanks && level >= 0 && level < (int)h->H[rank].dist.size(),
+              "phb_amg_dist_ghost_gids: bad argument");
+  const DistLevel &D = h->H[rank].dist[level];
+  std::copy(D.gid.begin() + D.n, D.gid.end(), out);
+  return PHB_OK;
+}
+
 int phb_amg_dist_destroy(phb_amg_dist *h) {
   delete h;
   return PHB_OK;

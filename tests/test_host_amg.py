@@ -221,6 +221,12 @@ class DistAmg:
                                         rp_.ctypes.data_as(_capi.pi)) == 0
         return sp_, si[:sp_[-1]], rp_
 
+    def ghost_gids(self, rank, level):
+        n = int(self.halo(rank, level, 100000)[2][-1])
+        out = np.zeros(max(n, 1), np.int32)
+        assert self.L.phb_amg_dist_ghost_gids(self.h, rank, level, out.ctypes.data_as(_capi.pi)) == 0
+        return out[:n]
+
     def tail(self, rank):
         t = HostAmg.__new__(HostAmg)
         t.L = self.L
@@ -239,7 +245,7 @@ def block_partition(nx, ny, px, py):
     return (np.minimum(j * py // ny, py - 1) * px + np.minimum(i * px // nx, px - 1)).astype(np.int32)
 
 
-@pytest.mark.parametrize("px,py,fixed", [(2, 1, False), (2, 2, True), (1, 3, False)])
+@pytest.mark.parametrize("px,py,fixed", [(2, 1, False), (2, 2, True), (1, 3, False), (2, 4, False)])
 def test_distributed_hierarchy_is_the_global_galerkin_hierarchy(px, py, fixed):
     nx, ny = 48, 36
     A = neumann_laplacian(nx, ny, fixed_left=fixed)
@@ -281,6 +287,8 @@ def test_distributed_hierarchy_is_the_global_galerkin_hierarchy(px, py, fixed):
                 sent = gid_r[si_r[sp_r[q]:sp_r[q + 1]]]
                 rp_q = H.halo(q, l, 100000)[2]
                 assert rp_q[r + 1] - rp_q[r] == len(sent)
+                # ... cell by cell, in order: the k-th value r packs for q lands in q's k-th ghost slot of r
+                assert np.array_equal(sent, H.ghost_gids(q, l)[rp_q[r]:rp_q[r + 1]])
     # a V(1,1) cycle over the global levels + the replicated tail preconditions BiCGStab like the serial one
     tail = H.tail(0).cycle()
 
