@@ -222,6 +222,8 @@ int phb_amg_dist_matrix(const phb_amg_dist *h, int rank, int level, int which, i
                         double *vals, int *rowGid);
 int phb_amg_dist_halo(const phb_amg_dist *h, int rank, int level, int *sendPtr, int *sendIdx, int *recvPtr);
 int phb_amg_dist_ghost_gids(const phb_amg_dist *h, int rank, int level, int *out);
+/* which + 10 in phb_amg_dist_matrix*: the rank's LOCAL column numbering (what the device cycle works on) */
+int phb_amg_dist_tail_offsets(const phb_amg_dist *h, int *offsets);
 int phb_amg_dist_destroy(phb_amg_dist *h);
 
 /* ---------------------------------------------------------- fields, equations

@@ -74,6 +74,7 @@ SIGNATURES = {
     "phb_amg_dist_matrix": (ci, [vp, ci, ci, ci, pi, pi, pd, pi]),
     "phb_amg_dist_halo": (ci, [vp, ci, ci, pi, pi, pi]),
     "phb_amg_dist_ghost_gids": (ci, [vp, ci, ci, pi]),
+    "phb_amg_dist_tail_offsets": (ci, [vp, pi]),
     "phb_amg_dist_destroy": (ci, [vp]),
     "phb_field_create": (ci, [vp, ci, cs, pvp]),
     "phb_field_destroy": (ci, [vp]),

@@ -1502,11 +1502,17 @@ const phb_amg_host *phb_amg_dist_tail(const phb_amg_dist *h, int rank) {
 // which: 0 = A_l (rows = the rank's cells of level l, global column ids of level l),
 //        1 = P_l (same rows, global column ids of level l + 1),
 //        2 = R_l (rows = the rank's cells of level l + 1, global column ids of level l)
-static const HCsr &dist_pick(const DistLevel &D, int which) { return which == 0 ? D.L.A : which == 1 ? D.L.P : D.L.R; }
+// which + 10: the same matrices with the rank's LOCAL column numbering (owned, then ghosts), i.e. exactly the
+// data the device cycle works on
+static const HCsr &dist_pick(const DistLevel &D, int which) {
+  which %= 10;
+  return which == 0 ? D.L.A : which == 1 ? D.L.P : D.L.R;
+}
 
 int phb_amg_dist_matrix_size(const phb_amg_dist *h, int rank, int level, int which, int *nRows, long long *nnz) {
   PHB_REQUIRE(h && nRows && nnz && rank >= 0 && rank < h->nRanks && level >= 0 &&
-              level < (int)h->H[rank].dist.size() && which >= 0 && which <= 2, "phb_amg_dist_matrix_size: bad argument");
+              level < (int)h->H[rank].dist.size() && which >= 0 && which % 10 <= 2 && which < 20,
+              "phb_amg_dist_matrix_size: bad argument");
   const HCsr &M = dist_pick(h->H[rank].dist[level], which);
   *nRows = M.n; *nnz = M.nnz();
   return PHB_OK;
@@ -1515,13 +1521,19 @@ int phb_amg_dist_matrix_size(const phb_amg_dist *h, int rank, int level, int whi
 int phb_amg_dist_matrix(const phb_amg_dist *h, int rank, int level, int which, int *rowPtr, int *colGid,
                         double *vals, int *rowGid) {
   PHB_REQUIRE(h && rowPtr && colGid && vals && rowGid && rank >= 0 && rank < h->nRanks && level >= 0 &&
-              level < (int)h->H[rank].dist.size() && which >= 0 && which <= 2, "phb_amg_dist_matrix: bad argument");
+              level < (int)h->H[rank].dist.size() && which >= 0 && which % 10 <= 2 && which < 20,
+              "phb_amg_dist_matrix: bad argument");
   const DistHierarchy &H = h->H[rank];
   const DistLevel &D = H.dist[level];
   const HCsr &M = dist_pick(D, which);
   const bool last = level + 1 == (int)H.dist.size();
   std::copy(M.rp.begin(), M.rp.end(), rowPtr);
   std::copy(M.v.begin(), M.v.end(), vals);
+  if (which >= 10) {
+    std::copy(M.ci.begin(), M.ci.end(), colGid);
+    for (int i = 0; i < M.n; ++i) rowGid[i] = i;
+    return PHB_OK;
+  }
   auto coarseGid = [&](int c) { return last ? H.tailOff[rank] + c : H.dist[level + 1].gid[c]; };
   if (which == 2) {
     for (int i = 0; i < M.n; ++i) rowGid[i] = coarseGid(i);
@@ -1547,6 +1559,13 @@ int phb_amg_dist_halo(const phb_amg_dist *h, int rank, int level, int *sendPtr, 
   std::copy(a.sendPtr.begin(), a.sendPtr.end(), sendPtr);
   std::copy(a.sendIdx.begin(), a.sendIdx.end(), sendIdx);
   std::copy(a.recvPtr.begin(), a.recvPtr.end(), recvPtr);
+  return PHB_OK;
+}
+
+// rank segments of the first replicated level: nRanks + 1 offsets
+int phb_amg_dist_tail_offsets(const phb_amg_dist *h, int *out) {
+  PHB_REQUIRE(h && out, "phb_amg_dist_tail_offsets: NULL argument");
+  std::copy(h->H[0].tailOff.begin(), h->H[0].tailOff.end(), out);
   return PHB_OK;
 }
 

@@ -342,3 +342,109 @@ def test_setup_does_not_depend_on_the_thread_count(monkeypatch):
     assert len(mats[0]) == len(mats[1])
     for a, b in zip(*mats):
         assert a.shape == b.shape and abs(a - b).max() == 0.0
+
+
+@pytest.mark.parametrize("px,py", [(2, 1), (2, 2), (2, 4)])
+def test_rank_local_cycle_with_halo_exchanges_equals_the_global_cycle(px, py):
+    """numpy transcription of the DEVICE cycle (Cycle::run in amg.cu) on exactly the per-rank data it uses -- local
+    matrices with ghost columns, send/receive lists, rank-local restriction, gathered tail -- against the same cycle
+    on the assembled global matrices."""
+    nx, ny = 48, 40
+    A = neumann_laplacian(nx, ny)
+    H = DistAmg(A, block_partition(nx, ny, px, py))
+    NR, ND = H.nRanks, H.nDist
+    toff = np.zeros(NR + 1, np.int32)
+    assert H.L.phb_amg_dist_tail_offsets(H.h, toff.ctypes.data_as(_capi.pi)) == 0
+
+    def local(rank, level, which, ncols):
+        rp, ci, v, _ = H.rank_matrix(rank, level, which + 10)
+        return sp.csr_matrix((v, ci, rp), shape=(len(rp) - 1, ncols))
+
+    lev = []
+    for l in range(ND):
+        ranks = []
+        for r in range(NR):
+            sp_, si, rp_ = H.halo(r, l, 100000)
+            n = H.rank_matrix(r, l, 10)[0].shape[0] - 1
+            g = int(rp_[-1])
+            ncr = H.rank_matrix(r, l, 12)[0].shape[0] - 1
+            gcn = int(toff[-1]) if l + 1 == ND else None
+            ranks.append(dict(n=n, g=g, sp=sp_, si=si, rp=rp_, nc=ncr, A=local(r, l, 0, n + g), Pc=gcn))
+        lev.append(ranks)
+    for l in range(ND):
+        for r in range(NR):
+            e = lev[l][r]
+            mcols = e["Pc"] if e["Pc"] is not None else lev[l + 1][r]["n"] + lev[l + 1][r]["g"]
+            e["P"] = local(r, l, 1, mcols)
+            e["R"] = local(r, l, 2, e["n"])
+            d = e["A"].diagonal()
+            rho = (abs(e["A"]).sum(axis=1).A1 / abs(d)).max()
+            e["w"] = (4.0 / 3.0 / rho) / d
+    tail = H.tail(0).cycle()
+
+    def halo(l, X):
+        for r in range(NR):
+            for q in range(NR):
+                if q == r:
+                    continue
+                src, dst = lev[l][q], lev[l][r]
+                vals = X[q][src["si"][src["sp"][r]:src["sp"][r + 1]]]
+                X[r][dst["n"] + dst["rp"][q]:dst["n"] + dst["rp"][q + 1]] = vals
+
+    def dist_cycle(b_ranks):
+        xs, bs = [], [b_ranks]
+        for l in range(ND):                                    # down
+            X = []
+            for r in range(NR):
+                e = lev[l][r]
+                x = np.zeros(e["n"] + e["g"])
+                x[:e["n"]] = e["w"] * bs[l][r]
+                X.append(x)
+            halo(l, X)
+            bc = [lev[l][r]["R"] @ (bs[l][r] - lev[l][r]["A"] @ X[r]) for r in range(NR)]
+            xs.append(X)
+            bs.append(bc)
+        xg = tail(np.concatenate(bs[ND]))                      # gathered, replicated tail
+        for l in range(ND - 1, -1, -1):                        # up
+            X = xs[l]
+            if l + 1 < ND:
+                halo(l + 1, xs[l + 1])
+            for r in range(NR):
+                e = lev[l][r]
+                xc = xg if l + 1 == ND else xs[l + 1][r]
+                X[r][:e["n"]] += e["P"] @ xc
+            halo(l, X)
+            for r in range(NR):
+                e = lev[l][r]
+                X[r][:e["n"]] = X[r][:e["n"]] + e["w"] * (bs[l][r] - e["A"] @ X[r])
+        return [X[r][:lev[0][r]["n"]] for r, X_ in enumerate(xs[0])]
+
+    # the same cycle on the assembled global matrices, with the per-rank smoother weights scattered by global id
+    glob, size = [], A.shape[0]
+    Al = A
+    for l in range(ND):
+        nc = sum(lev[l][r]["nc"] for r in range(NR))
+        P = H.global_matrix(l, 1, (size, nc))
+        R = H.global_matrix(l, 2, (nc, size))
+        w = np.zeros(size)
+        for r in range(NR):
+            w[H.rank_matrix(r, l, 0)[3]] = lev[l][r]["w"]
+        glob.append((Al, P, R, w))
+        Al, size = (R @ Al @ P).tocsr(), nc
+
+    def glob_cycle(l, b):
+        if l == ND:
+            return tail(b)
+        A_, P_, R_, w_ = glob[l]
+        x = w_ * b
+        x = x + P_ @ glob_cycle(l + 1, R_ @ (b - A_ @ x))
+        return x + w_ * (b - A_ @ x)
+
+    b = np.random.default_rng(5).standard_normal(A.shape[0])
+    b -= b.mean()
+    gids = [H.rank_matrix(r, 0, 0)[3] for r in range(NR)]
+    xd = dist_cycle([b[g] for g in gids])
+    xg = glob_cycle(0, b)
+    for r in range(NR):
+        assert np.abs(xd[r] - xg[gids[r]]).max() <= 1e-11 * np.abs(xg).max()
+    H.close()
