@@ -106,6 +106,12 @@ HCsr spgemm(const HCsr &A, const HCsr &B) {
     std::vector<int> marker(B.m, -1);
     std::vector<int> &cc = ci[t];
     std::vector<double> &cv = v[t];
+    {  // one allocation per chunk: rows of A B hold about (entries per row of A) x (entries per row of B) / 2 entries
+      const double perRowA = A.n ? (double)A.nnz() / A.n : 0., perRowB = B.n ? (double)B.nnz() / B.n : 0.;
+      const size_t guess = (size_t)((end - begin) * std::max(perRowA, std::min(perRowA * perRowB, perRowA * perRowB * 0.5 + 2.)));
+      cc.reserve(guess);
+      cv.reserve(guess);
+    }
     std::vector<std::pair<int, double>> row;
     for (int i = begin; i < end; ++i) {
       const int start = (int)cc.size();
@@ -290,6 +296,8 @@ int make_prolongator(const HCsr &A, double theta, double omegaP, int level, Host
   parallel_chunks(n, [&](int begin, int end, int t) {
     chunkBegin[t] = begin;
     std::vector<std::pair<int, double>> row;
+    pci[t].reserve((size_t)(end - begin) * 4);
+    pv[t].reserve((size_t)(end - begin) * 4);
     for (int i = begin; i < end; ++i) {
       row.clear();
       row.push_back({agg[i], 1. - w});  // diagonal term of Af: df/df = 1

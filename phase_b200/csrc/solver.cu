@@ -682,7 +682,7 @@ int phb_solver_setup(phb_solver *s, const char *key, const char *value) {
     PHB_REQUIRE(s->amg.theta >= 0. && s->amg.theta < 1., "amgTheta must lie in [0, 1)");
   } else if (k == "amgCoarsest") {
     s->amg.coarsest = std::stoi(v); s->amg.built = false;
-    PHB_REQUIRE(s->amg.coarsest >= 1, "amgCoarsest must be positive");
+    PHB_REQUIRE(s->amg.coarsest >= 1 && s->amg.coarsest <= 1024, "amgCoarsest must lie in 1..1024 (dense coarsest solve)");
   } else if (k == "amgSweeps") {
     s->amg.nu = std::stoi(v);
     PHB_REQUIRE(s->amg.nu >= 1 && s->amg.nu <= 4, "amgSweeps must lie in 1..4");
