@@ -194,6 +194,10 @@ int phb_solver_bytes(const phb_solver *s, double out[2]);
  * info = [levels, operator complexity, host setup ms, setups so far, coarsest rows, kernel launches
  *         per cycle, iterations of the first solve after the last setup, hierarchy stale (0/1)] */
 int phb_solver_amg_info(const phb_solver *s, double info[8]);
+/* live timing (CUDA events, resident data) of the cycle's level-0 kernels and of one whole cycle:
+ * out = ms per launch of [residual, restriction, prolongation, Jacobi sweep], ms per cycle, algorithmic bytes of
+ * the Jacobi launch, of the cycle, launches per cycle (bench.py roofline leg; single rank) */
+int phb_solver_time_amg(phb_solver *s, int reps, double out[8]);
 /* The same setup on a host CSR matrix, level matrices readable (works on a host-only context; used by
  * the CPU tests to check the Galerkin products and the cycle against scipy).
  * which: 0 = A_l, 1 = P_l (n_l x n_{l+1}), 2 = R_l = P_l^T */

@@ -61,6 +61,7 @@ SIGNATURES = {
     "phb_solver_time_spmv": (ci, [vp, ci, pd]),
     "phb_solver_bytes": (ci, [vp, pd]),
     "phb_solver_amg_info": (ci, [vp, pd]),
+    "phb_solver_time_amg": (ci, [vp, ci, pd]),
     "phb_amg_host_build": (ci, [ci, pi, pi, pd, cd, ci, pvp]),
     "phb_amg_host_levels": (ci, [vp, pi, pi, pi]),
     "phb_amg_host_level_size": (ci, [vp, ci, ci, pi, pi, C.POINTER(cll), pd]),

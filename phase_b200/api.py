@@ -285,6 +285,13 @@ class SparseMatrixSolver:
                 "itersAfterSetup", "stale")
         return dict(zip(keys, (float(v) for v in out)))
 
+    def timeAmg(self, reps=20):
+        out = (C.c_double * 8)()
+        check(self.L.phb_solver_time_amg(self.h, reps, out))
+        keys = ("msResidual", "msRestriction", "msProlongation", "msJacobi", "msCycle", "bytesJacobi", "bytesCycle",
+                "launchesPerCycle")
+        return dict(zip(keys, (float(v) for v in out)))
+
     def close(self):
         if self.own and self.h:
             self.L.phb_solver_destroy(self.h)

@@ -1395,6 +1395,64 @@ int amg_apply(phb_solver *s, const double *in, double *out, bool inLoop) {
   return cy.run(in, out);
 }
 
+// Live timing of the cycle's dominant launches (bench.py roofline leg): CUDA events on the context stream around
+// `reps` launches of each level-0 kernel and of the whole cycle, on the solver's own vectors.
+template <typename T>
+int amg_time_t(phb_solver *s, int reps, double out[8]) {
+  phb_ctx *c = s->ctx;
+  AmgData &D = s->amg;
+  AmgLevel &V = *D.lev[0], &C = *D.lev[1];
+  const int ld = V.ld;
+  const SellPattern &pat0 = *s->pat;
+  const T *val0 = level0_vals<T>(D), *w = as<T>(V.w);
+  T *x = as<T>(V.x), *r = as<T>(V.r);
+  const double *in = s->p.p;
+  double *res = s->ph.p;
+  cudaEvent_t e0, e1;
+  PHB_CUDA(cudaEventCreate(&e0));
+  PHB_CUDA(cudaEventCreate(&e1));
+  Cycle<T> cy{s, D, false, nullptr, s->nComp};
+  auto timed = [&](int which, double *ms) -> int {
+    for (int k = -2; k < reps; ++k) {
+      if (k == 0) PHB_CUDA(cudaEventRecord(e0, c->stream));
+      if (which == 0) launch<1>(s, pat0, val0, (const T *)x, ld, r, ld, in, (const T *)nullptr, false);
+      if (which == 1) launch<0>(s, V.R.pat, (const T *)as<T>(V.R.vals), (const T *)r, ld, as<T>(C.b) + cy.mySeg(1), C.ld,
+                                (const T *)nullptr, (const T *)nullptr, false);
+      if (which == 2) launch<3>(s, V.P.pat, (const T *)as<T>(V.P.vals), (const T *)as<T>(C.x), C.ld, x, ld, (const T *)nullptr,
+                                (const T *)nullptr, false);
+      if (which == 3) launch<2>(s, pat0, val0, (const T *)x, ld, res, ld, in, w, false);
+      if (which == 4) PHB_CHECK(cy.run(in, res));
+    }
+    PHB_CUDA(cudaEventRecord(e1, c->stream));
+    PHB_CUDA(cudaEventSynchronize(e1));
+    float t = 0.f;
+    PHB_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    *ms = (double)t / reps;
+    return PHB_OK;
+  };
+  PHB_CUDA(cudaMemsetAsync(x, 0, (size_t)ld * s->nComp * sizeof(T), c->stream));
+  for (int k = 0; k < 5; ++k) PHB_CHECK(timed(k, &out[k]));
+  PHB_CUDA(cudaMemsetAsync(x, 0, (size_t)ld * s->nComp * sizeof(T), c->stream));
+  PHB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double v = sizeof(T), n = V.n, k = s->nComp;
+  // Jacobi sweep of level 0: matrix (index + value per entry, row pointers), w, then per component the gathered x,
+  // the row's own x (cycle precision), b read and result written (both fp64: Krylov vectors)
+  out[5] = (4. + v) * (double)pat0.nnz + 4. * (n + 1.) + v * n + (2. * v + 16.) * k * n;
+  out[6] = amg_cycle_bytes(s);
+  out[7] = amg_launches_per_apply(s);
+  return PHB_OK;
+}
+
+int amg_time(phb_solver *s, int reps, double out[8]) {
+  AmgData &D = s->amg;
+  PHB_REQUIRE(D.built && D.lev.size() >= 2 && s->pat && s->ph.p && s->p.p,
+              "phb_solver_time_amg: no multigrid hierarchy with at least two levels has been used yet");
+  PHB_REQUIRE(reps > 0, "phb_solver_time_amg: reps must be positive");
+  return D.builtSingle ? amg_time_t<float>(s, reps, out) : amg_time_t<double>(s, reps, out);
+}
+
 }  // namespace phb
 
 // ===================================================================== C ABI (inspection / tests)
@@ -1666,6 +1724,16 @@ int phb_amg_host_coarse_inverse(const phb_amg_host *h, double *inv) {
 int phb_amg_host_destroy(phb_amg_host *h) {
   delete h;
   return PHB_OK;
+}
+
+// out = ms per launch of the level-0 [residual, restriction, prolongation, Jacobi sweep], ms per whole cycle,
+// algorithmic bytes of the Jacobi launch, of the cycle, launches per cycle (single rank: no exchanges are timed)
+int phb_solver_time_amg(phb_solver *s, int reps, double out[8]) {
+  PHB_TRY_BEGIN
+  PHB_REQUIRE(s && out, "phb_solver_time_amg: NULL argument");
+  PHB_REQUIRE(s->ctx->nProcs == 1 || s->amg.nDist == 0, "phb_solver_time_amg: single-rank hierarchies only");
+  return phb::amg_time(s, reps, out);
+  PHB_TRY_END
 }
 
 // [levels, operator complexity, setup ms (host), setups so far, coarsest rows, kernel launches per cycle,

@@ -164,4 +164,5 @@ int amg_apply(phb_solver *s, const double *in, double *out, bool inLoop);
 int amg_launches_per_apply(const phb_solver *s);
 void amg_record_iters(phb_solver *s, int iters);
 double amg_cycle_bytes(const phb_solver *s);
+int amg_time(phb_solver *s, int reps, double out[8]);
 }  // namespace phb
