@@ -156,6 +156,7 @@ def run_reference(args):
     import oracle as O
     nx = ny = args.n
     dt = 0.5 / nx
+    config = workload_config(args, 1)     # the same workload description as the B200 arm prints
     if args.precond == "amg":
         args.precond = "ilu0"        # the reference arm always runs the reference's algorithm
     iu, ip, src = typical_iters(args.precond)
@@ -171,7 +172,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, 1),
+            "config": config,
+            "reference_algorithm": "the reference's path: host CrsEquation-style assembly + right-preconditioned BiCGStab with "
+                                   "ILU(0) (Belos/Ifpack2 RILUK(0) role) on all host cores, same mesh, time step and tolerance",
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "detail": detail},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
