@@ -64,7 +64,7 @@ class HostAmg:
         assert self.L.phb_amg_host_coarse_inverse(self.h, inv.ctypes.data_as(_capi.pd)) == 0
         return inv
 
-    def cycle(self, nu=1, omega_s=4.0 / 3.0):
+    def cycle(self, nu=1, omega_s=1.8):
         """scipy transcription of amg_apply() (amg.cu)"""
         lv = []
         for l in range(self.nLevels):
