@@ -61,24 +61,33 @@ class ClockSampler:
         for line in self.proc.stdout:
             p = [x.strip() for x in line.split(",")]
             try:
-                self.samples.append(float(p[0]))
+                active = [n for n, v in zip(names, p[2:6]) if v.lower().startswith("active")]
+                self.samples.append((time.perf_counter(), float(p[0]), active))
                 self.max_mhz = float(p[1])
-                for n, v in zip(names, p[2:6]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(n)
             except Exception:
                 pass
 
+    def mark(self):
+        """start of the timed region (the sampler itself is started earlier: nvidia-smi needs ~0.1 s to come up)"""
+        self.t0 = time.perf_counter()
+
     def stop(self):
+        t1 = time.perf_counter()
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+        t0 = getattr(self, "t0", 0.0)
+        inside = [x for x in self.samples if t0 <= x[0] <= t1]
+        # a timed region shorter than the sampling period: fall back to the samples closest to it (under the same load:
+        # the last warm-up step) and say so
+        used = inside if inside else self.samples[-2:]
+        mhz = sorted(x[1] for x in used)
+        reasons = sorted({r for x in used for r in x[2]})
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(inside), "samples_used": len(used), "period_ms": 50}
 
 
 def cpu_reference_sample(nx, ny, dt, iters_u, iters_p, cap=12, precond="ilu0"):
@@ -313,13 +322,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                    # before the warm-up, so that it is sampling when the timed region starts
     stats = []
     for _ in range(args.warmup):
         stats.append(fs.solve(dt))
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     launches0 = comm.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
