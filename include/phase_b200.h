@@ -187,7 +187,7 @@ int phb_solver_bytes(const phb_solver *s, double out[2]);
 
 /* `preconditioner amg` -- smoothed-aggregation multigrid V-cycle (the reference's `lib muelu`,
  * Math/TrilinosMueluSparseMatrixSolver.cpp:27-32).  Extra setup keys: amgTheta (strength threshold, 0),
- * amgCoarsest (rows of the densely inverted coarsest level, 400), amgSweeps (Jacobi sweeps before and
+ * amgCoarsest (rows of the densely inverted coarsest level, at most 1000 = default), amgSweeps (Jacobi sweeps before and
  * after the coarse correction, 1), amgSmootherWeight (1.8, divided by the Gershgorin bound of
  * rho(D^-1 A)), amgRebuild (auto | always).  The hierarchy is built on the host once per matrix and
  * reused while the matrix stays a scalar multiple of it or the iteration count does not degrade.

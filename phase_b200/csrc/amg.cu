@@ -218,29 +218,58 @@ struct phb_amg_host {
 namespace {
 
 bool dense_inverse(std::vector<double> &M, int n) {
-  // Gauss-Jordan with partial pivoting on [M | I]
-  std::vector<double> I((size_t)n * n, 0.);
-  for (int i = 0; i < n; ++i) I[(size_t)i * n + i] = 1.;
-  for (int c = 0; c < n; ++c) {
-    int piv = c;
-    double best = std::fabs(M[(size_t)c * n + c]);
-    for (int r = c + 1; r < n; ++r)
-      if (std::fabs(M[(size_t)r * n + c]) > best) { best = std::fabs(M[(size_t)r * n + c]); piv = r; }
+  // LU with partial pivoting (row-major, in place), then the columns of the inverse by forward / backward substitution,
+  // column blocks in parallel
+  std::vector<int> perm(n);
+  std::iota(perm.begin(), perm.end(), 0);
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    double best = std::fabs(M[(size_t)k * n + k]);
+    for (int r = k + 1; r < n; ++r)
+      if (std::fabs(M[(size_t)r * n + k]) > best) { best = std::fabs(M[(size_t)r * n + k]); piv = r; }
     if (!(best > 0.)) return false;
-    if (piv != c)
-      for (int k = 0; k < n; ++k) {
-        std::swap(M[(size_t)c * n + k], M[(size_t)piv * n + k]);
-        std::swap(I[(size_t)c * n + k], I[(size_t)piv * n + k]);
-      }
-    const double inv = 1. / M[(size_t)c * n + c];
-    for (int k = 0; k < n; ++k) { M[(size_t)c * n + k] *= inv; I[(size_t)c * n + k] *= inv; }
-    for (int r = 0; r < n; ++r) {
-      if (r == c) continue;
-      const double f = M[(size_t)r * n + c];
-      if (f == 0.) continue;
-      double *mr = &M[(size_t)r * n], *mc = &M[(size_t)c * n], *ir = &I[(size_t)r * n], *ic = &I[(size_t)c * n];
-      for (int k = 0; k < n; ++k) { mr[k] -= f * mc[k]; ir[k] -= f * ic[k]; }
+    if (piv != k) {
+      std::swap_ranges(M.begin() + (size_t)k * n, M.begin() + (size_t)(k + 1) * n, M.begin() + (size_t)piv * n);
+      std::swap(perm[k], perm[piv]);
     }
+    const double inv = 1. / M[(size_t)k * n + k];
+    const double *rk = &M[(size_t)k * n];
+    for (int r = k + 1; r < n; ++r) {
+      double *rr = &M[(size_t)r * n];
+      const double l = rr[k] * inv;
+      if (l == 0.) continue;
+      rr[k] = l;
+      for (int c = k + 1; c < n; ++c) rr[c] -= l * rk[c];
+    }
+  }
+  std::vector<double> I((size_t)n * n);
+  const int T = std::max(1, std::min(host_threads(), n / 64));
+  auto solve_cols = [&](int j0, int j1) {
+    std::vector<double> y(n);
+    for (int j = j0; j < j1; ++j) {
+      // column j of the inverse solves A x = e_j, i.e. L U x = P e_j
+      for (int i = 0; i < n; ++i) {
+        double acc = perm[i] == j ? 1. : 0.;
+        const double *ri = &M[(size_t)i * n];
+        for (int k = 0; k < i; ++k) acc -= ri[k] * y[k];
+        y[i] = acc;
+      }
+      for (int i = n - 1; i >= 0; --i) {
+        double acc = y[i];
+        const double *ri = &M[(size_t)i * n];
+        for (int k = i + 1; k < n; ++k) acc -= ri[k] * y[k];
+        y[i] = acc / ri[i];
+      }
+      for (int i = 0; i < n; ++i) I[(size_t)i * n + j] = y[i];
+    }
+  };
+  if (T == 1) {
+    solve_cols(0, n);
+  } else {
+    std::vector<std::thread> th;
+    const int chunk = (n + T - 1) / T;
+    for (int t = 0; t < T; ++t) th.emplace_back(solve_cols, std::min(n, t * chunk), std::min(n, (t + 1) * chunk));
+    for (auto &x : th) x.join();
   }
   M.swap(I);
   return true;
@@ -1540,7 +1569,7 @@ int phb_amg_dist_build(int nRanks, int n, const int *rowPtr, const int *colInd, 
       ThreadExchanger ex;
       ex.rank = r; ex.nProcs = nRanks; ex.B = &board;
       rc[r] = build_dist_hierarchy(ex, std::move(A[r]), std::move(halo[r]), std::move(gid[r]), theta,
-                                   coarsest > 0 ? coarsest : 400, tailRows, 4. / 3., h->H[r]);
+                                   coarsest > 0 ? coarsest : 1000, tailRows, 4. / 3., h->H[r]);
       if (rc[r] != PHB_OK) err[r] = phb_last_error();
     });
   for (auto &t : th) t.join();
@@ -1672,7 +1701,7 @@ int phb_amg_host_build(int n, const int *rowPtr, const int *colInd, const double
     A.rp[r + 1] = (int)A.ci.size();
   }
   std::unique_ptr<phb_amg_host> h(new phb_amg_host());
-  PHB_CHECK(build_hierarchy(std::move(A), theta, coarsest > 0 ? coarsest : 400, 4. / 3., h->H));
+  PHB_CHECK(build_hierarchy(std::move(A), theta, coarsest > 0 ? coarsest : 1000, 4. / 3., h->H));
   *out = h.release();
   return PHB_OK;
   PHB_TRY_END

@@ -93,7 +93,7 @@ struct AmgData {
   std::vector<int> tailOff, tailCnt, tailSendOff, tailSendCnt;
   const SellPattern *src = nullptr;
   bool built = false, denseCoarse = false, stale = false, rebuildAlways = false;
-  int nComp = 1, nCoarse = 0, nu = 1, coarsest = 400, setups = 0, itersAfterSetup = -1;
+  int nComp = 1, nCoarse = 0, nu = 1, coarsest = 1000, setups = 0, itersAfterSetup = -1;
   // smoother weight omegaS / rho(D^-1 A): 1.8 instead of the textbook 4/3 -- inside a Krylov method the stronger damping of
   // the mid-range modes wins (scipy transcription, 1M cells: 10-12 instead of 13-15 iterations; 11-13 % fewer on the
   // variable-density and 7-point operators); |1 - 1.8 lambda / rho| <= 0.8 for every mode, so the sweep stays a contraction

@@ -448,3 +448,21 @@ def test_rank_local_cycle_with_halo_exchanges_equals_the_global_cycle(px, py):
     for r in range(NR):
         assert np.abs(xd[r] - xg[gids[r]]).max() <= 1e-11 * np.abs(xg).max()
     H.close()
+
+
+def test_dense_coarsest_level_of_a_thousand_rows():
+    """the coarsest level may hold up to 1024 rows: LU + column solves (threaded) give the inverse to round-off,
+    for a regular and for a singular (regularised) operator"""
+    A = neumann_laplacian(31, 30, fixed_left=True)
+    H = HostAmg(A, coarsest=1000)
+    assert H.nLevels == 1 and H.dense
+    assert np.abs(H.coarse_inverse() @ A.toarray() - np.eye(930)).max() < 1e-9
+    H.close()
+    A = neumann_laplacian(31, 30)
+    H = HostAmg(A, coarsest=1000)
+    inv = H.coarse_inverse()
+    b = np.random.default_rng(0).standard_normal(930)
+    b -= b.mean()
+    x = inv @ b
+    assert np.abs(A @ x - b).max() < 1e-9 * np.abs(b).max() * 930          # solves compatible systems of the singular operator
+    H.close()
