@@ -2,14 +2,15 @@
 """bench.py -- the hot path's headline benchmark on B200.
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA arm
-    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port, all host cores)
 
-Workload (BASELINE.json configs[1]): lid-driven cavity, rho=1, mu=0.1, on a
-synthetic 2000x2000 quad mesh (4M cells) per GPU; one "step" = one whole time step
-of the snapshot's solver module (FractionalStep::solve: assemble uEqn_, BiCGStab,
-interpolate, assemble pEqn_, BiCGStab, gradient, correct).  The north star calls
-the time step "PISO"; the mounted snapshot ships only the fractional-step
-successor, which is what is timed and parity-checked.
+Workload (BASELINE.json configs[1]): lid-driven cavity, rho=1, mu=0.1, on a synthetic 2000x2000 quad mesh
+(4M cells); one "step" = one whole time step of the snapshot's solver module (FractionalStep::solve: assemble
+uEqn_, BiCGStab, interpolate, assemble pEqn_, BiCGStab, gradient, correct).  The north star calls the time step
+"PISO"; the mounted snapshot ships only the fractional-step successor, which is what is timed
+and parity-checked.  With N > 1 the same 4M-cell problem is split over the GPUs (strong scaling, `value`) and the
+line also carries the 8M-cells-per-GPU series that ends in the north star's 64M-cell / 8-GPU point
+(`weak_8M_per_gpu`) and a multi-GPU parity check against the oracle (`parity`).
 
 Prints ONE JSON line (rank 0).
 """
@@ -90,106 +91,7 @@ class ClockSampler:
                 "samples": len(inside), "samples_used": len(used), "period_ms": 50}
 
 
-def cpu_reference_sample(nx, ny, dt, iters_u, iters_p, cap=12, precond="ilu0"):
-    """Time the oracle (CPU port of the reference path) on a bounded sample of the
-    SAME 4M-cell step: full assembly + field glue once, and `cap` BiCGStab+Jacobi
-    iterations of each solve on all host cores; the step time is then scaled to
-    the iteration counts the tolerance needs."""
-    import ctypes as C
-    import numpy as np
-    import oracle as O
-    t0 = time.perf_counter()
-    om = O.Mesh.rectilinear(nx, ny, 1.0, 1.0)
-    ofs = O.cavity(om, 1.0, 0.1)
-    t_mesh = time.perf_counter() - t0
-    # a non-trivial state: one cheap capped step so u, p, gradP are not all zero
-    ofs.set_solver_params(tol=1e-30, max_iters=2, precond=1)
-    ofs.step(dt)
-    t0 = time.perf_counter()
-    ue = ofs.assemble_u(dt)
-    t_asm_u = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    pe = ofs.assemble_p(dt)
-    t_asm_p = time.perf_counter() - t0
-    per_iter, t_setup = [], []
-    for e in (ue, pe):
-        rp, ci, va, rhs = e.export()
-        if precond == "ilu0":
-            # the CUDA path's algorithm: ILU(0) in the multicolour ordering, sweeps parallel inside a colour
-            rp2, ci2, va2, new2old, bp = O.multicolor_permute(rp, ci, va)
-            b2 = np.ascontiguousarray((-rhs)[new2old])
-            tt = []
-            for k in (cap, 2 * cap):
-                x2 = np.zeros_like(b2)
-                rr = C.c_double()
-                t0 = time.perf_counter()
-                O.lib().or_bicgstab_blocks(len(b2), O._ip(rp2), O._ip(ci2), O._dp(va2), O._dp(b2), O._dp(x2), 1e-30, k,
-                                           len(bp) - 1, O._ip(bp), C.byref(rr))
-                tt.append(time.perf_counter() - t0)
-            per_iter.append(max((tt[1] - tt[0]) / cap, 0.25 * tt[1] / (2 * cap)))
-            t_setup.append(max(0.0, tt[0] - cap * per_iter[-1]))      # factorisation + initial residual
-        else:
-            t0 = time.perf_counter()
-            O.bicgstab(rp, ci, va, -rhs, tol=1e-30, max_iters=cap, precond=1 if precond == "jacobi" else 0)
-            per_iter.append((time.perf_counter() - t0) / cap)
-            t_setup.append(0.0)
-    # field glue (interpolate, gradient, correct) is part of step(); measure via a capped step
-    ofs.set_solver_params(tol=1e-30, max_iters=1, precond=1)
-    t0 = time.perf_counter()
-    ofs.step(dt)
-    t_step1 = time.perf_counter() - t0
-    t_glue = max(0.0, t_step1 - t_asm_u - t_asm_p - per_iter[0] - per_iter[1])
-    t_full = t_asm_u + t_asm_p + t_glue + sum(t_setup) + iters_u * per_iter[0] + iters_p * per_iter[1]
-    detail = dict(t_mesh_s=t_mesh, t_precond_setup_s=sum(t_setup), preconditioner=precond, t_assemble_u_s=t_asm_u, t_assemble_p_s=t_asm_p, t_glue_s=t_glue,
-                  s_per_iter_u=per_iter[0], s_per_iter_p=per_iter[1], iters_u=iters_u, iters_p=iters_p)
-    return 1.0 / t_full, detail
-
-
-def typical_iters(precond="ilu0"):
-    """Iteration counts per solve at tolerance 1e-8 on the 4M-cell cavity, measured
-    on the GPU arm (same algorithm: right-preconditioned BiCGStab + Jacobi) and
-    committed under profiles/ so the CPU arm can scale its bounded sample."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "iters_4M.json")) as f:
-            d = json.load(f)
-        d = d.get(precond, d)
-        return float(d["iters_u"]), float(d["iters_p"]), "profiles/iters_4M.json"
-    except Exception:
-        return 60.0, 3000.0, "default estimate (profiles/iters_4M.json missing)"
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    import oracle as O
-    nx = ny = args.n
-    dt = 0.5 / nx
-    config = workload_config(args, 1)     # the same workload description as the B200 arm prints
-    if args.precond == "amg":
-        args.precond = "ilu0"        # the reference arm always runs the reference's algorithm
-    iu, ip, src = typical_iters(args.precond)
-    vals = []
-    detail = None
-    for _ in range(max(1, min(args.steps, 2))):
-        v, detail = cpu_reference_sample(nx, ny, dt, iu, ip, precond=args.precond)
-        vals.append(v)
-    v = max(vals)
-    cores = O.lib().or_num_threads()
-    sample = ("1 assembled 4M-cell step + 12/24 BiCGStab(%s) iterations per solve on %d OpenMP threads, scaled to "
-              "%.0f (uEqn) / %.0f (pEqn) iterations per solve (%s)" % (args.precond, cores, iu, ip, src))
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
-            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config,
-            "reference_algorithm": "the reference's path: host CrsEquation-style assembly + right-preconditioned BiCGStab with "
-                                   "ILU(0) (Belos/Ifpack2 RILUK(0) role) on all host cores, same mesh, time step and tolerance",
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "detail": detail},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
-
-
+# ------------------------------------------------------------------------------------------------ workload
 def block_layout(nprocs):
     """px x py blocks, as square as possible (1 -> 1x1, 2 -> 1x2, 4 -> 2x2, 8 -> 2x4)."""
     px = 1
@@ -198,36 +100,414 @@ def block_layout(nprocs):
     return px, nprocs // px
 
 
-def workload_config(args, nprocs):
-    px, py = block_layout(nprocs)
-    strong = getattr(args, "scaling", "strong") == "strong"
-    gx, gy = (args.n, args.n) if strong else (args.n * px, args.n * py)
-    if getattr(args, "mesh", "quad") == "tri":
-        import math
+def workload_config(args):
+    """What is computed -- identical for both arms and (strong scaling) for every N.  How it is computed
+    (preconditioner, precision, partition, exchange mechanism) is each arm's `algorithm` record."""
+    import math
+    if args.mesh == "tri":
         tn = int(round(args.n / math.sqrt(2.0)))
-        return {"workload": "lid-driven cavity (rho=1, mu=0.1, lid u=1), unstructured triangles: %dx%d lattice split along "
-                            "alternating diagonals = %d cells, FractionalStep time step, dt = 0.5 h, BiCGStab + %s, tolerance %g, "
-                            "warm start" % (tn, tn, 2 * tn * tn, args.precond, args.tol),
-                "cells_per_gpu": 2 * tn * tn // nprocs, "global_cells": 2 * tn * tn,
-                "partition": "none" if nprocs == 1 else "RCB, %d parts" % nprocs,
-                "l2": "inputs larger than L2; no flush needed", "tolerance": args.tol, "max_iters": args.max_iters,
-                "preconditioner": args.precond, "comm": "single GPU" if nprocs == 1 else args.comm}
-    return {"workload": "lid-driven cavity (rho=1, mu=0.1, lid u=1), %dx%d quads = %d cells%s, "
-                        "FractionalStep time step (the snapshot's PISO successor), dt = 0.5 h (maxCo 0.5), "
-                        "BiCGStab + %s, tolerance %g on ||r||/||b||, warm start from the previous step"
-                        % (gx, gy, gx * gy, "" if strong or nprocs == 1 else " (%dx%d per GPU)" % (args.n, args.n),
-                           "smoothed-aggregation AMG V(1,1) on pEqn_ / %s on uEqn_" % getattr(args, "u_precond", "ilu0") if args.precond == "amg"
-                           else args.precond, args.tol),
-            "cells_per_gpu": gx * gy // nprocs, "global_cells": gx * gy,
-            "partition": "none" if nprocs == 1 else "%dx%d blocks of %dx%d cells, one per GPU (global grid %dx%d)" % (
-                px, py, gx // px, gy // py, gx, gy),
-            "l2": "inputs larger than L2 (matrix + vectors ~0.6 GB per solve vs 126 MB L2); no flush needed",
-            "tolerance": args.tol, "max_iters": args.max_iters, "preconditioner": args.precond,
-            "comm": "single GPU" if nprocs == 1 else (
-                "NVLink peer-memory kernels inside the Krylov loop (2 halo + 2 all-reduce one-CTA kernels per iteration, "
-                "in the CUDA graph); NCCL outside the loop" if args.comm == "peer" else
-                "NVLink peer memory, halo push/wait and the sigma all-reduce inside the compute kernels" if args.comm == "peer-fused" else
-                "NCCL send/recv + all-reduce")}
+        mesh = "unstructured triangles: %dx%d lattice split along alternating diagonals = %d cells" % (tn, tn, 2 * tn * tn)
+        cells = 2 * tn * tn
+    else:
+        mesh = "%dx%d quads = %d cells" % (args.n, args.n, args.n * args.n)
+        cells = args.n * args.n
+    per = " per GPU (weak scaling: the global grid grows with N)" if args.scaling == "weak" else ""
+    return {"workload": "lid-driven cavity (rho=1, mu=0.1, lid u=1), %s%s, FractionalStep time step (the snapshot's PISO "
+                        "successor), dt = 0.5 h (maxCo 0.5), both equations solved by right-preconditioned BiCGStab to "
+                        "||r||/||b|| <= %g, warm start from the previous step" % (mesh, per, args.tol),
+            "cells": cells, "mesh": args.mesh, "tolerance": args.tol, "max_iters": args.max_iters,
+            "l2": "inputs larger than L2 (matrix + vectors ~0.6 GB per solve vs 126 MB L2); no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_converged_steps(nx, ny, dt, tol, max_iters, n_warm, n_timed, budget_s, state=None):
+    """The oracle (CPU port of the reference path: cell-loop assembly into CrsEquation-style CSR, BiCGStab + ILU(0),
+    field glue) advancing the SAME cavity with every solve converged to `tol`: real wall time per step, nothing
+    scaled.  `state` (u, p, gradP of another run) replaces the rest state; timed steps stop at the wall budget."""
+    import numpy as np
+    import oracle as O
+    cores = O.set_num_threads()            # all host cores, whatever OMP_NUM_THREADS the launcher exported
+    t0 = time.perf_counter()
+    om = O.Mesh.rectilinear(nx, ny, 1.0, 1.0)
+    ofs = O.cavity(om, 1.0, 0.1)
+    t_mesh = time.perf_counter() - t0
+    guesses = None
+    if state is not None:
+        for k in ("ux", "uy", "ufx", "ufy", "p", "pf", "gpx", "gpy"):
+            ofs.view(k)[:] = state[k]
+        guesses = {2 * nx * ny: np.concatenate([state["ux"], state["uy"]]), nx * ny: state["p"]}
+    ofs.use_ilu0_solver(tol=tol, max_iters=max_iters, guesses=guesses)
+    for _ in range(n_warm):
+        ofs.step(dt)
+    n0 = len(ofs.solve_log)
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(n_timed):
+        t0 = time.perf_counter()
+        ofs.step(dt)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    log = ofs.solve_log[n0:]
+    detail = {"threads": cores, "t_mesh_s": t_mesh, "steps_timed": len(times), "warmup_steps": n_warm,
+              "s_per_step": times, "preconditioner": "ilu0 (multicolour ordering, OpenMP over the rows of a colour)",
+              "assembly": "serial cell loops (the reference has no threads)",
+              "iters_u": [it for n, it, rr, t in log if n == 2 * nx * ny],
+              "iters_p": [it for n, it, rr, t in log if n == nx * ny],
+              "relres_max": max([rr for n, it, rr, t in log] or [0.0]),
+              "solve_s_per_step": sum(t for n, it, rr, t in log) / max(1, len(times))}
+    return len(times) / sum(times), cores, detail
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nx = ny = args.n
+    dt = 0.5 / nx
+    n_warm = 1 if args.warmup > 0 else 0
+    v, cores, detail = cpu_converged_steps(nx, ny, dt, args.tol, args.max_iters, n_warm, max(1, args.steps),
+                                           budget_s=args.ref_budget)
+    k = detail["steps_timed"]
+    sample = ("%d fully converged time steps (steps %d..%d from rest) of the %dx%d cavity, tolerance %g, after %d converged "
+              "warm-up step; wall clock per step, nothing extrapolated" % (k, n_warm + 1, n_warm + k, nx, ny, args.tol, n_warm))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": k, "steps_requested": args.steps, "warmup": n_warm, "warmup_requested": args.warmup,
+            "ms_per_step": 1e3 / v, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "algorithm": {"preconditioner": "ilu0", "what": "the reference's path: host CrsEquation-style assembly + right-"
+                          "preconditioned BiCGStab with ILU(0) (the Belos/Ifpack2 RILUK(0) default, "
+                          "M/TrilinosBelosSparseMatrixSolver.cpp:52-83) on all host cores", "threads": cores},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "detail": detail},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+class Job:
+    """torch.distributed + one phase_b200 context per sub-problem."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+
+    def communicator(self):
+        from phase_b200.api import Communicator
+        uid = None
+        if self.world > 1:
+            box = [Communicator.unique_id() if self.rank == 0 else None]
+            self.dist.broadcast_object_list(box, src=0)
+            uid = box[0]
+        return Communicator(self.local_rank, self.rank, self.world, uid)
+
+    def all_gather(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([v], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+
+def solver_keys(args, precond, extra=None):
+    cfg = dict(solver="BICGSTAB", maxIters=args.max_iters, tolerance=args.tol, preconditioner=precond,
+               peerFusion=1 if args.comm == "peer-fused" else 0)
+    for kv in args.solver_key:
+        k, v = kv.split("=", 1)
+        cfg[k] = v
+    cfg.update(extra or {})
+    return cfg
+
+
+def make_cavity(job, comm, args, nx, ny, width, height, px, py, u_pc, p_pc, extra=None, mesh="quad"):
+    """Grid (one block per rank) + FractionalStep with the lid-driven-cavity boundary conditions."""
+    from phase_b200.api import Communicator, FiniteVolumeGrid2D, lid_driven_cavity
+    world = job.world
+    if mesh == "tri":
+        if world == 1:
+            grid = FiniteVolumeGrid2D.triangulated(comm, nx, ny, width, height)
+        else:                                                # generic path: global mesh on the host, RCB, local mesh
+            hostc = Communicator(Communicator.HOST_ONLY)
+            gg = FiniteVolumeGrid2D.triangulated(hostc, nx, ny, width, height)
+            grid = gg.local(gg.partition_rcb(world), comm)
+            gg.close()
+    elif world == 1:
+        grid = FiniteVolumeGrid2D.rectilinear(comm, nx, ny, width, height)
+    else:
+        grid = FiniteVolumeGrid2D.rectilinear_block(comm, nx, ny, width, height, px, py)
+    if world > 1 and args.comm.startswith("peer"):
+        comm.enable_peer_memory(grid, job.all_gather)
+    fs = lid_driven_cavity(grid, 1.0, 0.1, solver=solver_keys(args, u_pc, extra),
+                           pSolver=dict(preconditioner=p_pc) if p_pc != u_pc else None)
+    fs.setup(guessOrder=args.guess_order)
+    return grid, fs
+
+
+def timed_steps(job, comm, fs, dt, warmup, steps, sampler=None):
+    """W untimed + K timed steps, CUDA events on the library's stream, barrier + synchronize on both sides,
+    max over ranks."""
+    torch = job.torch
+    stream = torch.cuda.ExternalStream(comm.stream())
+    for _ in range(warmup):
+        fs.solve(dt)
+    job.barrier()
+    if sampler:
+        sampler.mark()
+    launches0 = comm.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record()
+    stats = [fs.solve(dt) for _ in range(steps)]
+    with torch.cuda.stream(stream):
+        e1.record()
+    job.barrier()
+    ms = job.max_over_ranks(e0.elapsed_time(e1))
+    return ms / steps, stats, comm.kernel_launches() - launches0
+
+
+def pressure_solve_record(job, comm, fs, peak):
+    """pEqn_ as assembled by the last step, solved from a zero guess: whole-solve algorithmic throughput =
+    iterations x bytes per iteration (2 SpMV + 2 preconditioner applies + vector passes)."""
+    torch = job.torch
+    stream = torch.cuda.ExternalStream(comm.stream())
+    fs.pEqn.solve(warmStart=False)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    job.barrier()
+    with torch.cuda.stream(stream):
+        e0.record()
+    fs.pEqn.solve(warmStart=False)
+    with torch.cuda.stream(stream):
+        e1.record()
+    job.barrier()
+    ms = job.max_over_ranks(e0.elapsed_time(e1))
+    its = fs.pEqn.solver.nIters()
+    _, b_iter = fs.pEqn.solver.bytes()
+    gbs = its * b_iter / (ms * 1e-3) / 1e9
+    return {"what": "pEqn_ of the last step solved from a zero guess, CUDA events around phb_eqn_solve (max over ranks)",
+            "iterations": its, "ms": ms, "ms_per_iteration": ms / max(1, its), "relres": fs.pEqn.solver.error(),
+            "algorithmic_bytes_per_iteration_per_gpu": b_iter, "achieved_GBps_per_gpu": gbs,
+            "frac_of_measured_peak": gbs / peak, "frac_of_8TBs_nominal": gbs / 8000.0}
+
+
+def mean(xs):
+    xs = list(xs)
+    return float(sum(xs)) / max(1, len(xs))
+
+
+def sub_record(job, args, u_pc, p_pc, extra, warmup, steps, what):
+    """The same 4M-cell workload under another algorithm choice (single GPU), device-resident, same timing rules."""
+    comm = job.communicator()
+    grid, fs = make_cavity(job, comm, args, args.n, args.n, 1.0, 1.0, 1, 1, u_pc, p_pc, extra)
+    dt = 0.5 / args.n
+    ms, stats, launches = timed_steps(job, comm, fs, dt, warmup, steps)
+    peak, _ = measured_peak()
+    rec = {"what": what, "value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup,
+           "iters_per_solve": {"uEqn": mean(s["itersU"] for s in stats), "pEqn": mean(s["itersP"] for s in stats)},
+           "relres_p": stats[-1]["errorP"], "gpu_launches": int(launches),
+           "pressure_solve": pressure_solve_record(job, comm, fs, peak)}
+    fs.close(); grid.close(); comm.close()
+    return rec
+
+
+def parity_record(job, args):
+    """A small cavity on the same communicator layout and default solver keys against the oracle's single-domain
+    direct solve (4 steps, rel-L2 of the owned cells; p minus its global mean).  N > 1: RCB partition, the
+    distributed multigrid hierarchy forced onto three levels, peer-memory exchanges."""
+    import numpy as np
+    import oracle as O
+    from phase_b200.api import Communicator, FiniteVolumeGrid2D as G, lid_driven_cavity
+    nx, ny, steps = 64, 48, 4
+    comm = job.communicator()
+    if job.world == 1:
+        gl = G.rectilinear(comm, nx, ny, 1.0, 1.0)
+    else:
+        host = Communicator(Communicator.HOST_ONLY)
+        g = G.rectilinear(host, nx, ny, 1.0, 1.0)
+        gl = g.local(g.partition_rcb(job.world), comm)
+        g.close()
+        if args.comm.startswith("peer"):
+            comm.enable_peer_memory(gl, job.all_gather)
+    amg = args.precond == "amg"
+    keys = dict(tolerance=1e-11, maxIters=50000, preconditioner=args.u_precond if amg else args.precond)
+    if amg:
+        keys.update(amgCoarsest=40, amgTailRows=200)
+    fs = lid_driven_cavity(gl, 1.0, 0.1, solver=keys, pSolver=dict(preconditioner="amg") if amg else None)
+    ofs = O.cavity(O.Mesh.rectilinear(nx, ny, 1.0, 1.0), 1.0, 0.1)
+    ofs.use_direct_solver()
+    dt = 0.5 / nx
+    for _ in range(steps):
+        st = fs.solve(dt)
+        ofs.step(dt)
+    owner, gid = gl.i32("owner"), gl.i32("globalId")
+    mine = owner == job.rank
+    u, p, po = fs.u.get("cells"), fs.p.get("cells"), ofs.view("p")
+    ou = (ofs.view("ux"), ofs.view("uy"))
+    num = sum(float(np.sum((u[k][mine] - ou[k][gid[mine]]) ** 2)) for k in (0, 1))
+    psum, cnt = job.sum_over_ranks([float(p[mine].sum()), float(mine.sum())])
+    pm = psum / cnt
+    nump = float(np.sum(((p[mine] - pm) - (po[gid[mine]] - po.mean())) ** 2))
+    num, nump = job.sum_over_ranks([num, nump])
+    eu = (num / float(np.sum(ou[0] ** 2) + np.sum(ou[1] ** 2))) ** 0.5
+    ep = (nump / float(np.sum((po - po.mean()) ** 2))) ** 0.5
+    rec = {"what": "%dx%d cavity, %d steps, %d rank(s)%s, fields against the oracle's single-domain direct solve"
+                   % (nx, ny, steps, job.world, ", RCB partition" if job.world > 1 else ""),
+           "relL2_u": eu, "relL2_p": ep, "tolerance": 1e-6, "ok": bool(eu < 1e-6 and ep < 1e-6),
+           "preconditioner": "amg (3+ levels, distributed)" if amg else args.precond,
+           "itersP_last": st["itersP"], "max_divergence": st["maxDivergence"]}
+    fs.close(); gl.close(); comm.close()
+    return rec
+
+
+def weak_record(job, args, peak):
+    """The series that ends in the north star's 64M-cell / 8-GPU point: 4000x2000 = 8M cells PER GPU (h = 1/4000
+    everywhere), cavity time steps and the zero-guess pressure solve.  Weak-scaling efficiency follows from the
+    N = 1 line's record of the same name."""
+    px, py = block_layout(job.world)
+    bx, by = args.weak_block
+    nx, ny = bx * px, by * py
+    comm = job.communicator()
+    t0 = time.perf_counter()
+    grid, fs = make_cavity(job, comm, args, nx, ny, float(px), float(py) * by / bx, px, py,
+                           args.u_precond if args.precond == "amg" else args.precond, args.precond)
+    dt = 0.5 / bx
+    t_setup = time.perf_counter() - t0
+    ms, stats, launches = timed_steps(job, comm, fs, dt, 2, args.weak_steps)
+    rec = {"what": "lid-driven cavity on %dx%d = %d cells, %dx%d blocks of %dx%d cells (one per GPU), dt = 0.5 h, same "
+                   "solver keys as the headline run" % (nx, ny, nx * ny, px, py, bx, by),
+           "global_cells": nx * ny, "cells_per_gpu": bx * by, "n_gpus": job.world,
+           "time_steps_per_s": 1e3 / ms, "ms_per_step": ms, "steps": args.weak_steps, "warmup": 2,
+           "cell_updates_per_s": nx * ny * 1e3 / ms,
+           "iters_per_solve": {"uEqn": mean(s["itersU"] for s in stats), "pEqn": mean(s["itersP"] for s in stats)},
+           "pressure_solve": pressure_solve_record(job, comm, fs, peak),
+           "host_setup_s": t_setup}
+    if args.precond == "amg":
+        rec["amg"] = fs.pEqn.solver.amgInfo()
+    fs.close(); grid.close(); comm.close()
+    return rec
+
+
+def e2e_record(job, comm, fs, dt, steps, sizes, weak):
+    """The same step through the public API with HOST state in pinned memory: per step H2D of the state a time step
+    starts from (u cells + faces, p cells; grad p and the boundary faces of p follow from p on the device), the
+    step, D2H of the same arrays -- a serial chain, since a host-owned state feeds every step with the previous
+    step's output."""
+    torch = job.torch
+    N, F = sizes["nCells"], sizes["nFaces"]
+    host = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k, n in (("uc", 2 * N), ("uf", 2 * F), ("pc", N))}
+    parts = {"uc": (fs.u, "cells"), "uf": (fs.u, "faces"), "pc": (fs.p, "cells")}
+    for k, (fld, part) in parts.items():
+        host[k].numpy()[:] = fld.get(part).reshape(-1)
+    nbytes = sum(v.numel() for v in host.values()) * 8
+    job.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for k, (fld, part) in parts.items():
+            fld.set(part, host[k].numpy())
+        fs.p.sendMessages(); fs.p.setBoundaryFaces(); fs.computeGradP()
+        fs.solve(dt)
+        for k, (fld, part) in parts.items():
+            fld.get(part, out=host[k].numpy())
+    job.barrier()
+    s = job.max_over_ranks((time.perf_counter() - t0) / steps)
+    return {"value": (job.world if weak else 1) / s, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+            "steps": steps, "ms_per_step": 1e3 * s,
+            "what": "pinned host state (u cells + faces, p cells) copied in, grad p rebuilt, FractionalStep.solve, the same "
+                    "arrays copied out, every step; wall clock, max over ranks"}
+
+
+def seam1_record(comm, fs, dt, args):
+    """Seam 1 alone (single GPU): the reference-facing backend call with HOST CSR arrays, exactly what
+    FiniteVolumeEquation<T>::solve hands to a SparseMatrixSolver: set(rowPtr,colInd,vals) + setRhs(-rhs_) + solve + x."""
+    from phase_b200.api import SparseMatrixSolver
+    rp, ci, va, rhs = fs.assembleP(dt).export(1)      # reference layout: ELL-5 padded, nb before diagonal
+    b = -rhs
+    s1 = SparseMatrixSolver(comm).setup(solver_keys(args, args.precond))
+    s1.setup(dict(nullSpace="constant"))
+    s1.setRank(len(b)); s1.set(rp, ci, va); s1.setRhs(b); s1.solve()   # warm-up: pattern analysis, graph capture
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        s1.setRank(len(b)); s1.set(rp, ci, va); s1.setRhs(b); s1.solve(); xs = s1.x()
+        ts.append(time.perf_counter() - t0)
+    rec = {"what": "pEqn_ (%d rows, %d padded entries) through set(rowPtr,colInd,vals)+setRhs+solve+x with host arrays "
+                   "(pageable, as a std::vector is); best of 3" % (len(b), len(ci)),
+           "seconds_per_solve": min(ts), "iterations": s1.nIters(), "relres": s1.error(),
+           "h2d_bytes": int(rp.nbytes + ci.nbytes + va.nbytes + b.nbytes), "d2h_bytes": int(xs.nbytes)}
+    s1.close()
+    return rec
+
+
+def committed_traffic(name, rows):
+    """DRAM bytes per launch from the committed `ncu --set full` capture -- only when it was taken on this size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            d = json.load(f)
+        return d.get("dram_bytes_per_launch") if int(d.get("rows", -1)) == int(rows) else None
+    except Exception:
+        return None
+
+
+def roofline_records(fs, peak, peak_src, ms_per_step, iters_u, iters_p, world, amg, nrows):
+    """Live timing of the dominant kernels on the resident pEqn_ system (CUDA events on the library's stream)."""
+    spmv_ms = fs.pEqn.solver.time_spmv(50)
+    b_spmv, _ = fs.pEqn.solver.bytes()
+    ach = b_spmv / (spmv_ms * 1e-3) / 1e9
+    spmv = {"bound": "hbm", "kernel": "k_spmv<1,0> (fp64 sliced-ELL SpMV of the BiCGStab loop, pEqn_, %d rows per GPU)" % nrows,
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "frac_of_8TBs_nominal": ach / 8000.0,
+            "traffic": committed_traffic("spmv_traffic.json", nrows) if world == 1 else None,
+            "algorithmic_bytes_per_launch": b_spmv, "ms_per_launch": spmv_ms, "peak_source": peak_src,
+            "bytes_formula": "12 nnz + 4 (n+1) + 16 n  (SURVEY 8d)",
+            "share_of_step": 2.0 * iters_p * spmv_ms / ms_per_step}
+    if not amg or world > 1:
+        return spmv, None
+    try:
+        ta = fs.pEqn.solver.timeAmg(20)
+    except Exception as exc:           # keep the line (SpMV roofline) rather than lose the run
+        print("bench: timeAmg failed: %s" % exc, file=sys.stderr)
+        return spmv, None
+    aj = ta["bytesJacobi"] / (ta["msJacobi"] * 1e-3) / 1e9
+    cyc = ta["bytesCycle"] / (ta["msCycle"] * 1e-3) / 1e9
+    roof = {"bound": "hbm",
+            "kernel": "k_amg_spmv<MODE 2> (damped-Jacobi sweep on multigrid level 0 of pEqn_, %d rows, single-precision "
+                      "matrix, fp64 Krylov vectors in and out): the largest launch of the V-cycle" % nrows,
+            "achieved": aj, "peak": peak, "unit": "GB/s", "frac": aj / peak, "frac_of_8TBs_nominal": aj / 8000.0,
+            "traffic": committed_traffic("amg_traffic.json", nrows),
+            "algorithmic_bytes_per_launch": ta["bytesJacobi"], "ms_per_launch": ta["msJacobi"], "peak_source": peak_src,
+            "bytes_formula": "8 nnz + 4 (n/32+1) [slice offsets] + 4 n [w] + 4 n [x, once] + 8 n [b] + 8 n [y]",
+            "share_of_step": 2.0 * iters_p * ta["msJacobi"] / ms_per_step,
+            "level0_ms": {"residual": ta["msResidual"], "restriction": ta["msRestriction"],
+                          "prolongation": ta["msProlongation"], "jacobi": ta["msJacobi"]},
+            "cycle": {"ms": ta["msCycle"], "launches": ta["launchesPerCycle"], "algorithmic_bytes": ta["bytesCycle"],
+                      "achieved_GBps": cyc, "frac_of_measured_peak": cyc / peak,
+                      "share_of_step_pEqn": 2.0 * iters_p * ta["msCycle"] / ms_per_step}}
+    return spmv, roof
 
 
 def main():
@@ -236,13 +516,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--side", dest="n", type=int, default=2000, help="cells per side per GPU (2000 -> 4M cells)")
+    ap.add_argument("--side", dest="n", type=int, default=2000, help="cells per side (2000 -> 4M cells)")
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--max-iters", type=int, default=20000)
     ap.add_argument("--precond", default="amg", choices=["ilu0", "jacobi", "none", "amg"],
                     help="amg = smoothed-aggregation V-cycle on pEqn_; uEqn_ per --u-precond")
     ap.add_argument("--u-precond", default="amg", choices=["ilu0", "amg"], help="uEqn_ preconditioner when --precond amg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sub", action="store_true", help="skip the ilu0 / amg_double sub-records (N = 1)")
+    ap.add_argument("--no-weak", action="store_true", help="skip the 8M-cells-per-GPU record")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-line parity check")
+    ap.add_argument("--weak-block", type=int, nargs=2, default=[4000, 2000], metavar=("BX", "BY"))
+    ap.add_argument("--weak-steps", type=int, default=5)
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="reference arm: wall budget of the timed steps, s")
     ap.add_argument("--solver-key", action="append", default=[], metavar="KEY=VALUE",
                     help="extra LinearAlgebra key for both equations (e.g. amgPrecision=double, amgSweeps=2)")
     ap.add_argument("--mesh", default="quad", choices=["quad", "tri"],
@@ -257,260 +543,120 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    import math
     import numpy as np
-    import torch
-    from phase_b200.api import Communicator, FiniteVolumeGrid2D, lid_driven_cavity
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    uid = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        box = [Communicator.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        uid = box[0]
-    comm = Communicator(local_rank, rank, world, uid)
+    job = Job()
+    rank, world = job.rank, job.world
+    comm = job.communicator()
     px, py = block_layout(world)
-    if args.scaling == "weak":
+    weak = args.scaling == "weak"
+    amg = args.precond == "amg"
+    u_pc = args.u_precond if amg else args.precond
+    if args.mesh == "tri":
+        nx = ny = int(round(args.n / math.sqrt(2.0)))        # 2 tn^2 triangles ~ side^2 cells
+        width = height = 1.0
+        dt = 0.25 / nx                                       # triangles: half the lattice spacing
+    elif weak:
         nx, ny, width, height = args.n * px, args.n * py, float(px), float(py)
+        dt = 0.5 / args.n                                    # same cell size h = 1/side in every block
     else:
         nx, ny, width, height = args.n, args.n, 1.0, 1.0
-    if args.mesh == "tri":
-        import math
-        tn = int(round(args.n / math.sqrt(2.0)))            # 2 tn^2 triangles ~ side^2 cells
-        if world == 1:
-            grid = FiniteVolumeGrid2D.triangulated(comm, tn, tn, 1.0, 1.0)
-        else:                                                # generic path: global mesh on the host, RCB, local mesh
-            hostc = Communicator(Communicator.HOST_ONLY)
-            gg = FiniteVolumeGrid2D.triangulated(hostc, tn, tn, 1.0, 1.0)
-            grid = gg.local(gg.partition_rcb(world), comm)
-            gg.close()
-        nx = ny = tn
-    elif world == 1:
-        grid = FiniteVolumeGrid2D.rectilinear(comm, nx, ny, 1.0, 1.0)
-    else:
-        grid = FiniteVolumeGrid2D.rectilinear_block(comm, nx, ny, width, height, px, py)
-    if world > 1 and args.comm.startswith("peer"):
-        def all_gather(obj):
-            out = [None] * world
-            dist.all_gather_object(out, obj)
-            return out
-        comm.enable_peer_memory(grid, all_gather)
-    amg = args.precond == "amg"
-    cfg = dict(solver="BICGSTAB", maxIters=args.max_iters, tolerance=args.tol,
-               preconditioner=args.u_precond if amg else args.precond, peerFusion=1 if args.comm == "peer-fused" else 0)
-    for kv in args.solver_key:
-        k, v = kv.split("=", 1)
-        cfg[k] = v
-    fs = lid_driven_cavity(grid, 1.0, 0.1, solver=cfg, pSolver=dict(preconditioner="amg") if amg else None)
-    fs.setup(guessOrder=args.guess_order)
-    dt = 0.5 / nx                                            # maxCo 0.5 with the unit lid speed, h = 1/nx
-    if args.scaling == "weak" and args.mesh == "quad":
-        dt = 0.5 / args.n                                     # same cell size h = 1/side in every block
-    if args.mesh == "tri":
-        dt = 0.25 / nx                                        # triangles: half the lattice spacing
-    stream = torch.cuda.ExternalStream(comm.stream())
+        dt = 0.5 / nx                                        # maxCo 0.5 with the unit lid speed, h = 1/nx
+    grid, fs = make_cavity(job, comm, args, nx, ny, width, height, px, py, u_pc, args.precond, mesh=args.mesh)
     sizes = grid.sizes()
-    N, F = sizes["nCells"], sizes["nFaces"]
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(job.local_rank)
     if rank == 0:
         sampler.start()                    # before the warm-up, so that it is sampling when the timed region starts
-    stats = []
-    for _ in range(args.warmup):
-        stats.append(fs.solve(dt))
-    barrier()
-    sampler.mark()
-    launches0 = comm.kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        e0.record()
-    timed = []
-    for _ in range(args.steps):
-        timed.append(fs.solve(dt))
-    with torch.cuda.stream(stream):
-        e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = comm.kernel_launches() - launches0
+    ms_per_step, timed, launches = timed_steps(job, comm, fs, dt, args.warmup, args.steps, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
     steps_per_s = 1e3 / ms_per_step
-    # strong scaling: the job advances ONE side x side problem, value = its time steps per second.
-    # weak scaling: every rank advances a side x side block, so the job processes `world` such
-    # block-steps per step (aggregate; equals time-steps/s at N = 1)
-    value = steps_per_s * (world if args.scaling == "weak" else 1)
-
-    # ---- dominant kernel: the SpMV inside BiCGStab, timed alone on the resident pEqn matrix
-    spmv_ms = fs.pEqn.solver.time_spmv(50)
-    b_spmv, b_iter = fs.pEqn.solver.bytes()
+    # strong scaling: the job advances ONE problem, value = its time steps per second.  weak scaling: every rank
+    # advances a side x side block, the job processes `world` such block-steps per step
+    value = steps_per_s * (world if weak else 1)
+    iters_u, iters_p = mean(s["itersU"] for s in timed), mean(s["itersP"] for s in timed)
     peak, peak_src = measured_peak()
-    achieved = b_spmv / (spmv_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "spmv_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    spmv_roof, amg_roof = roofline_records(fs, peak, peak_src, ms_per_step, iters_u, iters_p, world, amg, sizes["nLocal"])
+    pressure = pressure_solve_record(job, comm, fs, peak)
+    amg_info = None
+    if amg:
+        amg_info = fs.pEqn.solver.amgInfo()
+        amg_info["uEqn"] = fs.uEqn.solver.amgInfo() if u_pc == "amg" else u_pc
+        amg_info["note"] = ("hierarchy built in the first (warm-up) solve and reused: pEqn_ = laplacian(dt, p) is constant up to "
+                            "the scalar dt; setupMs is that one-off cost, outside the timed steps")
+    e2e = e2e_record(job, comm, fs, dt, max(1, min(args.steps, 3)), sizes, weak)
+    seam1 = seam1_record(comm, fs, dt, args) if world == 1 else None
+    state = None
+    if world == 1 and rank == 0 and not args.no_cpu and args.mesh == "quad":
+        u, uf, g = fs.u.get("cells"), fs.u.get("faces"), fs.gradP.get("cells")
+        state = {"ux": u[0].copy(), "uy": u[1].copy(), "ufx": uf[0].copy(), "ufy": uf[1].copy(), "p": fs.p.get("cells").copy(),
+                 "pf": fs.p.get("faces").copy(), "gpx": g[0].copy(), "gpy": g[1].copy()}
+    nlocal = sizes["nLocal"]
+    fs.close(); grid.close(); comm.close()
 
-    # ---- with the multigrid preconditioner the V-cycle, not the Krylov SpMV, is where the step's time goes: time its
-    # level-0 kernels and one whole cycle live on the resident pEqn_ hierarchy
-    amg_roof, ta = None, None
-    if amg and world == 1:
+    extra = {}
+    if world == 1 and not args.no_sub and amg:
+        extra["ilu0"] = sub_record(job, args, "ilu0", "ilu0", None, 2, 3,
+                                   "like for like with the CPU arm: multicolour ILU(0) (the preconditioner family north_star names) "
+                                   "on both equations, everything else as the headline run")
+        extra["amg_double"] = sub_record(job, args, "amg", "amg", dict(amgPrecision="double"), 3, 10,
+                                         "the headline algorithm with the V-cycle in fp64 (no single-precision arithmetic anywhere)")
+    if not args.no_parity:
+        extra["parity"] = parity_record(job, args)
+    if not args.no_weak and args.mesh == "quad":
         try:
-            ta = fs.pEqn.solver.timeAmg(20)
-        except Exception as exc:           # keep the line (SpMV roofline) rather than lose the run
-            print("bench: timeAmg failed: %s" % exc, file=sys.stderr)
-    if ta:
-        atraffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "amg_traffic.json")) as f:
-                atraffic = json.load(f).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-        aj = ta["bytesJacobi"] / (ta["msJacobi"] * 1e-3) / 1e9
-        amg_roof = {"bound": "hbm",
-                    "kernel": "k_amg_spmv<MODE 2> (damped-Jacobi sweep on multigrid level 0 of pEqn_, 4M rows, single-precision "
-                              "matrix, fp64 Krylov vectors): the largest launch of the V-cycle that dominates the step",
-                    "achieved": aj, "peak": peak, "unit": "GB/s", "frac": aj / peak, "frac_of_8TBs_nominal": aj / 8000.0,
-                    "traffic": atraffic, "algorithmic_bytes_per_launch": ta["bytesJacobi"], "ms_per_launch": ta["msJacobi"],
-                    "peak_source": peak_src,
-                    "level0_ms": {"residual": ta["msResidual"], "restriction": ta["msRestriction"],
-                                  "prolongation": ta["msProlongation"], "jacobi": ta["msJacobi"]},
-                    "cycle": {"ms": ta["msCycle"], "launches": ta["launchesPerCycle"], "algorithmic_bytes": ta["bytesCycle"],
-                              "achieved_GBps": ta["bytesCycle"] / (ta["msCycle"] * 1e-3) / 1e9,
-                              "frac_of_measured_peak": ta["bytesCycle"] / (ta["msCycle"] * 1e-3) / 1e9 / peak}}
-
-    # ---- the pressure solve alone (pEqn_ as assembled by the last step, zero initial guess): whole-solve
-    # algorithmic throughput = iterations x bytes per iteration (2 SpMV + 2 preconditioner applies + vector passes)
-    fs.pEqn.solve(warmStart=False)
-    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.cuda.stream(stream):
-        pe0.record()
-    fs.pEqn.solve(warmStart=False)
-    with torch.cuda.stream(stream):
-        pe1.record()
-    barrier()
-    p_ms, p_its = pe0.elapsed_time(pe1), fs.pEqn.solver.nIters()
-    pressure_solve = {"what": "pEqn_ of the last step solved from a zero guess, CUDA events around phb_eqn_solve",
-                      "iterations": p_its, "ms": p_ms, "relres": fs.pEqn.solver.error(),
-                      "algorithmic_bytes_per_iteration": b_iter,
-                      "achieved_GBps_per_gpu": p_its * b_iter / (p_ms * 1e-3) / 1e9,
-                      "frac_of_measured_peak": p_its * b_iter / (p_ms * 1e-3) / 1e9 / peak}
-
-    # ---- e2e: the same step through the public API with HOST state in pinned memory:
-    # H2D of the step's input state, the step, D2H of the resulting u and p
-    host = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k, n in
-            (("uc", 2 * N), ("uf", 2 * F), ("pc", N), ("pf", F), ("gc", 2 * N))}
-    for k, (fld, part) in {"uc": (fs.u, "cells"), "uf": (fs.u, "faces"), "pc": (fs.p, "cells"),
-                           "pf": (fs.p, "faces"), "gc": (fs.gradP, "cells")}.items():
-        host[k].numpy()[:] = fld.get(part).reshape(-1)
-    h2d = sum(v.numel() for v in host.values()) * 8
-    d2h = (2 * N + N) * 8
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 2))
-    for _ in range(e2e_steps):
-        fs.u.set("cells", host["uc"].numpy()); fs.u.set("faces", host["uf"].numpy())
-        fs.p.set("cells", host["pc"].numpy()); fs.p.set("faces", host["pf"].numpy())
-        fs.gradP.set("cells", host["gc"].numpy())
-        st = fs.solve(dt)
-        fs.u.get("cells", out=host["uc"].numpy()); fs.p.get("cells", out=host["pc"].numpy())
-        fs.u.get("faces", out=host["uf"].numpy()); fs.p.get("faces", out=host["pf"].numpy())
-        fs.gradP.get("cells", out=host["gc"].numpy())
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    d2h_all = (2 * N + N + 2 * F + F + 2 * N) * 8
-
-    # ---- Seam 1 alone (single GPU): the reference-facing backend call with HOST CSR arrays, exactly what
-    # FiniteVolumeEquation<T>::solve hands to a SparseMatrixSolver: set(rowPtr,colInd,vals) + setRhs(-rhs_) + solve + x
-    seam1 = None
-    if world == 1:
-        from phase_b200.api import SparseMatrixSolver
-        rp, ci, va, rhs = fs.assembleP(dt).export(1)      # reference layout: ELL-5 padded, nb before diagonal
-        b = -rhs
-        s1 = SparseMatrixSolver(comm).setup(cfg)
-        s1.setup(dict(nullSpace="constant", preconditioner=args.precond))
-        s1.setRank(len(b)); s1.set(rp, ci, va); s1.setRhs(b); s1.solve()   # warm-up: pattern analysis, graph capture
-        t0 = time.perf_counter()
-        s1.setRank(len(b)); s1.set(rp, ci, va); s1.setRhs(b); s1.solve(); xs = s1.x()
-        t_s1 = time.perf_counter() - t0
-        seam1 = {"what": "pEqn_ (4M rows, 20M padded entries) through set(rowPtr,colInd,vals)+setRhs+solve+x with host arrays",
-                 "seconds_per_solve": t_s1, "iterations": s1.nIters(), "relres": s1.error(),
-                 "h2d_bytes": int(rp.nbytes + ci.nbytes + va.nbytes + b.nbytes), "d2h_bytes": int(xs.nbytes)}
-        s1.close()
+            extra["weak_8M_per_gpu"] = weak_record(job, args, peak)
+        except Exception as exc:
+            extra["weak_8M_per_gpu"] = {"error": str(exc)}
 
     if rank != 0:
-        fs.close(); grid.close(); comm.close()
-        dist.destroy_process_group()
+        if job.dist:
+            job.dist.destroy_process_group()
         return
-    iters_u = float(np.mean([s["itersU"] for s in timed]))
-    iters_p = float(np.mean([s["itersP"] for s in timed]))
+    single = not any(kv.startswith("amgPrecision=double") for kv in args.solver_key)
+    algorithm = {"preconditioner": ("smoothed-aggregation AMG V(1,1), damped Jacobi, on pEqn_; %s on uEqn_" % u_pc) if amg else args.precond,
+                 "precision": ("fp64 assembly, Krylov recurrences, residual test and true-residual recheck; %s multigrid cycle"
+                               % ("fp32" if single else "fp64")) if amg else "fp64 throughout",
+                 "n_gpus": world, "cells_per_gpu": nlocal,
+                 "partition": "none" if world == 1 else ("RCB, %d parts" % world if args.mesh == "tri" else
+                                                         "%dx%d blocks of %dx%d cells" % (px, py, nx // px, ny // py)),
+                 "comm": "single GPU" if world == 1 else (
+                     "NVLink peer-memory kernels inside the Krylov loop (halo + all-reduce one-CTA kernels in the CUDA graph); "
+                     "NCCL outside the loop" if args.comm == "peer" else
+                     "NVLink peer memory, halo push/wait and the sigma all-reduce inside the compute kernels"
+                     if args.comm == "peer-fused" else "NCCL send/recv + all-reduce"),
+                 "departure_from_north_star": "north_star names level-scheduled ILU(0)/Jacobi; AMG is this backend's MueLu-role "
+                                              "preconditioner (M/TrilinosMueluSparseMatrixSolver.cpp:27-32); the ILU(0) run of the "
+                                              "same workload is the `ilu0` record" if amg else None}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
-            "value_definition": ("time steps per second of the %dx%d-cell problem (split over the GPUs)" % (nx, ny)) if args.scaling == "strong"
-            else "4M-cell block time-steps per second summed over GPUs = n_gpus x (time steps of the global problem per second)",
+            "vs_baseline": None,
+            "dtype": ("f64 (assembly, BiCGStab, residuals) + f32 (multigrid preconditioner cycle)" if amg and single else "f64"),
+            "data": "synthetic", "config": workload_config(args), "algorithm": algorithm,
+            "value_definition": "block time-steps per second summed over GPUs = n_gpus x (time steps of the global problem per second)"
+            if weak else "time steps per second of the %dx%d problem (split over the GPUs)" % (nx, ny),
             "global_time_steps_per_s": steps_per_s,
-            "cell_updates_per_s": steps_per_s * sizes["nLocal"] * world,
-            "ms_per_bicgstab_iteration": ms_per_step / max(1.0, float(np.mean([s["itersP"] + s["itersU"] for s in timed]))),
+            "cell_updates_per_s": steps_per_s * nlocal * world,
+            "ms_per_bicgstab_iteration": ms_per_step / max(1.0, iters_p + iters_u),
             "iters_per_solve": {"uEqn": iters_u, "pEqn": iters_p,
                                 "relres_p": timed[-1]["errorP"], "relres_u": timed[-1]["errorU"]},
             "max_divergence": timed[-1]["maxDivergence"], "max_courant": timed[-1]["maxCourant"],
-            "roofline_spmv" if amg_roof else "roofline":
-                        {"bound": "hbm", "kernel": "k_spmv (fp64 sliced-ELL SpMV inside BiCGStab, pEqn_ 4M rows)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "frac_of_8TBs_nominal": achieved / 8000.0, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": b_spmv, "ms_per_launch": spmv_ms, "peak_source": peak_src},
-            "pressure_solve": pressure_solve,
-            "bicgstab": {"bytes_per_iteration": b_iter,
-                         "note": "whole-solve GB/s = iters * bytes_per_iteration / solve time; see profiles/"},
-            "e2e": {"value": (world if args.scaling == "weak" else 1) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_all,
-                    "what": "host state (u, p, gradP cells+faces) copied in, FractionalStep.solve, state copied out, per step"},
-            "e2e_seam1": seam1, "gpu_launches": int(launches), "clocks": clocks}
+            "roofline": amg_roof or spmv_roof, "pressure_solve": pressure,
+            "e2e": e2e, "e2e_seam1": seam1, "gpu_launches": int(launches), "clocks": clocks}
     if amg_roof:
-        amg_roof["share_of_step"] = {"pEqn_cycles": 2.0 * iters_p * amg_roof["cycle"]["ms"] / ms_per_step,
-                                     "note": "2 cycles per BiCGStab iteration; uEqn_ runs the two-component variant of the same kernels"}
-        line["roofline"] = amg_roof
-    if amg:
-        line["amg"] = fs.pEqn.solver.amgInfo()
-        line["amg"]["uEqn"] = fs.uEqn.solver.amgInfo() if args.u_precond == "amg" else "ilu0"
-        line["amg"]["note"] = ("hierarchy built on the host in the first (warm-up) solve and reused: pEqn_ = laplacian(dt, p) "
-                               "is constant up to the scalar dt; setupMs is that one-off cost, outside the timed steps")
-    if not args.no_cpu and world == 1:
-        # the CPU arm runs the reference's algorithm (BiCGStab + ILU(0)); with AMG on the GPU arm its bounded
-        # sample is scaled by the ILU(0) iteration counts measured for this workload (profiles/iters_4M.json)
-        cpc = "ilu0" if amg else args.precond
-        ciu, cip, csrc = (typical_iters("ilu0") if amg else (iters_u, iters_p, "this run"))
-        v, detail = cpu_reference_sample(args.n, args.n, 0.5 / args.n, ciu, cip, precond=cpc)
-        import oracle as O
-        cores = O.lib().or_num_threads()
+        line["roofline_spmv"] = spmv_roof
+    if amg_info:
+        line["amg"] = amg_info
+    line.update(extra)
+    if state is not None:
+        # one fully converged CPU step of the reference algorithm from the state the B200 arm ended in
+        v, cores, detail = cpu_converged_steps(args.n, args.n, dt, args.tol, args.max_iters, 0, 1, 1e9, state=state)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "1 assembled 4M-cell step + 12/24 BiCGStab(%s) iterations per solve on %d "
-                                          "OpenMP threads, scaled to %.0f/%.0f iterations per solve (%s)" %
-                                          (cpc, cores, ciu, cip, csrc), "detail": detail}
+                                "sample": "1 fully converged time step (BiCGStab + ILU(0), tolerance %g) continuing from the state the "
+                                          "B200 arm ended in (warm-up + timed + end-to-end steps); wall clock, nothing extrapolated"
+                                          % args.tol, "detail": detail}
     print(json.dumps(line), flush=True)
-    fs.close(); grid.close(); comm.close()
-    if world > 1:
-        dist.destroy_process_group()
+    if job.dist:
+        job.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -112,8 +112,15 @@ def lib():
         L.or_bicgstab_blocks.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
                                          C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int,
                                          C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.or_set_num_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
+
+
+def set_num_threads(n=None):
+    """OpenMP threads of the oracle's solver (default: every host core, whatever OMP_NUM_THREADS the launcher
+    exported).  Returns the count in effect."""
+    return lib().or_set_num_threads(int(n or os.cpu_count() or 1))
 
 
 def ref_lib():
@@ -308,22 +315,55 @@ def csr_to_scipy(rp, ci, va, n=None):
     return sp.csr_matrix((va[keep], (rows[keep], ci[keep])), shape=(len(rp) - 1, n))
 
 
+_lu_cache = {}
+
+
+def _factor(A, key):
+    """splu with the minimum-degree ordering of A^T + A (the matrices here are structurally symmetric; the default
+    COLAMD ordering needs 30x longer on a 1M-row 5-point system); the last few factorisations are kept, keyed on
+    the matrix values, because uEqn_ and pEqn_ of the fractional step do not change between time steps."""
+    import scipy.sparse.linalg as spl
+    lu = _lu_cache.get(key)
+    if lu is None:
+        if len(_lu_cache) >= 4:
+            _lu_cache.pop(next(iter(_lu_cache)))
+        lu = _lu_cache[key] = spl.splu(A.tocsc(), permc_spec="MMD_AT_PLUS_A")
+    return lu
+
+
 def direct_solve(rp, ci, va, b):
     """Exact sparse LU (SuperLU): stand-in for the snapshot's Eigen SparseLU
     (M/EigenSparseMatrixSolver.cpp:60-64).  Singular all-Neumann systems are
-    regularised by pinning the constant mode (hard part 3)."""
+    regularised by pinning the constant mode (hard part 3): bordered system [A 1; 1^T 0]
+    (zero-mean solution) for small systems, first unknown pinned to zero for large ones (a dense border row
+    defeats the fill-reducing ordering) -- callers compare such fields minus their mean.
+    A vector system [x-block | y-block] whose two diagonal blocks are identical and uncoupled (every equation
+    here without SYMMETRY / PARTIAL_SLIP patches) is factorised once."""
     import scipy.sparse as sp
     import scipy.sparse.linalg as spl
-    A = csr_to_scipy(rp, ci, va).tocsc()
+    A = csr_to_scipy(rp, ci, va).tocsr()
     n = A.shape[0]
+    key = (n, A.nnz, hash(A.data.tobytes()), hash(A.indices.tobytes()))
+    if n % 2 == 0 and n >= 20000:
+        h = n // 2
+        Axx, Ayy = A[:h, :h], A[h:, h:]
+        if Axx.nnz + Ayy.nnz == A.nnz and Axx.nnz == Ayy.nnz and np.array_equal(Axx.indices, Ayy.indices) \
+                and np.array_equal(Axx.data, Ayy.data):
+            lu = _factor(Axx, key)
+            return np.concatenate([lu.solve(b[:h]), lu.solve(b[h:])])
     rs = np.abs(A @ np.ones(n)).max()
     if rs < 1e-12 * np.abs(A.diagonal()).max():
+        if n >= 50000:
+            lu = _factor(A[1:, 1:], key)
+            return np.concatenate([[0.0], lu.solve(b[1:] - b.mean())])
         # constant null space: bordered system  [A 1; 1^T 0]
         one = sp.csc_matrix(np.ones((n, 1)))
         K = sp.bmat([[A, one], [one.T, None]], format="csc")
         x = spl.splu(K).solve(np.concatenate([b, [0.0]]))
         return x[:n]
-    return spl.splu(A).solve(b)
+    if n >= 20000:
+        return _factor(A, key).solve(b)
+    return spl.splu(A.tocsc()).solve(b)
 
 
 class FracStep:
@@ -352,6 +392,53 @@ class FracStep:
             x_ = np.ctypeslib.as_array(x, (n,))
             x_[:] = direct_solve(rp_, ci_, va_, b_)
             return 1
+        self._cb = SOLVE_CB(cb)
+        lib().or_fs_set_solver(self.h, self._cb, None)
+
+    def use_ilu0_solver(self, tol=1e-8, max_iters=20000, null_space=True, guesses=None):
+        """Every solve of step() = right-preconditioned BiCGStab + ILU(0) (the Belos/Ifpack2 RILUK(0) role,
+        M/TrilinosBelosSparseMatrixSolver.cpp:52-83) in the multicolour ordering, OpenMP over the rows of a colour,
+        converged to `tol` on ||r||/||b||, warm-started from the equation's previous solution as the Tpetra
+        solution vector of the reference backend is (M/TrilinosSparseMatrixSolver.cpp).  The permutation is
+        cached per pattern.  `guesses` = {rows: x0} seeds the first solve of an equation (a state taken over from
+        elsewhere).  self.solve_log collects (rows, iterations, relres, seconds) per solve."""
+        import time
+        cache, self.solve_log = {}, []
+        guesses = dict(guesses or {})
+
+        def cb(n, rp, ci, va, b, x, user):
+            t0 = time.perf_counter()
+            rp_ = np.ctypeslib.as_array(rp, (n + 1,))
+            nnz = int(rp_[n])
+            ci_ = np.ctypeslib.as_array(ci, (nnz,))
+            va_ = np.ctypeslib.as_array(va, (nnz,))
+            b_ = np.ctypeslib.as_array(b, (n,))
+            x_ = np.ctypeslib.as_array(x, (n,))
+            c = cache.get(n)
+            if c is None or c["nnz"] != nnz or not np.array_equal(c["ci"], ci_):
+                rp2, ci2, _, new2old, bp = multicolor_permute(rp_, ci_, va_)
+                rows = np.repeat(np.arange(n, dtype=np.int32), np.diff(rp_))
+                keep = np.flatnonzero(ci_ >= 0)
+                old2new = np.empty(n, np.int32)
+                old2new[new2old] = np.arange(n, dtype=np.int32)
+                order = np.argsort(old2new[rows[keep]], kind="stable")
+                c = cache[n] = dict(nnz=nnz, ci=ci_.copy(), rp2=rp2, ci2=ci2, new2old=new2old, bp=bp,
+                                    src=np.ascontiguousarray(keep[order]), x=np.zeros(n))
+                if n in guesses:
+                    c["x"] = np.ascontiguousarray(np.asarray(guesses.pop(n), np.float64)[new2old])
+            va2 = np.ascontiguousarray(va_[c["src"]])
+            b2 = np.ascontiguousarray(b_[c["new2old"]])
+            if null_space:
+                rs = np.abs(np.add.reduceat(np.where(ci_ >= 0, va_, 0.0), rp_[:-1])).max()
+                if rs < 1e-12 * np.abs(va_).max():
+                    b2 -= b2.mean()                # all-Neumann pressure: compatible right-hand side
+            x2 = c["x"]
+            rr = C.c_double()
+            it = lib().or_bicgstab_blocks(n, _ip(c["rp2"]), _ip(c["ci2"]), _dp(va2), _dp(b2), _dp(x2), tol, max_iters,
+                                          len(c["bp"]) - 1, _ip(c["bp"]), C.byref(rr))
+            x_[c["new2old"]] = x2
+            self.solve_log.append((n, it, rr.value, time.perf_counter() - t0))
+            return it
         self._cb = SOLVE_CB(cb)
         lib().or_fs_set_solver(self.h, self._cb, None)
 

@@ -1572,6 +1572,16 @@ int or_num_threads(void) {
   return 1;
 #endif
 }
+/* launchers such as torch.distributed.run export OMP_NUM_THREADS=1: the timed CPU arm sets its thread count itself */
+int or_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
 
 static void spmv(int n, const int *rp, const int *ci, const double *v,
                  const double *x, double *y) {

@@ -134,6 +134,7 @@ int or_bicgstab_blocks(int n, const int *rowPtr, const int *colInd, const double
                        const double *b, double *x, double tol, int maxIters,
                        int nBlocks, const int *blockPtr, double *relres);
 int or_num_threads(void);
+int or_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -506,6 +506,11 @@ class FractionalStep:
         return dict(itersU=int(st[0]), itersP=int(st[1]), errorU=st[2], errorP=st[3],
                     maxDivergence=st[4], maxCourant=st[5])
 
+    def computeGradP(self):
+        """gradP_.compute (UF/ScalarGradient.cpp:34-74) from the current p: what a step leaves behind, rebuilt after p
+        has been replaced from the host."""
+        check(self.L.phb_field_gradient(self.p.h, self.gradP.h))
+
     def computeMaxTimeStep(self, maxCo, prevDt, maxDt):
         out = C.c_double()
         check(self.L.phb_fs_max_time_step(self.h, maxCo, prevDt, maxDt, C.byref(out)))

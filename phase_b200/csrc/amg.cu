@@ -1384,22 +1384,23 @@ int amg_launches_per_apply(const phb_solver *s) {
   return (L - 1) * perLevel + (D.denseCoarse ? 1 : 1 + kCoarseSweeps) + packs;
 }
 
-// algorithmic bytes of one cycle: every matrix streamed once per use (index + value per entry, 4 B per row
-// pointer), vectors read or written once per use; v = bytes of a cycle scalar (4 single, 8 double), the
-// Krylov vectors touched on level 0 (b, result) are fp64
+// algorithmic bytes of one cycle: every matrix streamed once per use (index + value per entry, 4 B per slice
+// offset -- the sliced-ELL kernels read no row pointers), every vector read or written ONCE per kernel that
+// touches it (the gathered x and the row's own x are the same array); v = bytes of a cycle scalar (4 single,
+// 8 double), the Krylov vectors touched on level 0 (b, result) are fp64
 double amg_cycle_bytes(const phb_solver *s) {
   const AmgData &D = s->amg;
   const int L = (int)D.lev.size();
   if (L == 0) return 0.;
   const double v = D.builtSingle ? 4. : 8.;
-  auto mat = [v](const SellPattern &P) { return (4. + v) * (double)P.nnz + 4. * (P.nRows + 1.); };
+  auto mat = [v](const SellPattern &P) { return (4. + v) * (double)P.nnz + 4. * (P.nSlices + 1.); };
   double total = 0.;
   for (int l = 0; l < L; ++l) {
     const AmgLevel &V = *D.lev[l];
     const double k = s->nComp, n = V.n, a = mat(l == 0 ? *s->pat : V.A.pat);
     const double vb = l == 0 ? 8. : v;                            // right-hand side of this level
-    const double jac = a + (v + (3. * v + vb) * k) * n;           // w | x gather, x, y, b per component
-    const double res = a + (2. * v + vb) * k * n;                 // x gather, r, b
+    const double jac = a + (v + (2. * v + vb) * k) * n;           // w | x, y, b per component
+    const double res = a + (2. * v + vb) * k * n;                 // x, r, b
     if (l + 1 < L) {
       const double nc = D.lev[l + 1]->n;
       total += (v + (v + vb) * k) * n + (D.nu - 1) * jac + res + (mat(V.R.pat) + v * k * (n + nc)) +
@@ -1466,9 +1467,9 @@ int amg_time_t(phb_solver *s, int reps, double out[8]) {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   const double v = sizeof(T), n = V.n, k = s->nComp;
-  // Jacobi sweep of level 0: matrix (index + value per entry, row pointers), w, then per component the gathered x,
-  // the row's own x (cycle precision), b read and result written (both fp64: Krylov vectors)
-  out[5] = (4. + v) * (double)pat0.nnz + 4. * (n + 1.) + v * n + (2. * v + 16.) * k * n;
+  // Jacobi sweep of level 0: matrix (index + value per entry, slice offsets), w, then per component x (cycle
+  // precision, read once), b read and result written (both fp64: Krylov vectors)
+  out[5] = (4. + v) * (double)pat0.nnz + 4. * (pat0.nSlices + 1.) + v * n + (v + 16.) * k * n;
   out[6] = amg_cycle_bytes(s);
   out[7] = amg_launches_per_apply(s);
   return PHB_OK;

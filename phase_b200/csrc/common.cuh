@@ -103,13 +103,14 @@ struct ncclComm;
 // -- no NCCL call, no host involvement (peer.cu).
 constexpr int kMaxPeers = 8;
 constexpr int kPeerRedChannels = 16, kPeerHaloChannels = 16;
-constexpr size_t kPeerHeaderBytes = 16384;  // red slots | halo flags | local epochs
+constexpr size_t kPeerHeaderBytes = 32768;  // red slots (two per channel and source, by epoch parity) | halo flags | local epochs
 struct PeerComm {
   bool enabled = false;
   char *arena = nullptr;
   size_t arenaBytes = 0, regionBytes = 0, vecBytes = 0;
   long long maxCols = 0;
-  int maxRegions = 0, nextRegion = 0;
+  int maxRegions = 0;
+  unsigned regionMask = 0;   // regions handed to live solvers (returned on phb_solver_destroy)
   char *peerArena[kMaxPeers] = {nullptr};
   bool opened[kMaxPeers] = {false};
 };
@@ -127,15 +128,35 @@ struct phb_ctx {
   PeerComm peer;
   // live solvers: their CUDA graphs may hold NCCL nodes, which must be gone before the communicator is
   std::vector<struct phb_solver *> solvers;
+  // first refused kernel launch since the last status check (PHB_LAUNCH)
+  cudaError_t launchError = cudaSuccess;
+  char launchWhere[160] = "";
 };
 
 namespace phb {
 void solver_drop_graph(struct phb_solver *s);   // solver.cu
+// PHB_ERR_CUDA (with the launch site in phb_last_error) if a kernel launch was refused since the last call
+inline int launch_status(phb_ctx *c) {
+  if (c->launchError == cudaSuccess) return PHB_OK;
+  set_error("kernel launch failed at %s: %s", c->launchWhere, cudaGetErrorString(c->launchError));
+  c->launchError = cudaSuccess;
+  cudaGetLastError();
+  return PHB_ERR_CUDA;
+}
 }
 
+// A refused launch (bad grid, too much shared memory ...) is recorded in the context -- launch sites sit in
+// void helpers and inside stream capture -- and reported by the next phb_ctx_launch_status() check
+// (end of every solve and time step, phb_ctx_sync).
 #define PHB_LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
   do {                                                                         \
     auto kfn__ = kernel;                                                       \
     kfn__<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);            \
     (ctx)->launches++;                                                         \
+    cudaError_t le__ = cudaPeekAtLastError();                                  \
+    if (le__ != cudaSuccess && (ctx)->launchError == cudaSuccess) {            \
+      (ctx)->launchError = le__;                                               \
+      snprintf((ctx)->launchWhere, sizeof((ctx)->launchWhere), "%s:%d %s",     \
+               __FILE__, __LINE__, #kernel);                                   \
+    }                                                                          \
   } while (0)

@@ -77,7 +77,7 @@ int phb_ctx_sync(phb_ctx *c) {
   if (c->device < 0) return PHB_OK;
   PHB_CUDA(cudaStreamSynchronize(c->stream));
   PHB_CUDA(cudaStreamSynchronize(c->commStream));
-  return PHB_OK;
+  return phb::launch_status(c);
 }
 
 int phb_comm_unique_id(void *out128) { return phb::comm_unique_id(out128); }

@@ -157,7 +157,7 @@ int phb_fs_step(phb_fracstep *fs, double dt, double stats[6]) {
     stats[0] = itU; stats[1] = itP; stats[2] = rrU; stats[3] = rrP;
     stats[4] = c->pinned[64]; stats[5] = c->pinned[65];
   }
-  return PHB_OK;
+  return phb::launch_status(c);
 }
 
 // driver options: "warmStart" 0/1 (guess = previous field values), "guessOrder" 0/1 (pEqn_ guess extrapolation)

@@ -170,19 +170,49 @@ int ilu_prepare(phb_solver *s, const SellPattern *P, const phb_mesh *halo) {
   cudaStream_t st = s->ctx->stream;
   const int n = P->nRows;
   auto oslot = [&](int r, int k) { return (size_t)P->hSliceOff[r >> 5] + (size_t)k * 32 + (r & 31); };
-  // ordered independent sets
+  // ordered independent sets.  Host-assembled patterns (Seam 1, immersed-boundary stencils) need not be
+  // structurally symmetric: the sets are built on the pattern of A + A^T (`tPtr/tInd` = for row j the rows
+  // i < j that hold an entry (i, j)), so that two coupled rows never share a set and L / U stay consistent.
+  std::vector<int> tPtr, tInd;
+  if (P == &s->own) {
+    int maxLen = 0;
+    for (int i = 0; i < n; ++i) maxLen = std::max(maxLen, P->hRowLen[i]);
+    if (maxLen > 64) {
+      set_error("ilu0: a row holds %d entries; the factorisation kernel handles at most 64 per row", maxLen);
+      return PHB_ERR_UNSUPPORTED;
+    }
+    tPtr.assign(n + 1, 0);
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < P->hRowLen[i]; ++k) {
+        const int j = P->hCol[oslot(i, k)];
+        if (j > i && j < n) tPtr[j + 1]++;
+      }
+    for (int i = 0; i < n; ++i) tPtr[i + 1] += tPtr[i];
+    tInd.resize(tPtr[n]);
+    std::vector<int> fill(tPtr.begin(), tPtr.end() - 1);
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < P->hRowLen[i]; ++k) {
+        const int j = P->hCol[oslot(i, k)];
+        if (j > i && j < n) tInd[fill[j]++] = i;
+      }
+  }
   std::vector<int> block(n, 0);
   int nBlocks = 1;
   if (s->iluOrdering == 0) {  // greedy multicolouring in the given order
     std::vector<int> mark;
     for (int i = 0; i < n; ++i) {
       mark.assign(16, 0);
+      auto see = [&](int j) {
+        if (block[j] >= (int)mark.size()) mark.resize(block[j] + 1, 0);
+        mark[block[j]] = 1;
+      };
       for (int k = 0; k < P->hRowLen[i]; ++k) {
         const int j = P->hCol[oslot(i, k)];
         if (j >= n || j >= i) continue;
-        if (block[j] >= (int)mark.size()) mark.resize(block[j] + 1, 0);
-        mark[block[j]] = 1;
+        see(j);
       }
+      if (!tPtr.empty())
+        for (int k = tPtr[i]; k < tPtr[i + 1]; ++k) see(tInd[k]);
       int c = 0;
       while (c < (int)mark.size() && mark[c]) ++c;
       block[i] = c;
@@ -195,6 +225,8 @@ int ilu_prepare(phb_solver *s, const SellPattern *P, const phb_mesh *halo) {
         const int j = P->hCol[oslot(i, k)];
         if (j < i) lv = std::max(lv, block[j] + 1);
       }
+      if (!tPtr.empty())
+        for (int k = tPtr[i]; k < tPtr[i + 1]; ++k) lv = std::max(lv, block[tInd[k]] + 1);
       block[i] = lv;
       nBlocks = std::max(nBlocks, lv + 1);
     }

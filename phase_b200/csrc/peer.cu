@@ -35,11 +35,11 @@ __global__ void k_peer_allreduce(PeerView pv, int ch, double *vals, int nvals, K
   }
   e = __shfl_sync(0xffffffffu, e, 0);
   if (t < pv.nProcs) {
-    RedSlot *dst = red_slot(pv.peer[t], ch, pv.rank);
+    RedSlot *dst = red_slot(pv.peer[t], ch, pv.rank, e);
     for (int k = 0; k < nvals; ++k) dst->v[k] = vals[k];
     __threadfence_system();
     st_release_sys(&dst->epoch, e);
-    const RedSlot *src = red_slot(pv.arena, ch, t);
+    const RedSlot *src = red_slot(pv.arena, ch, t, e);
     while (ld_acquire_sys(&src->epoch) < e) {}
     for (int k = 0; k < nvals; ++k) sv[t][k] = *reinterpret_cast<const volatile double *>(&src->v[k]);
   }
@@ -118,7 +118,7 @@ int peer_arena_create(phb_ctx *c, long long maxCols, int maxRegions, void *handl
   cudaIpcMemHandle_t h;
   PHB_CUDA(cudaIpcGetMemHandle(&h, P.arena));
   memcpy(handle64, &h, 64);
-  P.nextRegion = 0;
+  P.regionMask = 0;
   return PHB_OK;
 }
 

@@ -26,15 +26,19 @@ struct PeerFuse {
   PeerHalo halo;
 };
 
-__device__ __forceinline__ RedSlot *red_slot(char *arena, int ch, int src) {
-  return reinterpret_cast<RedSlot *>(arena) + (size_t)ch * kMaxPeers + src;
+// Reduction slots are double-buffered by epoch parity: consecutive reductions on one channel may follow each
+// other without a global synchronisation in between, and a fast rank must not overwrite the values of epoch e
+// that a slow rank has not read yet.  With two slots, epoch e + 2 (same slot as e) can only be written by a rank
+// that has finished reduction e + 1, which needed every rank's contribution to e + 1 -- sent after it read e.
+__device__ __forceinline__ RedSlot *red_slot(char *arena, int ch, int src, unsigned long long epoch) {
+  return reinterpret_cast<RedSlot *>(arena) + ((size_t)ch * 2 + (epoch & 1ull)) * kMaxPeers + src;
 }
 __device__ __forceinline__ unsigned long long *halo_flag(char *arena, int ch, int src) {
-  return reinterpret_cast<unsigned long long *>(arena + kPeerRedChannels * kMaxPeers * sizeof(RedSlot)) +
+  return reinterpret_cast<unsigned long long *>(arena + 2 * kPeerRedChannels * kMaxPeers * sizeof(RedSlot)) +
          (size_t)ch * kMaxPeers + src;
 }
 __device__ __forceinline__ unsigned long long *local_epoch(char *arena, int idx) {
-  return reinterpret_cast<unsigned long long *>(arena + 12288) + idx;
+  return reinterpret_cast<unsigned long long *>(arena + 20480) + idx;
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
   unsigned long long v;
@@ -107,7 +111,7 @@ __device__ __forceinline__ void reduce_push_warp(const PeerView &pv, int ch, con
   }
   e = __shfl_sync(0xffffffffu, e, 0);
   if (lane < pv.nProcs) {
-    RedSlot *dst = red_slot(pv.peer[lane], ch, pv.rank);
+    RedSlot *dst = red_slot(pv.peer[lane], ch, pv.rank, e);
     for (int k = 0; k < nvals; ++k) dst->v[k] = __ldcg(vals + k);
     __threadfence_system();
     st_release_sys(&dst->epoch, e);
@@ -120,7 +124,7 @@ __device__ __forceinline__ void reduce_wait_block(const PeerView &pv, int ch, do
   const int t = threadIdx.x;
   if (t < pv.nProcs) {
     const unsigned long long e = *local_epoch(pv.arena, ch);  // set by my own push (previous kernel)
-    const RedSlot *src = red_slot(pv.arena, ch, t);
+    const RedSlot *src = red_slot(pv.arena, ch, t, e);
     while (ld_acquire_sys(&src->epoch) < e) {}
 #pragma unroll
     for (int k = 0; k < NV; ++k) sv[t][k] = *reinterpret_cast<const volatile double *>(&src->v[k]);

@@ -400,14 +400,18 @@ int ensure_vectors(phb_solver *s) {
   PHB_CHECK(s->rhat.alloc(len)); PHB_CHECK(s->v.alloc(len)); PHB_CHECK(s->t.alloc(len));
   // the gathered vectors (p, s and their preconditioned images) live in the peer arena when
   // there is one, so that peers can store their halo values straight into the ghost segments
-  if (c->peer.enabled && c->nProcs > 1 && s->peerRegion == -1)
-    s->peerRegion = (c->peer.nextRegion < c->peer.maxRegions && c->peer.maxRegions * 4 <= kPeerHaloChannels)
-                        ? c->peer.nextRegion++ : -2;
+  if (c->peer.enabled && c->nProcs > 1 && s->peerRegion == -1) {
+    // first free region; solvers are created and destroyed in the same order on every rank, so the choice agrees
+    s->peerRegion = -2;
+    if (c->peer.maxRegions * 4 <= kPeerHaloChannels)
+      for (int r = 0; r < c->peer.maxRegions; ++r)
+        if (!(c->peer.regionMask & (1u << r))) { c->peer.regionMask |= 1u << r; s->peerRegion = r; break; }
+  }
   if (s->peerRegion >= 0 && len * sizeof(double) <= c->peer.vecBytes) {
     s->p.attach(peer_vector(c, s->peerRegion, 0), len); s->s.attach(peer_vector(c, s->peerRegion, 1), len);
     s->ph.attach(peer_vector(c, s->peerRegion, 2), len); s->sh.attach(peer_vector(c, s->peerRegion, 3), len);
   } else {
-    if (s->peerRegion >= 0) s->peerRegion = -2;
+    if (s->peerRegion >= 0) { c->peer.regionMask &= ~(1u << s->peerRegion); s->peerRegion = -2; }
     PHB_CHECK(s->p.alloc(len)); PHB_CHECK(s->s.alloc(len));
   }
   const size_t nb = (size_t)s->ctx->numSMs * kBlocksPerSM;
@@ -623,7 +627,7 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
   if (s->precond == PHB_PC_AMG) amg_record_iters(s, totalIters);
   if (iters) *iters = totalIters;
   if (relres) *relres = rel;
-  return PHB_OK;
+  return launch_status(c);
 }
 
 }  // namespace phb
@@ -646,6 +650,7 @@ int phb_solver_destroy(phb_solver *s) {
   if (!s) return PHB_OK;
   auto &live = s->ctx->solvers;
   live.erase(std::remove(live.begin(), live.end(), s), live.end());
+  if (s->peerRegion >= 0) s->ctx->peer.regionMask &= ~(1u << s->peerRegion);
   if (s->graphExec) cudaGraphExecDestroy(s->graphExec);
   delete s;
   return PHB_OK;
@@ -815,6 +820,10 @@ int phb_solver_set_csr(phb_solver *s, int nRows, const int *rowPtr, const int *c
     PHB_CHECK(s->ownVals.alloc((size_t)S.nSlots));
     PHB_CHECK(s->ownVals.zero(c->stream));
     if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
+    // `own` is rebuilt in place (same address, possibly the same slot count): everything derived from the old
+    // columns -- the ILU ordering / slot map and the multigrid hierarchy -- is stale
+    s->ilu.src = nullptr;
+    s->amg.built = false;
   }
   PHB_CHECK(s->csrVals.upload(vals, (size_t)nnzIn, c->stream));
   PHB_LAUNCH(c, k_scatter_vals, grid_for(c, nnzIn), kThreads, 0, nnzIn, s->csr2slot.p, s->csrVals.p, s->ownVals.p);

@@ -103,3 +103,60 @@ def test_cavity_with_amg_pressure_solve(comm, kind, nx, ny, upc):
     assert rel_l2(u[0], ofs.view("ux")) < TOL and rel_l2(u[1], ofs.view("uy")) < TOL
     assert rel_l2(p - p.mean(), po - po.mean()) < TOL
     gfs.close(); g.close()
+
+
+def test_cavity_bench_defaults_1m_cells(comm):
+    """The configuration bench.py times -- V-cycle on both equations, single-precision cycle, default
+    `amgCoarsest` (5 levels with a ~900-row dense tail at this size) -- at 1000x1000 cells for 3 steps against
+    the oracle's direct solve; only the residual tolerance is the parity one (1e-11)."""
+    from phase_b200.api import FiniteVolumeGrid2D as G, lid_driven_cavity
+    n = 1000
+    om, ofs = oracle_cavity("rect", n, n, 1.0, 1.0, 1.0, 0.1)
+    ofs.use_direct_solver()
+    g = G.rectilinear(comm, n, n, 1.0, 1.0)
+    gfs = lid_driven_cavity(g, 1.0, 0.1, solver=dict(tolerance=1e-11, maxIters=2000, preconditioner="amg"))
+    dt = 0.5 / n
+    for _ in range(3):
+        ofs.step(dt)
+        st = gfs.solve(dt)
+        assert st["errorU"] <= 1e-10 and st["errorP"] <= 1e-10 and st["itersP"] <= 60, st
+    info = gfs.pEqn.solver.amgInfo()
+    assert info["levels"] >= 4 and 100 < info["coarsestRows"] <= 1000 and info["setups"] == 1, info
+    u, p, po = gfs.u.get("cells"), gfs.p.get("cells"), ofs.view("p").copy()
+    assert rel_l2(u[0], ofs.view("ux")) < TOL and rel_l2(u[1], ofs.view("uy")) < TOL
+    assert rel_l2(p - p.mean(), po - po.mean()) < TOL
+    assert rel_l2(gfs.u.get("faces")[0], ofs.view("ufx")) < TOL
+    gfs.close(); g.close()
+
+
+def test_default_hierarchy_with_fixed_pressure_patch(comm):
+    """Same defaults on a NON-singular pEqn_ (p fixed on the lid patch): the dense coarsest inverse is the plain
+    one, not the constant-regularised one."""
+    from phase_b200.api import FIXED, NORMAL_GRADIENT, FiniteVolumeGrid2D as G, FractionalStep
+    n = 400
+    om = O.Mesh.rectilinear(n, n, 1.0, 1.0)
+    ofs = O.FracStep(om, 1.0, 0.1)
+    g = G.rectilinear(comm, n, n, 1.0, 1.0)
+    gfs = FractionalStep(g, 1.0, 0.1)
+    for pt in ("x-", "x+", "y-", "y+"):
+        lid = (1.0, 0.0) if pt == "y+" else (0.0, 0.0)
+        ofs.set_bc("u", pt, O.FIXED, *lid)
+        gfs.u.setBoundary(pt, FIXED, lid)
+        ofs.set_bc("p", pt, O.FIXED if pt == "y+" else O.NORMAL_GRADIENT, 0.0)
+        gfs.p.setBoundary(pt, FIXED if pt == "y+" else NORMAL_GRADIENT, 0.0)
+    ofs.initialize()
+    ofs.use_direct_solver()
+    cfg = dict(solver="BICGSTAB", tolerance=1e-11, maxIters=2000, preconditioner="amg")
+    gfs.uEqn.solver.setup(cfg); gfs.pEqn.solver.setup(cfg)
+    gfs.initialize()
+    dt = 0.5 / n
+    for _ in range(3):
+        ofs.step(dt)
+        st = gfs.solve(dt)
+        assert st["errorP"] <= 1e-10 and st["itersP"] <= 60, st
+    info = gfs.pEqn.solver.amgInfo()
+    assert info["levels"] >= 3 and info["coarsestRows"] > 40, info
+    u, p = gfs.u.get("cells"), gfs.p.get("cells")
+    assert rel_l2(u[0], ofs.view("ux")) < TOL and rel_l2(u[1], ofs.view("uy")) < TOL
+    assert rel_l2(p, ofs.view("p")) < TOL
+    gfs.close(); g.close()

@@ -227,3 +227,52 @@ def test_amg_singular_neumann_system(comm):
     x, xd = s.x(), O.direct_solve(rp, ci, va, bc)
     assert rel_l2(x - x.mean(), xd - xd.mean()) < 1e-7
     s.close()
+
+
+def _upwind_like_system(n, shift, seed):
+    """n x n system, every row [diagonal, i - shift, i + shift + 1] (wrapped): changing `shift` moves the
+    columns while every row keeps exactly three entries -- the slot count of the sliced-ELL image is unchanged.
+    Structurally NON-symmetric, as the upwind coefficients of a host-assembled CrsEquation are."""
+    rng = np.random.default_rng(seed)
+    rp = np.arange(0, 3 * n + 1, 3, dtype=np.int32)
+    ci = np.empty(3 * n, np.int32)
+    va = np.empty(3 * n)
+    i = np.arange(n)
+    ci[0::3], ci[1::3], ci[2::3] = i, (i - shift) % n, (i + shift + 1) % n
+    va[1::3], va[2::3] = -rng.uniform(0.5, 1.0, n), -rng.uniform(0.1, 0.5, n)
+    va[0::3] = 0.2 - va[1::3] - va[2::3]
+    return rp, ci, va, rng.standard_normal(n)
+
+
+@pytest.mark.parametrize("pc", ["ilu0", "amg", "jacobi"])
+def test_pattern_change_at_constant_row_lengths(comm, pc):
+    """A solver that lives as long as its equation (M/CrsEquation.cpp:16-26) sees the column pattern change
+    between solves while row lengths -- and the padded slot count -- stay the same (IB stencils; `+=` dropping
+    exact zeros).  Every cached analysis (ILU ordering and slot map, multigrid hierarchy, CUDA graph) has to go."""
+    from phase_b200.api import SparseMatrixSolver
+    n = 3000
+    s = SparseMatrixSolver(comm).setup(dict(solver="BICGSTAB", maxIters=5000, tolerance=1e-11, preconditioner=pc,
+                                            amgCoarsest=60))
+    for shift, seed in ((1, 0), (7, 1), (1, 2), (40, 3)):
+        rp, ci, va, b = _upwind_like_system(n, shift, seed)
+        s.setRank(n); s.set(rp, ci, va); s.setRhs(b)
+        err = s.solve()
+        assert err <= 1e-11, (shift, err)
+        xd = O.direct_solve(rp, ci, va, b)
+        assert rel_l2(s.x(), xd) < 1e-8, (pc, shift)
+    s.close()
+
+
+def test_ilu0_refuses_rows_beyond_64_entries(comm):
+    from phase_b200.api import PhaseB200Error, SparseMatrixSolver
+    n, w = 200, 70
+    rp = np.arange(0, w * n + 1, w, dtype=np.int32)
+    ci = ((np.arange(n)[:, None] + np.arange(w)[None, :]) % n).astype(np.int32).reshape(-1)
+    va = np.where(np.tile(np.arange(w), n) == 0, 100.0, -1.0)
+    s = SparseMatrixSolver(comm).setup(dict(preconditioner="ilu0"))
+    s.setRank(n); s.set(rp, ci, va); s.setRhs(np.ones(n))
+    with pytest.raises(PhaseB200Error):
+        s.solve()
+    s.setup(dict(preconditioner="jacobi"))
+    assert s.solve() <= 1e-8
+    s.close()
