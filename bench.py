@@ -425,19 +425,25 @@ def e2e_record(job, comm, fs, dt, steps, sizes, weak):
     for k, (fld, part) in parts.items():
         host[k].numpy()[:] = fld.get(part).reshape(-1)
     nbytes = sum(v.numel() for v in host.values()) * 8
-    job.barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
+
+    def one_step():
         for k, (fld, part) in parts.items():
             fld.set(part, host[k].numpy())
         fs.p.sendMessages(); fs.p.setBoundaryFaces(); fs.computeGradP()
         fs.solve(dt)
         for k, (fld, part) in parts.items():
             fld.get(part, out=host[k].numpy())
+
+    for _ in range(2):                  # the first transfers of a pinned buffer run at a third of the link rate
+        one_step()
+    job.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
     job.barrier()
     s = job.max_over_ranks((time.perf_counter() - t0) / steps)
     return {"value": (job.world if weak else 1) / s, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-            "steps": steps, "ms_per_step": 1e3 * s,
+            "steps": steps, "warmup": 2, "ms_per_step": 1e3 * s,
             "what": "pinned host state (u cells + faces, p cells) copied in, grad p rebuilt, FractionalStep.solve, the same "
                     "arrays copied out, every step; wall clock, max over ranks"}
 
@@ -583,7 +589,7 @@ def main():
         amg_info["uEqn"] = fs.uEqn.solver.amgInfo() if u_pc == "amg" else u_pc
         amg_info["note"] = ("hierarchy built in the first (warm-up) solve and reused: pEqn_ = laplacian(dt, p) is constant up to "
                             "the scalar dt; setupMs is that one-off cost, outside the timed steps")
-    e2e = e2e_record(job, comm, fs, dt, max(1, min(args.steps, 3)), sizes, weak)
+    e2e = e2e_record(job, comm, fs, dt, max(1, min(args.steps, 5)), sizes, weak)
     seam1 = seam1_record(comm, fs, dt, args) if world == 1 else None
     state = None
     if world == 1 and rank == 0 and not args.no_cpu and args.mesh == "quad":

@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = "/root/reference/src"
 ORACLE_SO = os.path.join(HERE, "_build", "libphase_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libphase_ref_crs.so")
+REF_FV_SO = os.path.join(HERE, "_ref", "libphase_ref_fv.so")
 
 
 def _newer(target, sources):
@@ -52,6 +53,69 @@ def build_ref(force=False):
     return REF_SO
 
 
+def ref_fv_sources():
+    """The reference translation units behind oracle/_ref/libphase_ref_fv.so, compiled where they lie: system +
+    CSR algebra, 2-D geometry, the unstructured grid, fields, equations, the fv:: / src:: / cicsam:: operators and
+    the fractional-step solver module.  Left out: everything that needs CGNS, Trilinos / Eigen (the backends; a
+    recording backend takes their place in ref_fv_driver.cpp), the command line and the immersed-boundary /
+    post-processing subsystems."""
+    import glob
+    R = REF_SRC
+    U = os.path.join(R, "2D", "Unstructured")
+    files = [os.path.join(R, "System", f) for f in ("Exception.cpp", "Communicator.cpp", "Input.cpp")]
+    files += [os.path.join(R, "Math", f) for f in ("Vector.cpp", "CrsEquation.cpp", "SparseMatrixSolver.cpp", "Matrix.cpp")]
+    files += sorted(glob.glob(os.path.join(R, "2D", "Geometry", "*.cpp")))
+    for root, _, names in sorted(os.walk(os.path.join(U, "FiniteVolumeGrid2D"))):
+        files += [os.path.join(root, n) for n in sorted(names)
+                  if n.endswith(".cpp") and "Cgns" not in n and "Factory" not in n]
+    files += sorted(glob.glob(os.path.join(U, "FiniteVolume", "Field", "*.cpp")))
+    files += sorted(glob.glob(os.path.join(U, "FiniteVolume", "Equation", "*.cpp")))
+    files += [os.path.join(U, "FiniteVolume", "Discretization", f) for f in
+              ("Laplacian.cpp", "Source.cpp", "Divergence.cpp", "Cicsam.cpp", "Axisymmetric.cpp")]
+    files += [os.path.join(U, "Solvers", f) for f in ("Solver.cpp", "FractionalStep.cpp")]
+    return files
+
+
+def _openblas():
+    """The LP64 OpenBLAS inside scipy (symbols prefixed scipy_, see oracle/ref_stub/{cblas,lapacke}.h)."""
+    import glob
+    import scipy
+    libs = glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas-*.so"))
+    return libs[0] if libs else None
+
+
+def build_ref_fv(force=False):
+    """oracle/_ref/libphase_ref_fv.so, or None when neither the reference sources nor a prebuilt exist."""
+    import concurrent.futures
+    driver = os.path.join(HERE, "ref_fv_driver.cpp")
+    if not os.path.exists(os.path.join(REF_SRC, "2D", "Unstructured", "Solvers", "FractionalStep.cpp")):
+        return REF_FV_SO if os.path.exists(REF_FV_SO) else None
+    srcs = ref_fv_sources() + [driver]
+    stubs = [os.path.join(r, n) for r, _, ns in os.walk(os.path.join(HERE, "ref_stub")) for n in ns]
+    if not force and _newer(REF_FV_SO, srcs + stubs):
+        return REF_FV_SO
+    blas = _openblas()
+    if blas is None:
+        return REF_FV_SO if os.path.exists(REF_FV_SO) else None
+    objdir = os.path.join(HERE, "_ref", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    inc = ["-I" + os.path.join(HERE, "ref_stub"), "-I" + REF_SRC, "-I" + os.path.join(REF_SRC, "2D"),
+           "-I" + os.path.join(REF_SRC, "2D", "Unstructured")]
+
+    def cc(src):
+        obj = os.path.join(objdir, os.path.relpath(src, "/").replace("/", "_") + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(f) for f in [src] + stubs):
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-w", "-c"] + inc + [src, "-o", obj])
+        return obj
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(cc, srcs))
+    subprocess.check_call(["g++", "-shared", "-o", REF_FV_SO] + objs +
+                          [blas, "-Wl,-rpath," + os.path.dirname(blas), "-lstdc++fs"])
+    return REF_FV_SO
+
+
 if __name__ == "__main__":
     print(build_oracle(force=True))
     print(build_ref(force=True))
+    print(build_ref_fv(force=True))

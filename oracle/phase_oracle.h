@@ -6,18 +6,26 @@
  * the CUDA product in phase_b200/csrc and to serve as the timed CPU baseline in
  * bench.py.  Nothing in the product path may include, link or call this file.
  *
- * Parity status: the reference's own tests pin nothing for this path
- * (SURVEY.md section 4), so this oracle is pinned by
- *   (1) oracle/_ref: the reference's own src/Math/{Vector,CrsEquation,
- *       SparseMatrixSolver}.cpp compiled in place (oracle/build_ref.py) and
- *       driven through oracle/ref_driver.cpp -- exact CSR insertion /
- *       compaction / operator algebra / set()+setRhs(-rhs) hand-off;
- *   (2) hand-simulated known answers derived from the reference code
- *       (3x3 rectilinear connectivity, uniform-grid
- *       coefficients, conservation identities), tests/test_oracle_kat.py.
- * The solve arithmetic of the reference lives in un-vendored Eigen3/Trilinos
- * (versions unpinned): for that part parity is UNPINNED and any exact direct
- * solve (scipy splu) is used as the stand-in.
+ * Parity status: PINNED on the reference's own code.
+ *   (1) oracle/_ref/libphase_ref_fv.so: the reference's grid, field, equation,
+ *       fv::/src::/cicsam:: operator and FractionalStep translation units compiled
+ *       where they lie (oracle/build.py: build_ref_fv) over stand-in headers for
+ *       Boost / MPI (one rank) / METIS / CGNS (oracle/ref_stub) and driven through
+ *       oracle/ref_fv_driver.cpp.  tests/test_oracle_ref_fv.py: connectivity, link
+ *       tables, IndexMap and the CSR patterns at the solver hand-off bit-exact;
+ *       coefficients, right-hand sides and fields after K FractionalStep::solve
+ *       calls to round-off.  tests/golden/ref_*.npz are written by that library
+ *       (tests/golden/make_ref_golden.py) and checked against this file and the
+ *       CUDA path wherever the tests run.
+ *   (2) oracle/_ref/libphase_ref_crs.so: src/Math/{Vector,CrsEquation,
+ *       SparseMatrixSolver}.cpp alone -- exact CSR insertion / compaction /
+ *       operator algebra / set()+setRhs(-rhs) hand-off (tests/test_oracle_ref_crs.py).
+ *   (3) hand-simulated known answers, tests/test_oracle_kat.py.
+ * Not pinned: the polygon area / centroid arithmetic (Boost.Geometry is absent;
+ * the stand-in implements the same shoelace / Bashein-Detmer formulas), the
+ * partition / halo maps (the reference needs MPI ranks and METIS for them) and
+ * the solve arithmetic itself, which lives in un-vendored Eigen3 / Trilinos
+ * (versions unpinned): any exact direct solve (scipy splu) stands in for it.
  */
 #ifndef PHASE_ORACLE_H
 #define PHASE_ORACLE_H

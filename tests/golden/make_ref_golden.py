@@ -1,0 +1,56 @@
+"""Writes tests/golden/ref_*.npz from the REFERENCE ITSELF: oracle/_ref/libphase_ref_fv.so is the reference's own
+grid / field / operator / FractionalStep sources compiled in place (oracle/build.py, oracle/ref_fv_driver.cpp), so
+every array below was produced by /root/reference/src code, not by the oracle restatement.  Run here (needs
+/root/reference):   python tests/golden/make_ref_golden.py
+
+Per case: connectivity and link tables (I1, I2), geometry (G1-G3), the cavity's fields after K converged time steps
+(direct solves) and what FiniteVolumeEquation<T>::solve handed to the solver backend in step K: uEqn_ in the
+compact layout, pEqn_ padded with the neighbour first (I4, A1-A8, S1).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import oracle as O  # noqa: E402
+from oracle import ref_fv as R  # noqa: E402
+from tests.test_oracle_ref_fv import F64_KEYS, INT_KEYS, ref_grid_like  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = [("ref_cavity_rect_16x12", "rect", 16, 12, 1.0, 1.0, 6), ("ref_cavity_rect_24x10", "rect", 24, 10, 2.0, 0.5, 4),
+         ("ref_cavity_tri_8x7", "tri", 8, 7, 1.0, 1.0, 5)]
+
+
+def make(name, kind, nx, ny, w, h, K):
+    case = R.Case(nx, ny, w, h, 1.0, 0.1)
+    if kind == "rect":
+        g = R.Grid.rectilinear(case)
+    else:   # node coordinates and cell -> node lists of the split lattice are inputs; everything derived is the reference's
+        g = ref_grid_like(O.Mesh.triangulated(nx, ny, w, h), case)
+    out = {"kind": kind, "nx": nx, "ny": ny, "w": w, "h": h, "K": K, "dt": 0.5 * w / nx, "rho": 1.0, "mu": 0.1}
+    for k in INT_KEYS + F64_KEYS:
+        out["mesh_" + k] = g.array(k)
+    for p in ("x-", "x+", "y-", "y+"):
+        out["patch_" + p] = np.sort(g.array("patch:" + p))
+    R.use_direct_solver()
+    fs = R.FracStep(case, g)
+    for _ in range(K):
+        fs.step(out["dt"])
+    for k in ("ux", "uy", "ufx", "ufy", "p", "pf", "gpx", "gpy"):
+        out["field_" + k] = fs.view(k)
+    for which in ("uEqn", "pEqn"):
+        rp, ci, va, b = fs.handoff(which)
+        out[which + "_rowPtr"], out[which + "_colInd"], out[which + "_vals"], out[which + "_b"] = rp, ci, va, b
+    out["maxDivergence"], out["maxCourant"] = fs.max_divergence(), fs.max_courant(out["dt"])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    fs.close(); g.close(); case.close()
+    print(name, "written")
+
+
+if __name__ == "__main__":
+    if not R.available():
+        sys.exit("the reference FV library is not available (needs /root/reference)")
+    for c in CASES:
+        make(*c)
