@@ -182,6 +182,9 @@ int phb_solver_spmv(phb_solver *s, const double *x, double *y, int n);
 /* repeat the device SpMV `reps` times on resident data; returns mean ms/launch
  * measured with CUDA events on the context stream (bench.py roofline leg) */
 int phb_solver_time_spmv(phb_solver *s, int reps, double *msPerLaunch);
+/* z = M^-1 r with the multigrid hierarchy of the last solve (host vectors over the owned rows, [x-block | y-block]):
+ * lets tests compare one application of the device V-cycle with a transcription of the same hierarchy */
+int phb_solver_apply_preconditioner(phb_solver *s, const double *r, double *z, int n);
 /* algorithmic byte counts of the current matrix: [spmv, bicgstabIteration] */
 int phb_solver_bytes(const phb_solver *s, double out[2]);
 
@@ -326,6 +329,26 @@ int phb_fs_step(phb_fracstep *fs, double dt, double stats[6]);
 /* computeMaxTimeStep: US/FractionalStep.cpp:68-77 */
 int phb_fs_max_time_step(phb_fracstep *fs, double maxCo, double prevDt,
                          double maxDt, double *out);
+
+/* ------------------------------------------------- multiphase fractional step
+ * Device-resident FractionalStepMultiphase::solve (US/FractionalStepMultiphase.cpp:52-218), config 4: CICSAM
+ * advection of gamma, density / viscosity blend, gravity and CELESTE surface-tension sources
+ * (U/FiniteVolume/Multiphase/{Celeste,CelesteStencil,SurfaceTensionForce,SurfaceTensionForceSmoothingKernel}.cpp),
+ * rho-weighted gradient reconstruction (UF/VectorFiniteVolumeField.cpp:28-50), momentum-weighted face velocity,
+ * variable-coefficient pressure equation.  Single rank.  Set gamma (cells and faces), then initialize.
+ * fields: u p gradP gamma gradGamma rho mu beta sg fst kappa gammaTilde gradGammaTilde n gradRho
+ * setup keys (before initialize): eps, kernelType (0 peskin, 1 pow6, 2 pow8), warmStart, contactAngle:<patch> (degrees)
+ * stats: [itersGamma, itersU, itersP, relresGamma, relresU, relresP, maxDivergence, maxCourant] */
+typedef struct phb_multiphase phb_multiphase;
+int phb_mp_create(phb_mesh *m, double rho1, double rho2, double mu1, double mu2, double sigma, double gx, double gy,
+                  double smoothingKernelRadius, phb_multiphase **out);
+int phb_mp_destroy(phb_multiphase *mp);
+phb_field *phb_mp_field(phb_multiphase *mp, const char *name);
+phb_eqn *phb_mp_eqn(phb_multiphase *mp, const char *name);       /* gammaEqn uEqn pEqn */
+phb_solver *phb_mp_solver(phb_multiphase *mp, const char *name);
+int phb_mp_setup(phb_multiphase *mp, const char *key, double value);
+int phb_mp_initialize(phb_multiphase *mp);
+int phb_mp_step(phb_multiphase *mp, double dt, double stats[8]);
 
 /* ------------------------------------------------------------ PISO time step
  * "phasePiso" of the north star.  The mounted snapshot has no PISO module any more

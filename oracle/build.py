@@ -72,7 +72,9 @@ def ref_fv_sources():
     files += sorted(glob.glob(os.path.join(U, "FiniteVolume", "Equation", "*.cpp")))
     files += [os.path.join(U, "FiniteVolume", "Discretization", f) for f in
               ("Laplacian.cpp", "Source.cpp", "Divergence.cpp", "Cicsam.cpp", "Axisymmetric.cpp")]
-    files += [os.path.join(U, "Solvers", f) for f in ("Solver.cpp", "FractionalStep.cpp")]
+    files += [os.path.join(U, "FiniteVolume", "Multiphase", f) for f in
+              ("Celeste.cpp", "CelesteStencil.cpp", "SurfaceTensionForce.cpp", "SurfaceTensionForceSmoothingKernel.cpp")]
+    files += [os.path.join(U, "Solvers", f) for f in ("Solver.cpp", "FractionalStep.cpp", "FractionalStepMultiphase.cpp")]
     return files
 
 

@@ -45,6 +45,12 @@ def lib():
         L.rfv_index_map.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.rfv_fs_create.restype = vp
         L.rfv_fs_create.argtypes = [vp, vp]
+        L.rfv_fsm_create.restype = vp
+        L.rfv_fsm_create.argtypes = [vp, vp]
+        L.rfv_fs_initialize.restype = C.c_long
+        L.rfv_fs_initialize.argtypes = [vp]
+        L.rfv_fs_any_field.restype = C.c_long
+        L.rfv_fs_any_field.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int]
         L.rfv_fs_close.argtypes = [vp]
         L.rfv_fs_step.restype = C.c_long
         L.rfv_fs_step.argtypes = [vp, C.c_double]
@@ -81,15 +87,19 @@ INT_ARRAYS = ("sizes", "cptr", "cind", "faceN1", "faceN2", "faceL", "faceR", "il
 class Case:
     """A case directory in the reference's INFO format (case.info, boundaries.info, ...), written to a temp dir."""
 
-    def __init__(self, nx, ny, width=1.0, height=1.0, rho=1.0, mu=0.1, time_step=1.0, bcs=None):
-        """bcs: {field: {patch or "*": (type, value string)}}; default = Examples/LidDrivenCavity/case/boundaries.info"""
+    def __init__(self, nx, ny, width=1.0, height=1.0, rho=1.0, mu=0.1, time_step=1.0, bcs=None, properties=None,
+                 solver=None):
+        """bcs: {field: {patch or "*": (type, value string)}}; default = Examples/LidDrivenCavity/case/boundaries.info.
+        properties / solver: extra `Properties` / `Solver` keys (rho1, sigma, g, smoothingKernelRadius, ...)"""
         self.dir = tempfile.mkdtemp(prefix="phase_ref_case_")
         if bcs is None:
             bcs = {"u": {"*": ("fixed", "(0,0)"), "y+": ("fixed", "(1,0)")}, "p": {"*": ("normal_gradient", "0")}}
         with open(os.path.join(self.dir, "case.info"), "w") as f:
-            f.write("Solver\n{\n  timeStep %.17g\n}\nProperties\n{\n  rho %.17g\n  mu %.17g\n}\n" % (time_step, rho, mu))
+            sol = "".join("  %s %s\n" % (k, v) for k, v in (solver or {}).items())
+            prop = "".join("  %s %s\n" % (k, v if isinstance(v, str) else "%.17g" % v) for k, v in (properties or {}).items())
+            f.write("Solver\n{\n  timeStep %.17g\n%s}\nProperties\n{\n  rho %.17g\n  mu %.17g\n%s}\n" % (time_step, sol, rho, mu, prop))
             f.write("Grid\n{\n  type rectilinear\n  nCellsX %d\n  nCellsY %d\n  width %.17g\n  height %.17g\n}\n" % (nx, ny, width, height))
-            f.write("LinearAlgebra\n{\n  uEqn\n  {\n    lib recording\n  }\n  pEqn\n  {\n    lib recording\n  }\n}\n")
+            f.write("LinearAlgebra\n{\n" + "".join("  %s\n  {\n    lib recording\n  }\n" % e for e in ("uEqn", "pEqn", "gammaEqn")) + "}\n")
         with open(os.path.join(self.dir, "boundaries.info"), "w") as f:
             f.write("Boundaries\n{\n")
             for field, patches in bcs.items():
@@ -211,6 +221,20 @@ class FracStep:
                                     b.ctypes.data_as(C.POINTER(C.c_double)), None))
         return rp, ci[:nnz.value], va[:nnz.value], b
 
+    def field(self, name, comp=-1, faces=False):
+        """any registered field by its reference name; comp -1 = scalar, 0 / 1 = vector component"""
+        out = np.zeros(self.F if faces else self.N)
+        _check(lib().rfv_fs_any_field(self.h, name.encode(), comp, int(faces), out.ctypes.data_as(C.POINTER(C.c_double)), 0))
+        return out
+
+    def set_field(self, name, v, comp=-1, faces=False):
+        v = np.ascontiguousarray(v, np.float64)
+        assert len(v) == (self.F if faces else self.N)
+        _check(lib().rfv_fs_any_field(self.h, name.encode(), comp, int(faces), v.ctypes.data_as(C.POINTER(C.c_double)), 1))
+
+    def initialize(self):
+        _check(lib().rfv_fs_initialize(self.h))
+
     def max_divergence(self):
         return lib().rfv_fs_max_divergence(self.h)
 
@@ -224,3 +248,13 @@ class FracStep:
         if self.h:
             lib().rfv_fs_close(self.h)
             self.h = None
+
+
+class Multiphase(FracStep):
+    """FractionalStepMultiphase(input, grid) (US/FractionalStepMultiphase.cpp); set gamma, then initialize()."""
+
+    def __init__(self, case, grid):
+        self.case, self.grid = case, grid
+        self.h = _check(lib().rfv_fsm_create(case.h, grid.h))
+        s = grid.array("sizes")
+        self.N, self.F = int(s[1]), int(s[2])

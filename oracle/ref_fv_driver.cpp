@@ -22,6 +22,7 @@
 #include "System/CgnsFile.h"
 #include "FiniteVolumeGrid2D/StructuredRectilinearGrid.h"
 #include "Solvers/FractionalStep.h"
+#include "Solvers/FractionalStepMultiphase.h"
 
 // ---- CGNS restart reader: never reached (the oracle does not restart)
 CgnsFile::CgnsFile(const std::string &, Mode) { throw Exception("CgnsFile", "CgnsFile", "not available in the oracle build"); }
@@ -107,9 +108,20 @@ public:
   using FractionalStep::u_;
   using FractionalStep::uEqn_;
 };
+class OpenMultiphase : public FractionalStepMultiphase {
+public:
+  using FractionalStepMultiphase::FractionalStepMultiphase;
+  using FractionalStepMultiphase::gammaEqn_;
+  using FractionalStepMultiphase::maxDivergenceError;
+  using FractionalStepMultiphase::pEqn_;
+  using FractionalStepMultiphase::uEqn_;
+};
 struct RefFs {
-  std::shared_ptr<OpenFracStep> fs;
+  std::shared_ptr<OpenFracStep> fs;          // kind 0
+  std::shared_ptr<OpenMultiphase> mp;        // kind 1
   std::shared_ptr<FiniteVolumeGrid2D> g;
+  Solver &solver() { return fs ? static_cast<Solver &>(*fs) : static_cast<Solver &>(*mp); }
+  FractionalStep &base() { return fs ? static_cast<FractionalStep &>(*fs) : static_cast<FractionalStep &>(*mp); }
 };
 
 template <class F> long guarded(F f) {
@@ -246,19 +258,72 @@ void *rfv_fs_create(void *caseHandle, void *grid) {
 }
 void rfv_fs_close(void *fs) { delete static_cast<RefFs *>(fs); }
 
-long rfv_fs_step(void *fs, double dt) {
-  return guarded([&] { static_cast<RefFs *>(fs)->fs->solve(dt); return 0L; });
+// FractionalStepMultiphase(input, grid) (US/FractionalStepMultiphase.cpp:11-50); NOT initialised: set gamma (and
+// whatever else) through rfv_fs_any_field first, then rfv_fs_initialize
+void *rfv_fsm_create(void *caseHandle, void *grid) {
+  RefFs *r = nullptr;
+  if (guarded([&] {
+        r = new RefFs();
+        r->g = static_cast<RefGrid *>(grid)->g;
+        r->mp = std::make_shared<OpenMultiphase>(static_cast<RefCase *>(caseHandle)->input, r->g);
+        return 0L;
+      }) < 0) { delete r; return nullptr; }
+  return r;
 }
-double rfv_fs_max_divergence(void *fs) { return static_cast<RefFs *>(fs)->fs->maxDivergenceError(); }
-double rfv_fs_max_courant(void *fs, double dt) { return static_cast<RefFs *>(fs)->fs->maxCourantNumber(dt); }
+long rfv_fs_initialize(void *fs) {
+  return guarded([&] {
+    RefFs &R = *static_cast<RefFs *>(fs);
+    if (R.fs) R.fs->initialize(); else R.mp->initialize();
+    return 0L;
+  });
+}
+long rfv_fs_step(void *fs, double dt) {
+  return guarded([&] {
+    RefFs &R = *static_cast<RefFs *>(fs);
+    if (R.fs) R.fs->solve(dt); else R.mp->solve(dt);
+    return 0L;
+  });
+}
+double rfv_fs_max_divergence(void *fs) {
+  RefFs &R = *static_cast<RefFs *>(fs);
+  return R.fs ? R.fs->maxDivergenceError() : R.mp->maxDivergenceError();
+}
+double rfv_fs_max_courant(void *fs, double dt) { return static_cast<RefFs *>(fs)->base().maxCourantNumber(dt); }
 double rfv_fs_max_time_step(void *fs, double maxCo, double prevDt) {
-  return static_cast<RefFs *>(fs)->fs->computeMaxTimeStep(maxCo, prevDt);
+  RefFs &R = *static_cast<RefFs *>(fs);
+  return R.fs ? R.fs->computeMaxTimeStep(maxCo, prevDt) : R.mp->computeMaxTimeStep(maxCo, prevDt);
+}
+
+// any registered field by its reference name (Solver::scalarField / vectorField: "gamma", "rho", "mu", "beta", "kappa",
+// "gammaTilde", "u", "sg", "fst", "n", "rhoU", "gradgamma", ...): comp < 0 = scalar field, 0 / 1 = component of a
+// vector field; faces != 0 = face values; set != 0 writes buf into the field.  Returns the length.
+long rfv_fs_any_field(void *fsHandle, const char *name, int comp, int faces, double *buf, int set) {
+  return guarded([&]() -> long {
+    RefFs &R = *static_cast<RefFs *>(fsHandle);
+    const FiniteVolumeGrid2D &g = *R.g;
+    if (comp < 0) {
+      std::shared_ptr<ScalarFiniteVolumeField> f = R.solver().scalarField(name);
+      if (!f) throw Exception("rfv_fs_any_field", "name", std::string("no scalar field \"") + name + "\"");
+      if (faces) { for (const Face &fc : g.faces()) { if (!buf) break; if (set) (*f)(fc) = buf[fc.id()]; else buf[fc.id()] = (*f)(fc); } return (long)g.nFaces(); }
+      for (const Cell &c : g.cells()) { if (!buf) break; if (set) (*f)(c) = buf[c.id()]; else buf[c.id()] = (*f)(c); }
+      return (long)g.nCells();
+    }
+    std::shared_ptr<VectorFiniteVolumeField> f = R.solver().vectorField(name);
+    if (!f) throw Exception("rfv_fs_any_field", "name", std::string("no vector field \"") + name + "\"");
+    if (faces) {
+      for (const Face &fc : g.faces()) { if (!buf) break; Vector2D &v = (*f)(fc); if (set) (comp ? v.y : v.x) = buf[fc.id()]; else buf[fc.id()] = comp ? v.y : v.x; }
+      return (long)g.nFaces();
+    }
+    for (const Cell &c : g.cells()) { if (!buf) break; Vector2D &v = (*f)(c); if (set) (comp ? v.y : v.x) = buf[c.id()]; else buf[c.id()] = comp ? v.y : v.x; }
+    return (long)g.nCells();
+  });
 }
 
 // field arrays in the oracle's naming: ux uy ufx ufy p pf gpx gpy gpfx gpfy ; set != 0 writes `buf` into the field
 long rfv_fs_field(void *fsHandle, const char *name, double *buf, int set) {
   return guarded([&]() -> long {
     RefFs &R = *static_cast<RefFs *>(fsHandle);
+    if (!R.fs) throw Exception("rfv_fs_field", "kind", "use rfv_fs_any_field on a multiphase solver");
     OpenFracStep &fs = *R.fs;
     const FiniteVolumeGrid2D &g = *R.g;
     const std::string nm(name);
@@ -302,8 +367,11 @@ long rfv_fs_field(void *fsHandle, const char *name, double *buf, int set) {
 // rowPtr (n+1), colInd / vals (rowPtr[n], -1 padded), b = -rhs_ (n).  NULL pointers: sizes only (n, nnz).
 long rfv_fs_handoff(void *fsHandle, const char *which, int *rowPtr, int *colInd, double *vals, double *b, long *nnz) {
   return guarded([&]() -> long {
-    OpenFracStep &fs = *static_cast<RefFs *>(fsHandle)->fs;
-    std::shared_ptr<SparseMatrixSolver> sp = std::string(which) == "uEqn" ? fs.uEqn_.sparseSolver() : fs.pEqn_.sparseSolver();
+    RefFs &R = *static_cast<RefFs *>(fsHandle);
+    const std::string w(which);
+    std::shared_ptr<SparseMatrixSolver> sp;
+    if (R.fs) sp = w == "uEqn" ? R.fs->uEqn_.sparseSolver() : R.fs->pEqn_.sparseSolver();
+    else sp = w == "uEqn" ? R.mp->uEqn_.sparseSolver() : w == "pEqn" ? R.mp->pEqn_.sparseSolver() : R.mp->gammaEqn_.sparseSolver();
     RecordingSolver *s = static_cast<RecordingSolver *>(sp.get());
     if (nnz) *nnz = (long)s->colInd_.size();
     if (rowPtr) std::copy(s->rowPtr_.begin(), s->rowPtr_.end(), rowPtr);

@@ -171,9 +171,35 @@ template <class P> detail::Nearest<P> nearest(const P &p, std::size_t k) { retur
 template <class G, class B> AndQ<WithinQ<G>, B> operator&&(const WithinQ<G> &a, const B &b) { return {a, b}; }
 template <class G, class B> AndQ<CoveredQ<G>, B> operator&&(const CoveredQ<G> &a, const B &b) { return {a, b}; }
 
+// a query's results travel with its begin iterator (qbegin / qend are evaluated in unspecified order when both
+// are arguments of one call); the end iterator is a sentinel
+template <class Value> class query_iterator {
+public:
+  typedef std::forward_iterator_tag iterator_category;
+  typedef Value value_type;
+  typedef std::ptrdiff_t difference_type;
+  typedef const Value *pointer;
+  typedef const Value &reference;
+  query_iterator() : i_(0) {}
+  explicit query_iterator(std::shared_ptr<std::vector<Value>> r) : r_(std::move(r)), i_(0) {}
+  reference operator*() const { return (*r_)[i_]; }
+  pointer operator->() const { return &(*r_)[i_]; }
+  query_iterator &operator++() { ++i_; return *this; }
+  query_iterator operator++(int) { query_iterator t(*this); ++i_; return t; }
+  bool at_end() const { return !r_ || i_ >= r_->size(); }
+  bool operator==(const query_iterator &o) const {
+    if (at_end() || o.at_end()) return at_end() && o.at_end();
+    return r_ == o.r_ && i_ == o.i_;
+  }
+  bool operator!=(const query_iterator &o) const { return !(*this == o); }
+private:
+  std::shared_ptr<std::vector<Value>> r_;
+  std::size_t i_;
+};
+
 template <class Value, class Params, class Getter, class Equal> class rtree {
 public:
-  typedef typename std::vector<Value>::const_iterator const_query_iterator;
+  typedef query_iterator<Value> const_query_iterator;
   void insert(const Value &v) { items_.push_back(v); }
   template <class It> void insert(It b, It e) { for (; b != e; ++b) items_.push_back(Value(*b)); }
   template <class T> std::size_t remove(const T &v) {
@@ -186,23 +212,22 @@ public:
   void clear() { items_.clear(); }
   std::size_t size() const { return items_.size(); }
   template <class Q> const_query_iterator qbegin(const Q &q) const {
-    result_.clear();
-    run(q);
-    return result_.begin();
+    auto out = std::make_shared<std::vector<Value>>();
+    run(q, *out);
+    return const_query_iterator(out);
   }
-  const_query_iterator qend() const { return result_.end(); }
+  const_query_iterator qend() const { return const_query_iterator(); }
 
 private:
-  template <class T> static const T &deref(const T &v) { return v; }
   template <class P, class Item> bool keep(const WithinQ<P> &q, const Item &it) const { return boost::geometry::within(Getter()(it), q.g); }
   template <class P, class Item> bool keep(const CoveredQ<P> &q, const Item &it) const { return boost::geometry::covered_by(Getter()(it), q.g); }
   template <class F, class Item> bool keep(const SatisfiesQ<F> &q, const Item &it) const { return q.f(it); }
   template <class A, class B, class Item> bool keep(const AndQ<A, B> &q, const Item &it) const { return keep(q.a, it) && keep(q.b, it); }
-  template <class Q> void run(const Q &q) const {
+  template <class Q> void run(const Q &q, std::vector<Value> &out) const {
     for (const Value &v : items_)
-      if (keep(q, v.get())) result_.push_back(v);
+      if (keep(q, v.get())) out.push_back(v);
   }
-  template <class P> void run(const detail::Nearest<P> &q) const {
+  template <class P> void run(const detail::Nearest<P> &q, std::vector<Value> &out) const {
     std::vector<std::pair<double, std::size_t>> d;
     for (std::size_t i = 0; i < items_.size(); ++i) {
       const auto c = Getter()(items_[i].get());
@@ -210,10 +235,9 @@ private:
     }
     const std::size_t k = std::min(q.k, d.size());
     std::partial_sort(d.begin(), d.begin() + k, d.end());
-    for (std::size_t i = 0; i < k; ++i) result_.push_back(items_[d[i].second]);
+    for (std::size_t i = 0; i < k; ++i) out.push_back(items_[d[i].second]);
   }
   std::vector<Value> items_;
-  mutable std::vector<Value> result_;
 };
 }  // namespace index
 }}  // namespace boost::geometry

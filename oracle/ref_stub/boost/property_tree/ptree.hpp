@@ -79,9 +79,10 @@ public:
   }
   template <class T> T get_value() const { return convert<T>(data_); }
   template <class T> T get(const std::string &path) const { return convert<T>(get_child(path).data_); }
-  template <class T> T get(const std::string &path, const T &def) const {
+  template <class T> T get(const std::string &path, const T &def) const {   // default when absent OR untranslatable
     const ptree *t = walk(path);
-    return t ? convert<T>(t->data_) : def;
+    if (!t) return def;
+    try { return convert<T>(t->data_); } catch (const ptree_bad_data &) { return def; }
   }
   std::string get(const std::string &path, const char *def) const { return get<std::string>(path, std::string(def)); }
   ptree &put(const std::string &path, const std::string &value) {

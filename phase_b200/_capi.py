@@ -59,6 +59,7 @@ SIGNATURES = {
     "phb_solver_get_x": (ci, [vp, pd, ci]),
     "phb_solver_spmv": (ci, [vp, pd, pd, ci]),
     "phb_solver_time_spmv": (ci, [vp, ci, pd]),
+    "phb_solver_apply_preconditioner": (ci, [vp, pd, pd, ci]),
     "phb_solver_bytes": (ci, [vp, pd]),
     "phb_solver_amg_info": (ci, [vp, pd]),
     "phb_solver_time_amg": (ci, [vp, ci, pd]),
@@ -115,6 +116,14 @@ SIGNATURES = {
     "phb_fs_assemble_p": (ci, [vp, cd]),
     "phb_fs_step": (ci, [vp, cd, pd]),
     "phb_fs_max_time_step": (ci, [vp, cd, cd, cd, pd]),
+    "phb_mp_create": (ci, [vp, cd, cd, cd, cd, cd, cd, cd, cd, pvp]),
+    "phb_mp_destroy": (ci, [vp]),
+    "phb_mp_field": (vp, [vp, cs]),
+    "phb_mp_eqn": (vp, [vp, cs]),
+    "phb_mp_solver": (vp, [vp, cs]),
+    "phb_mp_setup": (ci, [vp, cs, cd]),
+    "phb_mp_initialize": (ci, [vp]),
+    "phb_mp_step": (ci, [vp, cd, pd]),
     "phb_piso_create": (ci, [vp, cd, cd, pvp]),
     "phb_piso_destroy": (ci, [vp]),
     "phb_piso_field": (vp, [vp, cs]),

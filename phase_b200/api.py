@@ -248,8 +248,10 @@ class SparseMatrixSolver:
         check(rc)
         return self._err
 
-    def x(self):
-        out = np.zeros(self._n, np.float64)
+    def x(self, out=None):
+        """the solution (M/SparseMatrixSolver.h: x(i)); `out` = caller's array to fill instead of a new one"""
+        if out is None:
+            out = np.zeros(self._n, np.float64)
         check(self.L.phb_solver_get_x(self.h, _dp(out), self._n))
         return out
 
@@ -267,6 +269,13 @@ class SparseMatrixSolver:
         y = np.zeros_like(x)
         check(self.L.phb_solver_spmv(self.h, _dp(x), _dp(y), len(x)))
         return y
+
+    def applyPreconditioner(self, r):
+        """z = M^-1 r with the multigrid hierarchy of the last solve (owned rows)"""
+        r = np.ascontiguousarray(r, np.float64)
+        z = np.zeros_like(r)
+        check(self.L.phb_solver_apply_preconditioner(self.h, _dp(r), _dp(z), len(r)))
+        return z
 
     def time_spmv(self, reps):
         ms = C.c_double()
@@ -519,6 +528,46 @@ class FractionalStep:
     def close(self):
         if self.h:
             self.L.phb_fs_destroy(self.h)
+            self.h = None
+
+
+class FractionalStepMultiphase:
+    """US/FractionalStepMultiphase: device-resident VOF time step (CICSAM + CELESTE surface tension), config 4.
+    Set `gamma` (cells and faces) and the boundary conditions, configure the three solvers, then initialize()."""
+
+    FIELDS = {"u": 2, "p": 1, "gradP": 2, "gamma": 1, "gradGamma": 2, "rho": 1, "mu": 1, "beta": 1, "sg": 2, "fst": 2,
+              "kappa": 1, "gammaTilde": 1, "gradGammaTilde": 2, "n": 2, "gradRho": 2}
+
+    def __init__(self, grid, rho1, rho2, mu1, mu2, sigma, g=(0.0, 0.0), smoothingKernelRadius=1.0, **keys):
+        self.grid, self.L = grid, grid.L
+        h = C.c_void_p()
+        check(self.L.phb_mp_create(grid.h, rho1, rho2, mu1, mu2, sigma, float(g[0]), float(g[1]), smoothingKernelRadius,
+                                   C.byref(h)))
+        self.h = h
+        for name, nc in self.FIELDS.items():
+            setattr(self, name, FiniteVolumeField(grid, nc, name, handle=C.c_void_p(self.L.phb_mp_field(h, name.encode()))))
+        for e, fld in (("gammaEqn", self.gamma), ("uEqn", self.u), ("pEqn", self.p)):
+            eq = FiniteVolumeEquation(fld, e, handle=C.c_void_p(self.L.phb_mp_eqn(h, e.encode())))
+            eq.solver = SparseMatrixSolver(grid.comm, handle=C.c_void_p(self.L.phb_mp_solver(h, e.encode())))
+            setattr(self, e, eq)
+        for k, v in keys.items():
+            self.setup(k, v)
+
+    def setup(self, key, value):
+        check(self.L.phb_mp_setup(self.h, key.encode(), float(value)))
+
+    def initialize(self):
+        check(self.L.phb_mp_initialize(self.h))
+
+    def solve(self, dt):
+        st = (C.c_double * 8)()
+        check(self.L.phb_mp_step(self.h, dt, st))
+        return dict(itersGamma=int(st[0]), itersU=int(st[1]), itersP=int(st[2]), errorGamma=st[3], errorU=st[4],
+                    errorP=st[5], maxDivergence=st[6], maxCourant=st[7])
+
+    def close(self):
+        if self.h:
+            self.L.phb_mp_destroy(self.h)
             self.h = None
 
 

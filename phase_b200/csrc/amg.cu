@@ -958,6 +958,60 @@ __global__ void k_amg_pack(int nSend, int nc, int ld, const int *__restrict__ se
   for (int c = 0; c < nc; ++c) buf[(size_t)c * nSend + i] = x[(size_t)c * ld + src];
 }
 
+// ---- ghost refresh over NVLink peer memory (one CTA): gather my send list of x, store it straight into the
+// ghost segments of the peers' copy of the same level vector, publish an epoch at each peer, wait for the epochs
+// of the peers I receive from.  sendIdx == nullptr: contiguous segment [sendOff, sendOff + sendCnt) (tail gather).
+// Safety of re-using a ghost segment: between two refreshes of the same vector every rank passes a refresh or
+// reduction involving all its neighbours (other levels, the tail gather, the Krylov all-reduces), which it can
+// only complete after those neighbours have issued -- in stream order -- the kernels that read the old ghosts.
+struct AmgPeerView {
+  char *block;
+  char *peer[kMaxPeers];
+  int rank, nProcs;
+};
+__device__ __forceinline__ unsigned long long *amg_flag(char *block, int ch, int src) {
+  return reinterpret_cast<unsigned long long *>(block) + (size_t)ch * kMaxPeers + src;
+}
+__device__ __forceinline__ unsigned long long *amg_epoch(char *block, int ch) {
+  return reinterpret_cast<unsigned long long *>(block + kAmgPeerChannels * kMaxPeers * sizeof(unsigned long long)) + ch;
+}
+template <typename T>
+__global__ void __launch_bounds__(1024)
+k_amg_peer_halo(AmgPeerView pv, int ch, AmgPeerLevel L, int vec, const T *__restrict__ x, int nc, int ld,
+                const int *__restrict__ sendIdx, const KrylovSums *S, int maxIters) {
+  if (S && krylov_done(S, maxIters)) return;
+  __shared__ unsigned long long se;
+  if (threadIdx.x == 0) {
+    unsigned long long *ep = amg_epoch(pv.block, ch);
+    se = *ep + 1;
+    *ep = se;
+  }
+  __syncthreads();
+  const unsigned long long e = se;
+  for (int q = 0; q < pv.nProcs; ++q) {
+    const int cnt = L.sendCnt[q];
+    if (q == pv.rank || cnt == 0) continue;
+    T *dst = reinterpret_cast<T *>(pv.peer[q] + L.vecOff[vec][q]);
+    const int off = L.sendOff[q];
+    for (int j = threadIdx.x; j < cnt * nc; j += blockDim.x) {
+      const int c = j / cnt, i = j - c * cnt;
+      const int src = sendIdx ? sendIdx[off + i] : off + i;
+      dst[(size_t)c * L.ld[q] + L.recvOff[q] + i] = x[(size_t)c * ld + src];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < pv.nProcs && t != pv.rank) {
+    if (L.sendCnt[t] > 0) st_release_sys(amg_flag(pv.peer[t], ch, pv.rank), e);
+    if (L.recvCnt[t] > 0) {
+      const unsigned long long *f = amg_flag(pv.block, ch, t);
+      while (ld_acquire_sys(f) < e) {}
+    }
+  }
+  __syncthreads();
+}
+
 // max relative deviation of `a` from ratio * ref over the slots, ratio = a[first] / ref[first]
 __global__ void __launch_bounds__(kThreads)
 k_amg_changed(long long nSlots, const double *__restrict__ a, const double *__restrict__ ref, int first,
@@ -1115,6 +1169,91 @@ int finish_level(phb_solver *s, AmgLevel &L, const HostLevel &h, int ld, bool ha
   return PHB_OK;
 }
 
+// Peer-memory ghost refreshes of the distributed levels: move the vectors peers write into (x, x2 per distributed
+// level, the gathered right-hand side of the first replicated level) into one CUDA-IPC block, exchange handles
+// and layouts, open the peers' blocks.  Collective: every rank calls it with the same level structure.
+template <typename T>
+int setup_peer(phb_solver *s, Exchanger &ex) {
+  phb_ctx *c = s->ctx;
+  AmgData &D = s->amg;
+  const int NP = c->nProcs, me = c->rank, nD = D.nDist;
+  auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  std::vector<size_t> off(2 * nD + 1);
+  size_t total = kAmgPeerHeaderBytes;
+  for (int l = 0; l < nD; ++l) {
+    const size_t vb = align((size_t)D.lev[l]->ld * s->nComp * sizeof(T));
+    off[2 * l] = total; total += vb;
+    off[2 * l + 1] = total; total += vb;
+  }
+  AmgLevel &TL = *D.lev[nD];
+  off[2 * nD] = total;
+  total += align((size_t)TL.ld * s->nComp * sizeof(T));
+  std::unique_ptr<AmgPeer> P(new AmgPeer());
+  P->bytes = total;
+  PHB_CUDA(cudaMalloc((void **)&P->block, total));
+  PHB_CUDA(cudaMemset(P->block, 0, total));
+  cudaIpcMemHandle_t h;
+  PHB_CUDA(cudaIpcGetMemHandle(&h, P->block));
+  std::vector<char> blob;
+  blob.insert(blob.end(), (const char *)&h, (const char *)&h + sizeof(h));
+  put<int>(blob, nD);
+  for (int l = 0; l < nD; ++l) {
+    put<unsigned long long>(blob, off[2 * l]);
+    put<unsigned long long>(blob, off[2 * l + 1]);
+    put<int>(blob, D.lev[l]->ld);
+    for (int q = 0; q < NP; ++q) put<int>(blob, D.lev[l]->recvOff[q]);
+  }
+  put<unsigned long long>(blob, off[2 * nD]);
+  put<int>(blob, TL.ld);
+  std::vector<std::vector<char>> all;
+  PHB_CHECK(ex.allgatherv(blob, all));
+  P->lev.assign(nD, AmgPeerLevel());
+  memset(P->lev.data(), 0, nD * sizeof(AmgPeerLevel));
+  memset(&P->tail, 0, sizeof(AmgPeerLevel));
+  for (int q = 0; q < NP; ++q) {
+    const char *p = all[q].data();
+    cudaIpcMemHandle_t hq;
+    memcpy(&hq, p, sizeof(hq));
+    p += sizeof(hq);
+    if (q == me) P->peer[q] = P->block;
+    else {
+      void *m = nullptr;
+      PHB_CUDA(cudaIpcOpenMemHandle(&m, hq, cudaIpcMemLazyEnablePeerAccess));
+      P->peer[q] = (char *)m;
+      P->opened[q] = true;
+    }
+    const int nq = take<int>(p);
+    PHB_REQUIRE(nq == nD, "amg: rank %d holds %d distributed levels, rank %d holds %d", q, nq, me, nD);
+    for (int l = 0; l < nD; ++l) {
+      AmgPeerLevel &L = P->lev[l];
+      L.vecOff[0][q] = take<unsigned long long>(p);
+      L.vecOff[1][q] = take<unsigned long long>(p);
+      L.ld[q] = take<int>(p);
+      for (int r = 0; r < NP; ++r) {
+        const int ro = take<int>(p);
+        if (r == me) L.recvOff[q] = ro;      // where my values land in rank q's vector
+      }
+      L.sendOff[q] = D.lev[l]->sendOff[q]; L.sendCnt[q] = D.lev[l]->sendCnt[q]; L.recvCnt[q] = D.lev[l]->recvCnt[q];
+    }
+    P->tail.vecOff[0][q] = take<unsigned long long>(p);
+    P->tail.ld[q] = take<int>(p);
+    P->tail.recvOff[q] = D.tailOff[me];
+    P->tail.sendOff[q] = D.tailOff[me];
+    P->tail.sendCnt[q] = q == me ? 0 : D.tailOff[me + 1] - D.tailOff[me];
+    P->tail.recvCnt[q] = q == me ? 0 : D.tailCnt[q];
+  }
+  // the level vectors now live inside the block (zero-filled: ghost and padding entries are finite)
+  auto words = [](size_t bytes) { return (bytes + 7) / 8; };
+  for (int l = 0; l < nD; ++l) {
+    const size_t vb = (size_t)D.lev[l]->ld * s->nComp * sizeof(T);
+    D.lev[l]->x.attach(reinterpret_cast<double *>(P->block + off[2 * l]), words(vb));
+    D.lev[l]->x2.attach(reinterpret_cast<double *>(P->block + off[2 * l + 1]), words(vb));
+  }
+  TL.b.attach(reinterpret_cast<double *>(P->block + off[2 * nD]), words((size_t)TL.ld * s->nComp * sizeof(T)));
+  D.peer = std::move(P);
+  return PHB_OK;
+}
+
 // hierarchy spanning the ranks: level 0 = the solver's matrix with its ghost columns and the mesh's halo lists
 template <typename T>
 int rebuild_dist_t(phb_solver *s) {
@@ -1147,6 +1286,7 @@ int rebuild_dist_t(phb_solver *s) {
   PHB_CHECK(build_dist_hierarchy(ex, std::move(A0), std::move(h0), std::move(gid), D.theta, D.coarsest, D.tailRows,
                                  4. / 3., H));
   D.lev.clear();
+  D.peer.reset();
   D.nDist = (int)H.dist.size();
   for (int l = 0; l < D.nDist; ++l) {
     std::unique_ptr<AmgLevel> L(new AmgLevel());
@@ -1181,6 +1321,7 @@ int rebuild_dist_t(phb_solver *s) {
   D.nCoarse = TH.lev.back().A.n;
   D.denseCoarse = !TH.coarseInv.empty();
   if (D.denseCoarse) PHB_CHECK(D.coarseInv.upload(TH.coarseInv, c->stream));
+  if (c->peer.enabled && NP <= kMaxPeers && 2 * D.nDist + 1 <= kAmgPeerChannels) PHB_CHECK(setup_peer<T>(s, ex));
   PHB_CHECK(D.refVals.alloc((size_t)P->nSlots));
   PHB_CUDA(cudaMemcpyAsync(D.refVals.p, s->dVals, (size_t)P->nSlots * sizeof(double), cudaMemcpyDeviceToDevice,
                            c->stream));
@@ -1226,6 +1367,12 @@ template <typename T> struct Cycle {
     AmgLevel &V = *D.lev[l];
     if (!V.dist) return PHB_OK;
     phb_ctx *c = s->ctx;
+    if (D.peer) {
+      const int vec = x == as<T>(V.x) ? 0 : 1;
+      PHB_LAUNCH(c, (k_amg_peer_halo<T>), 1, 1024, 0, peer_view(), 2 * l + vec, D.peer->lev[l], vec, (const T *)x, nc, V.ld,
+                 (const int *)V.sendIdx.p, S, s->maxIters);
+      return PHB_OK;
+    }
     T *buf = as<T>(V.sendBuf);
     if (V.nSend)
       PHB_LAUNCH(c, (k_amg_pack<T>), (V.nSend + 255) / 256, 256, 0, V.nSend, nc, V.ld, V.sendIdx.p, (const T *)x, buf, S,
@@ -1236,8 +1383,21 @@ template <typename T> struct Cycle {
     return PHB_OK;
   }
   // first replicated level: every rank contributes its segment of the right-hand side
+  AmgPeerView peer_view() const {
+    AmgPeerView v;
+    v.block = D.peer->block;
+    for (int q = 0; q < kMaxPeers; ++q) v.peer[q] = D.peer->peer[q];
+    v.rank = s->ctx->rank;
+    v.nProcs = s->ctx->nProcs;
+    return v;
+  }
   int gather_tail(T *b) {
     AmgLevel &V = *D.lev[D.nDist];
+    if (D.peer) {
+      PHB_LAUNCH(s->ctx, (k_amg_peer_halo<T>), 1, 1024, 0, peer_view(), 2 * D.nDist, D.peer->tail, 0, (const T *)b, nc, V.ld,
+                 (const int *)nullptr, S, s->maxIters);
+      return PHB_OK;
+    }
     for (int k = 0; k < nc; ++k)
       PHB_CHECK(comm_exchange_bytes(s->ctx, b + (size_t)k * V.ld, D.tailSendOff.data(), D.tailSendCnt.data(),
                                     b + (size_t)k * V.ld, D.tailOff.data(), D.tailCnt.data(), sizeof(T)));

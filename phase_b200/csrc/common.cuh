@@ -96,6 +96,7 @@ constexpr int kSliceRows = 32;  // SELL slice height = one warp, lane <-> row
 }  // namespace phb
 
 struct ncclComm;
+namespace phb { struct PinnedStage; }
 
 // Peer-memory communication over NVLink (CUDA IPC, one arena per rank, identical
 // layout on every rank): reductions and halos inside the Krylov loop are done by
@@ -128,6 +129,7 @@ struct phb_ctx {
   PeerComm peer;
   // live solvers: their CUDA graphs may hold NCCL nodes, which must be gone before the communicator is
   std::vector<struct phb_solver *> solvers;
+  phb::PinnedStage *stage = nullptr;   // pageable <-> device transfers of Seam 1 (hostcopy.cuh), created on first use
   // first refused kernel launch since the last status check (PHB_LAUNCH)
   cudaError_t launchError = cudaSuccess;
   char launchWhere[160] = "";

@@ -4,6 +4,7 @@
 
 #include "comm.cuh"
 #include "common.cuh"
+#include "hostcopy.cuh"
 
 namespace phb {
 static thread_local char g_err[1024] = "";
@@ -63,6 +64,7 @@ int phb_ctx_destroy(phb_ctx *c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->commStream) cudaStreamDestroy(c->commStream);
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->stage) { c->stage->release(); delete c->stage; }
   delete c;
   return PHB_OK;
 }

@@ -14,6 +14,7 @@
 #include <cmath>
 
 #include "comm.cuh"
+#include "hostcopy.cuh"
 #include "kernels.cuh"
 #include "peerdev.cuh"
 #include "solver.cuh"
@@ -749,10 +750,13 @@ int phb_solver_set_csr(phb_solver *s, int nRows, const int *rowPtr, const int *c
   PHB_REQUIRE(s && rowPtr && colInd && vals && nRows > 0, "phb_solver_set_csr: bad argument");
   phb_ctx *c = s->ctx;
   const long long nnzIn = rowPtr[nRows];
+  // exact comparison with the cached pattern (value-dependent patterns are the rule behind this seam: `+=` drops
+  // exact zeros), spread over the host cores: 96 MB at 4M rows
   const bool samePattern = s->haveMatrix && (int)s->cRowPtr.size() == nRows + 1 &&
                            (long long)s->cColInd.size() == nnzIn &&
-                           memcmp(s->cRowPtr.data(), rowPtr, (nRows + 1) * sizeof(int)) == 0 &&
-                           memcmp(s->cColInd.data(), colInd, nnzIn * sizeof(int)) == 0;
+                           parallel_equal(s->cRowPtr.data(), rowPtr, (nRows + 1) * sizeof(int)) &&
+                           parallel_equal(s->cColInd.data(), colInd, nnzIn * sizeof(int));
+  if (!c->stage) c->stage = new PinnedStage();
   if (!samePattern) {
     s->cRowPtr.assign(rowPtr, rowPtr + nRows + 1);
     s->cColInd.assign(colInd, colInd + nnzIn);
@@ -825,7 +829,8 @@ int phb_solver_set_csr(phb_solver *s, int nRows, const int *rowPtr, const int *c
     s->ilu.src = nullptr;
     s->amg.built = false;
   }
-  PHB_CHECK(s->csrVals.upload(vals, (size_t)nnzIn, c->stream));
+  PHB_CHECK(s->csrVals.alloc((size_t)nnzIn));
+  PHB_CHECK(c->stage->upload(s->csrVals.p, vals, (size_t)nnzIn * sizeof(double), c->stream));
   PHB_LAUNCH(c, k_scatter_vals, grid_for(c, nnzIn), kThreads, 0, nnzIn, s->csr2slot.p, s->csrVals.p, s->ownVals.p);
   PHB_CUDA(cudaStreamSynchronize(c->stream));  // caller may free its vectors now
   s->haveMatrix = true;
@@ -864,7 +869,8 @@ int phb_solver_set_rhs(phb_solver *s, const double *b, int n) {
   PHB_REQUIRE(s && b, "phb_solver_set_rhs: NULL argument");
   PHB_REQUIRE(s->haveMatrix && s->pat == &s->own, "phb_solver_set_rhs: call phb_solver_set_csr first");
   PHB_REQUIRE(n == s->own.nRows, "phb_solver_set_rhs: size %d != rank %d", n, s->own.nRows);
-  PHB_CUDA(cudaMemcpyAsync(s->b.p, b, n * sizeof(double), cudaMemcpyHostToDevice, s->ctx->stream));
+  if (!s->ctx->stage) s->ctx->stage = new PinnedStage();
+  PHB_CHECK(s->ctx->stage->upload(s->b.p, b, (size_t)n * sizeof(double), s->ctx->stream));
   PHB_CUDA(cudaStreamSynchronize(s->ctx->stream));
   s->haveRhs = true;
   return PHB_OK;
@@ -874,7 +880,8 @@ int phb_solver_set_guess(phb_solver *s, const double *x0, int n) {
   PHB_REQUIRE(s && x0, "phb_solver_set_guess: NULL argument");
   PHB_REQUIRE(s->haveMatrix && s->pat == &s->own, "phb_solver_set_guess: call phb_solver_set_csr first");
   PHB_REQUIRE(n == s->own.nRows, "phb_solver_set_guess: size %d != rank %d", n, s->own.nRows);
-  PHB_CUDA(cudaMemcpyAsync(s->x.p, x0, n * sizeof(double), cudaMemcpyHostToDevice, s->ctx->stream));
+  if (!s->ctx->stage) s->ctx->stage = new PinnedStage();
+  PHB_CHECK(s->ctx->stage->upload(s->x.p, x0, (size_t)n * sizeof(double), s->ctx->stream));
   PHB_CUDA(cudaStreamSynchronize(s->ctx->stream));
   s->haveGuess = true;
   return PHB_OK;
@@ -894,9 +901,8 @@ int phb_solver_solve(phb_solver *s, int *iters, double *relres) {
   int rc = phb::solver_run(s, iters, relres);
   if (rc != PHB_OK) return rc;
   s->hostX.resize(s->own.nRows);
-  PHB_CUDA(cudaMemcpyAsync(s->hostX.data(), s->x.p, s->own.nRows * sizeof(double), cudaMemcpyDeviceToHost,
-                           s->ctx->stream));
-  PHB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  if (!s->ctx->stage) s->ctx->stage = new PinnedStage();
+  PHB_CHECK(s->ctx->stage->download(s->hostX.data(), s->x.p, (size_t)s->own.nRows * sizeof(double), s->ctx->stream));
   return PHB_OK;
   PHB_TRY_END
 }
@@ -904,7 +910,7 @@ int phb_solver_solve(phb_solver *s, int *iters, double *relres) {
 int phb_solver_get_x(const phb_solver *s, double *x, int n) {
   PHB_REQUIRE(s && x, "phb_solver_get_x: NULL argument");
   PHB_REQUIRE(n == (int)s->hostX.size(), "phb_solver_get_x: size %d != rank %d", n, (int)s->hostX.size());
-  memcpy(x, s->hostX.data(), n * sizeof(double));
+  parallel_memcpy(x, s->hostX.data(), (size_t)n * sizeof(double));
   return PHB_OK;
 }
 
@@ -920,6 +926,27 @@ int phb_solver_spmv(phb_solver *s, const double *x, double *y, int n) {
   PHB_CUDA(cudaMemcpyAsync(y, s->v.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
   PHB_CUDA(cudaStreamSynchronize(st));
   return PHB_OK;
+}
+
+// z = M^-1 r with the preconditioner of the last solve (hierarchy / factors as they stand), host vectors over the
+// owned rows: lets tests compare ONE application of the device V-cycle with a transcription of the same hierarchy
+int phb_solver_apply_preconditioner(phb_solver *s, const double *r, double *z, int n) {
+  PHB_TRY_BEGIN
+  PHB_REQUIRE(s && r && z, "phb_solver_apply_preconditioner: NULL argument");
+  PHB_REQUIRE(s->pat && s->dVals && s->lastIters >= 0 && s->ph.p && s->p.p,
+              "phb_solver_apply_preconditioner: solve once first");
+  PHB_REQUIRE(n == s->pat->nRows * s->nComp, "phb_solver_apply_preconditioner: size %d != %d", n, s->pat->nRows * s->nComp);
+  PHB_REQUIRE(s->precond == PHB_PC_AMG && s->amg.built, "phb_solver_apply_preconditioner: multigrid preconditioner only");
+  cudaStream_t st = s->ctx->stream;
+  const int nr = s->pat->nRows;
+  for (int c = 0; c < s->nComp; ++c)
+    PHB_CUDA(cudaMemcpyAsync(s->p.p + (size_t)c * s->ld, r + (size_t)c * nr, nr * sizeof(double), cudaMemcpyHostToDevice, st));
+  PHB_CHECK(amg_apply(s, s->p.p, s->ph.p, false));
+  for (int c = 0; c < s->nComp; ++c)
+    PHB_CUDA(cudaMemcpyAsync(z + (size_t)c * nr, s->ph.p + (size_t)c * s->ld, nr * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PHB_CUDA(cudaStreamSynchronize(st));
+  return launch_status(s->ctx);
+  PHB_TRY_END
 }
 
 int phb_solver_time_spmv(phb_solver *s, int reps, double *ms) {

@@ -82,6 +82,33 @@ struct AmgLevel {
   phb::DevBuf<double> sendBuf;
 };
 constexpr int kCoarseSweeps = 8;   // Jacobi sweeps on a coarsest level too large for a dense inverse
+
+// Ghost refreshes of the distributed multigrid levels over NVLink peer memory (amg.cu): the level vectors that
+// peers write into (x, x2 of every distributed level, the gathered right-hand side of the first replicated
+// level) live in ONE CUDA-IPC block per rank; one one-CTA kernel per refresh packs, stores into the peers'
+// blocks, raises an epoch flag there and waits for its own.
+constexpr int kAmgPeerChannels = 32;          // 2 per distributed level + 1 for the tail gather
+constexpr size_t kAmgPeerHeaderBytes = 4096;  // flags[channel][source] | local epochs[channel]
+struct AmgPeerLevel {                          // how to reach level l of every peer (by value into the kernels)
+  unsigned long long vecOff[2][kMaxPeers];    // byte offset of x / x2 inside peer q's block
+  int ld[kMaxPeers];                          // leading dimension of peer q's level vectors
+  int recvOff[kMaxPeers];                     // where MY values land in peer q's vector
+  int sendOff[kMaxPeers], sendCnt[kMaxPeers], recvCnt[kMaxPeers];
+};
+struct AmgPeer {
+  char *block = nullptr;
+  size_t bytes = 0;
+  char *peer[kMaxPeers] = {nullptr};
+  bool opened[kMaxPeers] = {false};
+  std::vector<AmgPeerLevel> lev;              // distributed levels
+  AmgPeerLevel tail;                          // gathered vector of the first replicated level (vecOff[0], ld)
+  ~AmgPeer() {
+    for (int q = 0; q < kMaxPeers; ++q)
+      if (opened[q] && peer[q]) cudaIpcCloseMemHandle(peer[q]);
+    if (block) cudaFree(block);
+  }
+};
+
 struct AmgData {
   std::vector<std::unique_ptr<AmgLevel>> lev;
   phb::DevBuf<double> coarseInv, refVals, chk;
@@ -91,6 +118,7 @@ struct AmgData {
   int nDist = 0;                            // leading distributed levels; level nDist is gathered on every rank
   long long tailRows = 200000;
   std::vector<int> tailOff, tailCnt, tailSendOff, tailSendCnt;
+  std::unique_ptr<AmgPeer> peer;            // set when the context has peer memory enabled (else NCCL send/recv)
   const SellPattern *src = nullptr;
   bool built = false, denseCoarse = false, stale = false, rebuildAlways = false;
   int nComp = 1, nCoarse = 0, nu = 1, coarsest = 1000, setups = 0, itersAfterSetup = -1;

@@ -49,8 +49,48 @@ def make(name, kind, nx, ny, w, h, K):
     print(name, "written")
 
 
+def make_bubble(name, nx, ny, w, h, K, dt):
+    """FractionalStepMultiphase::solve (US/FractionalStepMultiphase.cpp) from a smooth bubble under a free surface:
+    the state after initialize() and after K steps."""
+    from tests import mp_util as U
+    radius = 2.1 * w / nx
+    case = U.reference_case(R, nx, ny, w, h, radius)
+    g = R.Grid.rectilinear(case)
+    cx, cy = g.array("cellCx"), g.array("cellCy")
+    gamma0 = U.initial_gamma(cx, cy, w, h)
+    # face values as FiniteVolumeField::interpolateFaces would set them (distance weights; boundary = cell value)
+    fl, fr, fw = g.array("faceL"), g.array("faceR"), g.array("faceW")
+    gf = np.where(fr >= 0, fw * gamma0[fl] + (1.0 - fw) * gamma0[np.maximum(fr, 0)], gamma0[fl])
+    R.use_direct_solver()
+    fs = R.Multiphase(case, g)
+    fs.set_field("gamma", gamma0)
+    fs.set_field("gamma", gf, faces=True)
+    fs.initialize()
+    out = {"nx": nx, "ny": ny, "w": w, "h": h, "K": K, "dt": dt, "radius": radius, "gamma0": gamma0, "gamma0_faces": gf}
+    for k in ("rho", "mu", "kappa", "gammaTilde"):
+        out["init_" + k] = fs.field(k)
+    for k in ("n", "fst", "sg"):
+        out["init_" + k + "_x"], out["init_" + k + "_y"] = fs.field(k, 0), fs.field(k, 1)
+    for _ in range(K):
+        fs.step(dt)
+    for k in U.SCALARS:
+        out["field_" + k] = fs.field(k)
+    for k in U.VECTORS:
+        rn = U.REF_NAME.get(k, k)
+        out["field_" + k + "_x"], out["field_" + k + "_y"] = fs.field(rn, 0), fs.field(rn, 1)
+    out["field_uf_x"], out["field_uf_y"] = fs.field("u", 0, faces=True), fs.field("u", 1, faces=True)
+    for which in ("gammaEqn", "uEqn", "pEqn"):
+        rp, ci, va, b = fs.handoff(which)
+        out[which + "_rowPtr"], out[which + "_colInd"], out[which + "_vals"], out[which + "_b"] = rp, ci, va, b
+    out["maxDivergence"], out["maxCourant"] = fs.max_divergence(), fs.max_courant(dt)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    fs.close(); g.close(); case.close()
+    print(name, "written")
+
+
 if __name__ == "__main__":
     if not R.available():
         sys.exit("the reference FV library is not available (needs /root/reference)")
     for c in CASES:
         make(*c)
+    make_bubble("ref_bubble_24x48", 24, 48, 1.0, 2.0, 4, 1e-3)

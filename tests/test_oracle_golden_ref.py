@@ -10,7 +10,7 @@ import pytest
 import oracle as O
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-GOLDEN = sorted(glob.glob(os.path.join(HERE, "golden", "ref_*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(HERE, "golden", "ref_cavity_*.npz")))
 INT_KEYS = ["cptr", "cind", "faceN1", "faceN2", "faceL", "faceR", "ilPtr", "ilFace", "ilCell", "blPtr", "blFace", "dlPtr", "dlCell"]
 
 
