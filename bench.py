@@ -93,9 +93,12 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ workload
 def block_layout(nprocs):
-    """px x py blocks, as square as possible (1 -> 1x1, 2 -> 1x2, 4 -> 2x2, 8 -> 2x4)."""
+    """px x py blocks, as square as possible, the extra factor of two going to y (1 -> 1x1, 2 -> 1x2, 4 -> 2x2,
+    8 -> 2x4): interfaces parallel to the row-major cell numbering cost the rank-local aggregation of the multigrid
+    setup fewer iterations than interfaces across it (4M cells, pEqn_: 11 vs 16 iterations on 2 ranks;
+    tools/proto/dist_iters.py)."""
     px = 1
-    while px * px * 2 <= nprocs and nprocs % (px * 2) == 0:
+    while px * px * 4 <= nprocs and nprocs % (px * 2) == 0:
         px *= 2
     return px, nprocs // px
 

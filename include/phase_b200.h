@@ -282,6 +282,15 @@ int phb_assemble_laplacian(phb_eqn *e, double gammaConst,
                            double theta, double sign);
 int phb_assemble_src(phb_eqn *e, const phb_field *f, double sign);
 int phb_assemble_src_div(phb_eqn *e, const phb_field *u, double sign);
+/* cell-group overloads (the immersed-boundary modules assemble on a CellGroup): fv::ddt(field, dt, cells)
+ * (UD/TimeDerivative.h:50-62) and src::div(field, cells) (UD/Source.cpp:5-21); `cells` = reference cell ids */
+int phb_assemble_ddt_cells(phb_eqn *e, const phb_field *phi, double dt, double sign, int nCells, const int *cells);
+int phb_assemble_src_div_cells(phb_eqn *e, const phb_field *u, double sign, int nCells, const int *cells);
+/* src::laplacian (UD/Source.cpp:27-75): rhs += sign * sum_links Gamma g_f (phi_nb - phi_P) (boundary links: phi_f).
+ * gammaField NULL: scalar Gamma.  gammaField given: Gamma_f from the field's faces (the reference's field overload,
+ * :50-75, indexes a one-component index map out of bounds and cannot be run; its evident intent is built). */
+int phb_assemble_src_laplacian(phb_eqn *e, double gammaConst, const phb_field *gammaField, const phb_field *phi,
+                               double sign);
 /* CICSAM (UD/Cicsam.cpp): face weights beta_f (:19-66) into beta's FACE values,
  * cicsam::div(u, gamma, beta, theta) (:89-138) accumulated with sign, and the
  * density-weighted momentum flux rhoU_f (:69-87) into rhoU's face values. */

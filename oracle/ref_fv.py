@@ -51,6 +51,12 @@ def lib():
         L.rfv_fs_initialize.argtypes = [vp]
         L.rfv_fs_any_field.restype = C.c_long
         L.rfv_fs_any_field.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int]
+        L.rfv_src_laplacian_scalar.restype = C.c_long
+        L.rfv_src_laplacian_scalar.argtypes = [vp, C.c_double, C.POINTER(C.c_double)]
+        L.rfv_src_div_cells.restype = C.c_long
+        L.rfv_src_div_cells.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.rfv_ddt_cells.restype = C.c_long
+        L.rfv_ddt_cells.argtypes = [vp, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.rfv_fs_close.argtypes = [vp]
         L.rfv_fs_step.restype = C.c_long
         L.rfv_fs_step.argtypes = [vp, C.c_double]
@@ -234,6 +240,28 @@ class FracStep:
 
     def initialize(self):
         _check(lib().rfv_fs_initialize(self.h))
+
+    # ---- operator probes on u_, p_, co_ (the reference's own src:: / fv:: functions)
+    def src_laplacian(self, gamma):
+        """src::laplacian(Scalar gamma, p_) (UD/Source.cpp:27-48); the field overload (:50-75) cannot be run: it
+        indexes the scalar index map out of bounds"""
+        out = np.zeros(self.N)
+        _check(lib().rfv_src_laplacian_scalar(self.h, float(gamma), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def src_div_cells(self, cells):
+        c = np.ascontiguousarray(cells, np.int32)
+        out = np.zeros(self.N)
+        _check(lib().rfv_src_div_cells(self.h, len(c), c.ctypes.data_as(C.POINTER(C.c_int)), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def ddt_cells(self, dt, cells):
+        """(diagonal, rhs_) of fv::ddt(p_, dt, cells) after p_.savePreviousTimeStep"""
+        c = np.ascontiguousarray(cells, np.int32)
+        d, r = np.zeros(self.N), np.zeros(self.N)
+        _check(lib().rfv_ddt_cells(self.h, dt, len(c), c.ctypes.data_as(C.POINTER(C.c_int)),
+                                   d.ctypes.data_as(C.POINTER(C.c_double)), r.ctypes.data_as(C.POINTER(C.c_double))))
+        return d, r
 
     def max_divergence(self):
         return lib().rfv_fs_max_divergence(self.h)

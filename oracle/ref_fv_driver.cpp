@@ -23,6 +23,8 @@
 #include "FiniteVolumeGrid2D/StructuredRectilinearGrid.h"
 #include "Solvers/FractionalStep.h"
 #include "Solvers/FractionalStepMultiphase.h"
+#include "FiniteVolume/Discretization/Source.h"
+#include "FiniteVolume/Discretization/TimeDerivative.h"
 
 // ---- CGNS restart reader: never reached (the oracle does not restart)
 CgnsFile::CgnsFile(const std::string &, Mode) { throw Exception("CgnsFile", "CgnsFile", "not available in the oracle build"); }
@@ -360,6 +362,46 @@ long rfv_fs_field(void *fsHandle, const char *name, double *buf, int set) {
       return (long)g.nFaces();
     }
     throw Exception("rfv_fs_field", "name", "unknown field \"" + nm + "\"");
+  });
+}
+
+// ---- operator probes on the fields of a FractionalStep (u_, p_, co_): the reference's own src:: / fv:: functions
+// src::laplacian(Scalar gamma, p_) -> out[N]   (UD/Source.cpp:27-48)
+long rfv_src_laplacian_scalar(void *fsHandle, double gamma, double *out) {
+  return guarded([&]() -> long {
+    OpenFracStep &fs = *static_cast<RefFs *>(fsHandle)->fs;
+    Vector v = src::laplacian(gamma, fs.p_);
+    std::copy(v.data().begin(), v.data().end(), out);
+    return (long)v.size();
+  });
+}
+// src::div(u_, cells) -> out[N]   (UD/Source.cpp:5-21)
+long rfv_src_div_cells(void *fsHandle, int nCells, const int *cells, double *out) {
+  return guarded([&]() -> long {
+    RefFs &R = *static_cast<RefFs *>(fsHandle);
+    CellGroup grp("probe");
+    for (int i = 0; i < nCells; ++i) grp.add(R.g->cells()[cells[i]]);
+    Vector v = src::div(R.fs->u_, grp);
+    std::copy(v.data().begin(), v.data().end(), out);
+    return (long)v.size();
+  });
+}
+// fv::ddt(p_, dt, cells) after p_.savePreviousTimeStep -> diagonal coefficient and source per cell   (UD/TimeDerivative.h:50-62)
+long rfv_ddt_cells(void *fsHandle, double dt, int nCells, const int *cells, double *diag, double *rhs) {
+  return guarded([&]() -> long {
+    RefFs &R = *static_cast<RefFs *>(fsHandle);
+    CellGroup grp("probe");
+    for (int i = 0; i < nCells; ++i) grp.add(R.g->cells()[cells[i]]);
+    R.fs->p_.savePreviousTimeStep(dt, 1);
+    FiniteVolumeEquation<Scalar> eqn = fv::ddt(R.fs->p_, dt, grp);
+    const long n = (long)R.g->nCells();
+    for (long i = 0; i < n; ++i) {
+      diag[i] = 0.;
+      for (Index k = eqn.rowPtr()[i]; k < eqn.rowPtr()[i + 1]; ++k)
+        if (eqn.colInd()[k] == i) diag[i] += eqn.vals()[k];
+      rhs[i] = eqn.b(i);
+    }
+    return n;
   });
 }
 

@@ -101,6 +101,9 @@ SIGNATURES = {
     "phb_cicsam_weights": (ci, [vp, vp, vp, cd, vp]),
     "phb_assemble_cicsam_div": (ci, [vp, vp, vp, vp, cd, cd]),
     "phb_cicsam_momentum_flux": (ci, [cd, cd, vp, vp, vp, vp]),
+    "phb_assemble_ddt_cells": (ci, [vp, vp, cd, cd, ci, pi]),
+    "phb_assemble_src_div_cells": (ci, [vp, vp, cd, ci, pi]),
+    "phb_assemble_src_laplacian": (ci, [vp, cd, vp, vp, cd]),
     "phb_eqn_scale_rows": (ci, [vp, vp]),
     "phb_eqn_relax": (ci, [vp, vp, cd]),
     "phb_eqn_export_csr": (cll, [vp, ci, pi, pi, pd, pd]),

@@ -443,6 +443,24 @@ class FiniteVolumeEquation:
         check(self.L.phb_assemble_src_div(self.h, u.h, sign))
         return self
 
+    def ddtCells(self, phi, dt, cells, sign=1.0):
+        """fv::ddt(field, timeStep, cells) (UD/TimeDerivative.h:50-62)"""
+        c = np.ascontiguousarray(cells, np.int32)
+        check(self.L.phb_assemble_ddt_cells(self.h, phi.h, dt, sign, len(c), _ip(c)))
+        return self
+
+    def srcDivCells(self, u, cells, sign=1.0):
+        """src::div(field, cells) (UD/Source.cpp:5-21)"""
+        c = np.ascontiguousarray(cells, np.int32)
+        check(self.L.phb_assemble_src_div_cells(self.h, u.h, sign, len(c), _ip(c)))
+        return self
+
+    def srcLaplacian(self, gamma, phi, sign=1.0):
+        """src::laplacian(gamma, phi) (UD/Source.cpp:27-75); gamma scalar or ScalarFiniteVolumeField"""
+        gf = gamma.h if isinstance(gamma, FiniteVolumeField) else None
+        check(self.L.phb_assemble_src_laplacian(self.h, 0.0 if gf is not None else float(gamma), gf, phi.h, sign))
+        return self
+
     def cicsamDiv(self, u, gamma, beta, theta, sign=1.0):
         check(self.L.phb_assemble_cicsam_div(self.h, u.h, gamma.h, beta.h, theta, sign))
         return self

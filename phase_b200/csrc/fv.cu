@@ -195,8 +195,10 @@ __global__ void k_pack_field(int nSend, int nc, int ld, const int *__restrict__ 
 template <int NC>
 __global__ void k_ddt(MeshView M, double *__restrict__ vals, double *__restrict__ rhs, int ldr,
                       const double *__restrict__ phi0, int ldc, double rhoConst,
-                      const double *__restrict__ rho, const double *__restrict__ rho0, double dt, double sign) {
+                      const double *__restrict__ rho, const double *__restrict__ rho0, double dt, double sign,
+                      const int *__restrict__ mask) {
   FOR_EACH_ROW(M)
+    if (mask && !mask[row]) continue;
     const double V = M.vol[row];
     const double rh = rho ? rho[row] : rhoConst, rh0 = rho0 ? rho0[row] : rhoConst;
     vals[slot0] += sign * (rh * V / dt);
@@ -372,6 +374,35 @@ __global__ void k_lap_bnd(MeshView M, const int *__restrict__ faceType, double *
   for (int c = 0; c < NC; ++c) rhs[(size_t)c * ldr + row] += sign * r[c];
 }
 
+// src::laplacian: rhs[row] += sign * sum c (phi_nb - phi_P)
+__global__ void k_src_lap(MeshView M, double *__restrict__ rhs, double gammaConst, const double *__restrict__ gamF,
+                          const double *__restrict__ phi, double sign) {
+  FOR_EACH_ROW(M)
+    double t = 0.;
+    const double p0 = phi[row];
+    for (int k = 1; k < wdt; ++k) {
+      const size_t slot = slot0 + (size_t)k * 32;
+      const int lf = M.linkFace[slot];
+      if (lf < 0) continue;
+      const int f = lf >> 1;
+      t += (phi[M.A.col[slot]] - p0) * ((gamF ? gamF[f] : gammaConst) * M.fG[f]);
+    }
+    rhs[row] += sign * t;
+  END_FOR_EACH_ROW
+}
+__global__ void k_src_lap_bnd(MeshView M, double *__restrict__ rhs, double gammaConst, const double *__restrict__ gamF,
+                              const double *__restrict__ phi, const double *__restrict__ phiF, double sign) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M.nBCells) return;
+  const int row = M.bcCell[i];
+  double t = 0.;
+  for (int j = M.bcPtr[i]; j < M.bcPtr[i + 1]; ++j) {
+    const int f = M.bcFace[j];
+    t += (phiF[f] - phi[row]) * ((gamF ? gamF[f] : gammaConst) * M.fG[f]);
+  }
+  rhs[row] += sign * t;
+}
+
 // src::src: rhs += sign * f V
 template <int NC>
 __global__ void k_src(MeshView M, double *__restrict__ rhs, int ldr, const double *__restrict__ f, int ldc,
@@ -387,8 +418,9 @@ __global__ void k_src(MeshView M, double *__restrict__ rhs, int ldr, const doubl
 // OUT 2: out = dt/V * sum max(flux,0) (Courant number)
 template <int OUT>
 __global__ void k_flux_sum(MeshView M, const double *__restrict__ uF, double *__restrict__ out, double sign,
-                           double dt) {
+                           double dt, const int *__restrict__ mask) {
   FOR_EACH_ROW(M)
+    if (mask && !mask[row]) continue;
     double d = 0.;
     for (int k = 1; k < wdt; ++k) {
       const int lf = M.linkFace[slot0 + (size_t)k * 32];
@@ -403,10 +435,11 @@ __global__ void k_flux_sum(MeshView M, const double *__restrict__ uF, double *__
 }
 template <int OUT>
 __global__ void k_flux_sum_bnd(MeshView M, const double *__restrict__ uF, double *__restrict__ out, double sign,
-                               double dt) {
+                               double dt, const int *__restrict__ mask) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M.nBCells) return;
   const int row = M.bcCell[i];
+  if (mask && !mask[row]) return;
   double d = 0.;
   for (int j = M.bcPtr[i]; j < M.bcPtr[i + 1]; ++j) {
     const int f = M.bcFace[j];
@@ -596,11 +629,11 @@ int field_flux_max(const phb_field *u, int mode, double dt, phb::DevBuf<double> 
   PHB_CHECK(scratch.alloc((size_t)m->nLocal));
   const int grid = row_grid(c, m);
   if (mode == 0) {
-    PHB_LAUNCH(c, k_flux_sum<1>, grid, kThreads, 0, M, u->faces.p, scratch.p, 1., dt);
-    if (m->nBCells) PHB_LAUNCH(c, k_flux_sum_bnd<1>, (m->nBCells + 255) / 256, 256, 0, M, u->faces.p, scratch.p, 1., dt);
+    PHB_LAUNCH(c, k_flux_sum<1>, grid, kThreads, 0, M, u->faces.p, scratch.p, 1., dt, (const int *)nullptr);
+    if (m->nBCells) PHB_LAUNCH(c, k_flux_sum_bnd<1>, (m->nBCells + 255) / 256, 256, 0, M, u->faces.p, scratch.p, 1., dt, (const int *)nullptr);
   } else {
-    PHB_LAUNCH(c, k_flux_sum<2>, grid, kThreads, 0, M, u->faces.p, scratch.p, 1., dt);
-    if (m->nBCells) PHB_LAUNCH(c, k_flux_sum_bnd<2>, (m->nBCells + 255) / 256, 256, 0, M, u->faces.p, scratch.p, 1., dt);
+    PHB_LAUNCH(c, k_flux_sum<2>, grid, kThreads, 0, M, u->faces.p, scratch.p, 1., dt, (const int *)nullptr);
+    if (m->nBCells) PHB_LAUNCH(c, k_flux_sum_bnd<2>, (m->nBCells + 255) / 256, 256, 0, M, u->faces.p, scratch.p, 1., dt, (const int *)nullptr);
   }
   const int g2 = flat_grid(c, m->nLocal);
   PHB_CHECK(partials.alloc((size_t)c->numSMs * 8));
@@ -793,8 +826,20 @@ int phb_eqn_zero(phb_eqn *e) {
   return e->rhs.zero(e->m->ctx->stream);
 }
 
-int phb_assemble_ddt(phb_eqn *e, const phb_field *phi, double rhoConst, const phb_field *rho, double dt,
-                     double sign) {
+// 0 / 1 per owned row (device numbering) from a list of reference cell ids
+static int cell_mask(phb_mesh *m, int nCells, const int *cells, phb::DevBuf<int> &mask) {
+  std::vector<int> h(std::max(1, m->nLocal), 0);
+  for (int i = 0; i < nCells; ++i) {
+    PHB_REQUIRE(cells[i] >= 0 && cells[i] < m->nCells, "cell group: cell id %d out of range", cells[i]);
+    const int d = m->cell2dev[cells[i]];
+    if (d < m->nLocal) h[d] = 1;
+  }
+  PHB_CHECK(mask.upload(h, m->ctx->stream));
+  return PHB_OK;
+}
+
+static int assemble_ddt(phb_eqn *e, const phb_field *phi, double rhoConst, const phb_field *rho, double dt,
+                        double sign, const int *mask) {
   PHB_CHECK(check_pair(e, phi, "phb_assemble_ddt"));
   PHB_REQUIRE(phi->nComp == e->nComp, "phb_assemble_ddt: component mismatch");
   PHB_REQUIRE(phi->hasOld, "phb_assemble_ddt: field has no previous time step (savePreviousTimeStep)");
@@ -805,11 +850,26 @@ int phb_assemble_ddt(phb_eqn *e, const phb_field *phi, double rhoConst, const ph
   const double *r = rho ? rho->cells.p : nullptr, *r0 = rho ? (rho->hasOld ? rho->cells0.p : rho->cells.p) : nullptr;
   if (e->nComp == 1)
     PHB_LAUNCH(m->ctx, k_ddt<1>, row_grid(m->ctx, m), kThreads, 0, M, e->vals.p, e->rhs.p, m->nLocal, phi->cells0.p,
-               m->nDev, rhoConst, r, r0, dt, sign);
+               m->nDev, rhoConst, r, r0, dt, sign, mask);
   else
     PHB_LAUNCH(m->ctx, k_ddt<2>, row_grid(m->ctx, m), kThreads, 0, M, e->vals.p, e->rhs.p, m->nLocal, phi->cells0.p,
-               m->nDev, rhoConst, r, r0, dt, sign);
+               m->nDev, rhoConst, r, r0, dt, sign, mask);
   return PHB_OK;
+}
+int phb_assemble_ddt(phb_eqn *e, const phb_field *phi, double rhoConst, const phb_field *rho, double dt,
+                     double sign) {
+  return assemble_ddt(e, phi, rhoConst, rho, dt, sign, nullptr);
+}
+// fv::ddt(field, timeStep, cells) (UD/TimeDerivative.h:50-62): the listed cells only (reference cell ids)
+int phb_assemble_ddt_cells(phb_eqn *e, const phb_field *phi, double dt, double sign, int nCells, const int *cells) {
+  PHB_TRY_BEGIN
+  PHB_REQUIRE(e && cells && nCells >= 0, "phb_assemble_ddt_cells: bad argument");
+  phb::DevBuf<int> mask;
+  PHB_CHECK(cell_mask(e->m, nCells, cells, mask));
+  PHB_CHECK(assemble_ddt(e, phi, 1., nullptr, dt, sign, mask.p));
+  PHB_CUDA(cudaStreamSynchronize(e->m->ctx->stream));   // the mask goes out of scope
+  return PHB_OK;
+  PHB_TRY_END
 }
 
 static int assemble_div(phb_eqn *e, const phb_field *u, const phb_field *cphi, double theta, double sign, int mode,
@@ -896,14 +956,46 @@ int phb_assemble_src(phb_eqn *e, const phb_field *f, double sign) {
   return PHB_OK;
 }
 
-int phb_assemble_src_div(phb_eqn *e, const phb_field *u, double sign) {
+static int assemble_src_div(phb_eqn *e, const phb_field *u, double sign, const int *mask) {
   PHB_CHECK(check_pair(e, u, "phb_assemble_src_div"));
   PHB_REQUIRE(e->nComp == 1 && u->nComp == 2, "phb_assemble_src_div: scalar equation, vector field");
   phb_mesh *m = e->m;
   const MeshView M = view(m);
-  PHB_LAUNCH(m->ctx, k_flux_sum<0>, row_grid(m->ctx, m), kThreads, 0, M, u->faces.p, e->rhs.p, sign, 0.);
+  PHB_LAUNCH(m->ctx, k_flux_sum<0>, row_grid(m->ctx, m), kThreads, 0, M, u->faces.p, e->rhs.p, sign, 0., (const int *)mask);
   if (m->nBCells)
-    PHB_LAUNCH(m->ctx, k_flux_sum_bnd<0>, (m->nBCells + 255) / 256, 256, 0, M, u->faces.p, e->rhs.p, sign, 0.);
+    PHB_LAUNCH(m->ctx, k_flux_sum_bnd<0>, (m->nBCells + 255) / 256, 256, 0, M, u->faces.p, e->rhs.p, sign, 0., (const int *)mask);
+  return PHB_OK;
+}
+int phb_assemble_src_div(phb_eqn *e, const phb_field *u, double sign) { return assemble_src_div(e, u, sign, nullptr); }
+// src::div(field, cells) (UD/Source.cpp:5-21): the listed cells only, the other rows get nothing
+int phb_assemble_src_div_cells(phb_eqn *e, const phb_field *u, double sign, int nCells, const int *cells) {
+  PHB_TRY_BEGIN
+  PHB_REQUIRE(e && cells && nCells >= 0, "phb_assemble_src_div_cells: bad argument");
+  phb::DevBuf<int> mask;
+  PHB_CHECK(cell_mask(e->m, nCells, cells, mask));
+  PHB_CHECK(assemble_src_div(e, u, sign, mask.p));
+  PHB_CUDA(cudaStreamSynchronize(e->m->ctx->stream));
+  return PHB_OK;
+  PHB_TRY_END
+}
+
+// src::laplacian (UD/Source.cpp:27-75): rhs += sign * sum_links c (phi_nb - phi_P), c = Gamma g_f; boundary links use
+// the face value of phi whatever the patch type.  The field-Gamma overload of the reference (:50-75) sizes its result
+// 2N and writes row indexMap->local(cell, 1) of a one-component index map -- an out-of-bounds read that crashes when
+// the reference's own code is run (oracle/_ref) -- so only its evident intent exists here: the same scalar sum with
+// Gamma_f taken from the field's face values.
+int phb_assemble_src_laplacian(phb_eqn *e, double gammaConst, const phb_field *gam, const phb_field *phi, double sign) {
+  PHB_CHECK(check_pair(e, phi, "phb_assemble_src_laplacian"));
+  PHB_REQUIRE(phi->nComp == 1, "phb_assemble_src_laplacian: phi must be a scalar field");
+  PHB_REQUIRE(!gam || (gam->nComp == 1 && gam->m == e->m), "phb_assemble_src_laplacian: gamma must be a scalar field");
+  PHB_REQUIRE(e->nComp == 1, "phb_assemble_src_laplacian: scalar equation expected");
+  phb_mesh *m = e->m;
+  const MeshView M = view(m);
+  const double *gF = gam ? gam->faces.p : nullptr;
+  PHB_LAUNCH(m->ctx, k_src_lap, row_grid(m->ctx, m), kThreads, 0, M, e->rhs.p, gammaConst, gF, phi->cells.p, sign);
+  if (m->nBCells)
+    PHB_LAUNCH(m->ctx, k_src_lap_bnd, (m->nBCells + 255) / 256, 256, 0, M, e->rhs.p, gammaConst, gF, phi->cells.p,
+               phi->faces.p, sign);
   return PHB_OK;
 }
 

@@ -44,7 +44,7 @@ def main():
         uid = box[0]
     comm = Communicator(lr, rank, world, uid)
     px = 1
-    while px * px * 2 <= world and world % (px * 2) == 0:
+    while px * px * 4 <= world and world % (px * 2) == 0:
         px *= 2
     py = world // px
     if world == 1:

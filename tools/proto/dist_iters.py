@@ -30,6 +30,6 @@ b = np.random.default_rng(2).standard_normal(n * n); b -= b.mean()
 S = HostAmg(A, coarsest=1000)
 print("serial levels", S.nLevels, "iters", bicgstab_iters(A, S.cycle(), b)[0], flush=True)
 for px, py in [tuple(int(v) for v in a.split("x")) for a in (sys.argv[2:] or ["1x2", "2x2", "2x4"])]:
-    for tail in (200000,):
+    for tail in (50000,):
         M, H = dist_cycle(A, block_partition(n, n, px, py), 1000, tail)
         print("ranks %dx%d tailRows %d: dist levels %d tail levels %d iters %d" % (px, py, tail, H.nDist, H.nTail, bicgstab_iters(A, M, b)[0]), flush=True)
