@@ -121,6 +121,22 @@ long long phb_mesh_get_f64(const phb_mesh *m, const char *name, double *out,
  * phb_partition_rcb: deterministic recursive coordinate bisection of cell
  * centroids into nParts (any nParts >= 1). */
 int phb_partition_rcb(const phb_mesh *global, int nParts, int *cellPartition);
+/* METIS, as the reference calls it: method 0 = METIS_PartMeshDual with ncommon 2 (FiniteVolumeGrid2D::partition,
+ * UG/FiniteVolumeGrid2D.cpp:287-297), method 1 = METIS_PartGraphRecursive on the face-neighbour graph (the
+ * PhasePartitionGrid utility, U/utilities/PhasePartitionGrid.cpp:42-50).  PHB_ERR_UNSUPPORTED when the library was
+ * built without the toolkit's libmetis_static.a.  objective (may be NULL) = edge cut reported by METIS. */
+int phb_partition_metis(const phb_mesh *global, int nParts, int method, int *cellPartition, long long *objective);
+/* What PhasePartitionGrid writes per partition (U/utilities/PhasePartitionGrid.cpp:56-153): cells = owned cells in
+ * ascending id, then the halo cells in discovery order (cellLinks of the partition-boundary cells, then the cells
+ * within minBufferWidth of them); GlobalID / ProcNo per cell; nodes renumbered in first-use order; element lists and
+ * patch node pairs with 1-based local node ids.  tools/partition_grid.py writes them as ADF-CGNS files. */
+typedef struct phb_partfile phb_partfile;
+int phb_partition_file_build(const phb_mesh *global, const int *cellPartition, int proc, double minBufferWidth,
+                             phb_partfile **out);
+int phb_partition_file_sizes(const phb_partfile *f, long long out[4]); /* nCells nNodes len(eind) nPatches */
+int phb_partition_file_get(const phb_partfile *f, int *globalId, int *procNo, double *nodesXY, int *eptr, int *eind);
+long long phb_partition_file_patch(const phb_partfile *f, int p, char *name, int cap, int *nodePairs);
+int phb_partition_file_destroy(phb_partfile *f);
 /* local mesh of ctx's rank: owned cells + every face- or node-neighbour of an
  * owned cell (buffer layer), reference numbering (ascending global id), halo
  * lists as in initCommBuffers (:460-511).  `global` must be finalized. */

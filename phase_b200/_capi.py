@@ -43,6 +43,12 @@ SIGNATURES = {
     "phb_mesh_get_i32": (cll, [vp, cs, pi, cll]),
     "phb_mesh_get_f64": (cll, [vp, cs, pd, cll]),
     "phb_partition_rcb": (ci, [vp, ci, pi]),
+    "phb_partition_metis": (ci, [vp, ci, ci, pi, C.POINTER(C.c_longlong)]),
+    "phb_partition_file_build": (ci, [vp, pi, ci, cd, pvp]),
+    "phb_partition_file_sizes": (ci, [vp, C.POINTER(C.c_longlong)]),
+    "phb_partition_file_get": (ci, [vp, pi, pi, pd, pi, pi]),
+    "phb_partition_file_patch": (cll, [vp, ci, C.c_char_p, ci, pi]),
+    "phb_partition_file_destroy": (ci, [vp]),
     "phb_mesh_create_local": (ci, [vp, vp, pi, pvp]),
     "phb_mesh_create_rect_strip": (ci, [vp, ci, ci, cd, cd, pvp]),
     "phb_mesh_create_rect_block": (ci, [vp, ci, ci, cd, cd, ci, ci, pvp]),

@@ -183,6 +183,35 @@ class FiniteVolumeGrid2D:
         check(self.L.phb_partition_rcb(self.h, nparts, _ip(part)))
         return part
 
+    def partition_metis(self, nparts, method="mesh_dual"):
+        """METIS as the reference calls it: "mesh_dual" (FiniteVolumeGrid2D::partition) or "graph_recursive"
+        (the PhasePartitionGrid utility).  Returns (cellPartition, edge cut)."""
+        part = np.zeros(self.sizes()["nCells"], np.int32)
+        obj = C.c_longlong()
+        check(self.L.phb_partition_metis(self.h, nparts, 0 if method == "mesh_dual" else 1, _ip(part), C.byref(obj)))
+        return part, obj.value
+
+    def partition_file(self, part, proc, minBufferWidth=0.0):
+        """The content of PhasePartitionGrid's solution/Proc<proc>/Grid.cgns (U/utilities/PhasePartitionGrid.cpp:56-153):
+        dict with GlobalID, ProcNo, nodes (n x 2), eptr, eind (1-based), patches {name: 1-based node pairs}."""
+        part = np.ascontiguousarray(part, np.int32)
+        h = C.c_void_p()
+        check(self.L.phb_partition_file_build(self.h, _ip(part), proc, minBufferWidth, C.byref(h)))
+        sz = (C.c_longlong * 4)()
+        check(self.L.phb_partition_file_sizes(h, sz))
+        gid, pno = np.zeros(sz[0], np.int32), np.zeros(sz[0], np.int32)
+        nodes, eptr, eind = np.zeros(2 * sz[1]), np.zeros(sz[0] + 1, np.int32), np.zeros(sz[2], np.int32)
+        check(self.L.phb_partition_file_get(h, _ip(gid), _ip(pno), _dp(nodes), _ip(eptr), _ip(eind)))
+        patches = {}
+        for p in range(sz[3]):
+            buf = C.create_string_buffer(64)
+            n = check(self.L.phb_partition_file_patch(h, p, buf, 64, None))
+            pairs = np.zeros(n, np.int32)
+            check(self.L.phb_partition_file_patch(h, p, buf, 64, _ip(pairs)))
+            patches[buf.value.decode()] = pairs
+        self.L.phb_partition_file_destroy(h)
+        return dict(GlobalID=gid, ProcNo=pno, nodes=nodes.reshape(-1, 2), eptr=eptr, eind=eind, patches=patches)
+
     def local(self, part, comm=None):
         comm = comm or self.comm
         part = np.ascontiguousarray(part, np.int32)

@@ -29,9 +29,15 @@ def headers():
     return hs
 
 
+# METIS ships with the CUDA toolkit as a static library (cuSOLVER's; 64-bit idx_t): the optional "same algorithm
+# family as the reference" partitioner (partition.cu)
+METIS = os.path.join(os.path.dirname(os.path.dirname(NVCC)), "targets", "x86_64-linux", "lib", "libmetis_static.a")
+
+
 def _compile(src, verbose):
     obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DPHB_HAVE_METIS"] if os.path.exists(METIS) else []) + \
+        ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -54,8 +60,8 @@ def build(force=False, verbose=False):
             for obj, log in ex.map(lambda s: _compile(s, verbose), todo):
                 logs.append(log)
     if todo or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                      "-lcudart", "-ldl"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ([METIS] if os.path.exists(METIS) else []) + \
+            ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
         subprocess.check_call(cmd)
     return LIB, "\n".join(logs)
 

@@ -6,72 +6,7 @@ sub-node table = "SNTb" endPtr(12) + entries name[32] ptr(12); data = "DaTa" end
 import numpy as np
 
 
-def _ptr(off):
-    return ("%08x%04x" % (off // 4096, off % 4096)).encode()
-
-
-class AdfWriter:
-    def __init__(self):
-        hdr = bytearray(b"\xc0\xa8\xa3\xa9ADF Database Version A02011>AdF0")
-        hdr += b" " * (266 - len(hdr))
-        self.buf = hdr
-        self.nodes = []
-
-    def _alloc(self, n):
-        off = len(self.buf)
-        self.buf += b"\0" * n
-        return off
-
-    def add(self, name, label, dtype="MT", data=None, dims=None, children=()):
-        """children: list of node offsets already written. returns this node's offset."""
-        data_off = 4096
-        nch = 0
-        if data is not None:
-            payload = data if isinstance(data, bytes) else np.ascontiguousarray(data).tobytes()
-            data_off = self._alloc(16 + len(payload) + 4)
-            self.buf[data_off:data_off + 4] = b"DaTa"
-            self.buf[data_off + 4:data_off + 16] = _ptr(data_off + 16 + len(payload))
-            self.buf[data_off + 16:data_off + 16 + len(payload)] = payload
-            self.buf[data_off + 16 + len(payload):data_off + 20 + len(payload)] = b"dEnD"
-            nch = 1
-        sub_off = 0
-        if children:
-            sub_off = self._alloc(16 + 44 * len(children) + 4)
-            self.buf[sub_off:sub_off + 4] = b"SNTb"
-            self.buf[sub_off + 4:sub_off + 16] = _ptr(sub_off + 16 + 44 * len(children))
-            p = sub_off + 16
-            for cname, coff in children:
-                self.buf[p:p + 32] = cname.encode().ljust(32)
-                self.buf[p + 32:p + 44] = _ptr(coff)
-                p += 44
-        dims = list(dims or [])
-        off = self._alloc(246)
-        rec = bytearray(b"NoDe")
-        rec += name.encode().ljust(32) + label.encode().ljust(32)
-        rec += ("%08x" % len(children)).encode() + ("%08x" % len(children)).encode() + _ptr(sub_off)
-        rec += dtype.encode().ljust(32) + ("%02x" % len(dims)).encode()
-        for i in range(12):
-            rec += ("%08x" % (dims[i] if i < len(dims) else 0)).encode()
-        rec += ("%04x" % nch).encode() + _ptr(data_off) + b"TaiL"
-        assert len(rec) == 246, len(rec)
-        self.buf[off:off + 246] = rec
-        return off
-
-    def finish(self, path, root_children):
-        # the reader takes the FIRST "NoDe" in the file as the root: write the root at offset 266
-        root = bytearray(b"NoDe") + b"ADF MotherNode".ljust(32) + b"Root Node of ADF File".ljust(32)
-        sub_off = self._alloc(16 + 44 * len(root_children) + 4)
-        self.buf[sub_off:sub_off + 4] = b"SNTb"
-        p = sub_off + 16
-        for cname, coff in root_children:
-            self.buf[p:p + 32] = cname.encode().ljust(32)
-            self.buf[p + 32:p + 44] = _ptr(coff)
-            p += 44
-        root += ("%08x" % len(root_children)).encode() * 2 + _ptr(sub_off) + b"MT".ljust(32) + b"00" + b"00000000" * 12
-        root += b"0000" + _ptr(4096) + b"TaiL"
-        assert len(root) == 246
-        self.buf[266:266 + 246] = root
-        open(path, "wb").write(bytes(self.buf))
+from phase_b200.adf import AdfWriter, _ptr  # noqa: F401  (the writer is product code: partition files)
 
 
 def write_cgns(path, xy, elements, bcs):
