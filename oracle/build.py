@@ -92,7 +92,7 @@ def build_ref_fv(force=False):
     driver = os.path.join(HERE, "ref_fv_driver.cpp")
     if not os.path.exists(os.path.join(REF_SRC, "2D", "Unstructured", "Solvers", "FractionalStep.cpp")):
         return REF_FV_SO if os.path.exists(REF_FV_SO) else None
-    srcs = ref_fv_sources() + [driver]
+    srcs = ref_fv_sources() + [driver, os.path.join(HERE, "ref_mpi_threads.cpp")]
     stubs = [os.path.join(r, n) for r, _, ns in os.walk(os.path.join(HERE, "ref_stub")) for n in ns]
     if not force and _newer(REF_FV_SO, srcs + stubs):
         return REF_FV_SO
@@ -113,7 +113,7 @@ def build_ref_fv(force=False):
     with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(cc, srcs))
     subprocess.check_call(["g++", "-shared", "-o", REF_FV_SO] + objs +
-                          [blas, "-Wl,-rpath," + os.path.dirname(blas), "-lstdc++fs"])
+                          [blas, "-Wl,-rpath," + os.path.dirname(blas), "-lstdc++fs", "-lpthread"])
     return REF_FV_SO
 
 

@@ -21,11 +21,16 @@
  *       SparseMatrixSolver}.cpp alone -- exact CSR insertion / compaction /
  *       operator algebra / set()+setRhs(-rhs) hand-off (tests/test_oracle_ref_crs.py).
  *   (3) hand-simulated known answers, tests/test_oracle_kat.py.
+ *       The same library runs the reference's partition(), initCommBuffers() and
+ *       IndexMap on several MPI ranks (threads, oracle/ref_mpi_threads.cpp) for a given
+ *       partition vector: local meshes, ownership, buffer / send groups and global
+ *       row numbers bit-exact (tests/test_oracle_ref_partition.py).
  * Not pinned: the polygon area / centroid arithmetic (Boost.Geometry is absent;
- * the stand-in implements the same shoelace / Bashein-Detmer formulas), the
- * partition / halo maps (the reference needs MPI ranks and METIS for them) and
- * the solve arithmetic itself, which lives in un-vendored Eigen3 / Trilinos
- * (versions unpinned): any exact direct solve (scipy splu) stands in for it.
+ * the stand-in implements the same shoelace / Bashein-Detmer formulas), the METIS
+ * call that produces the partition vector (version / options unpinned: the vector
+ * is an input) and the solve arithmetic itself, which lives in un-vendored
+ * Eigen3 / Trilinos (versions unpinned): any exact direct solve (scipy splu)
+ * stands in for it.
  */
 #ifndef PHASE_ORACLE_H
 #define PHASE_ORACLE_H

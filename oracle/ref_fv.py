@@ -57,6 +57,10 @@ def lib():
         L.rfv_src_div_cells.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.rfv_ddt_cells.restype = C.c_long
         L.rfv_ddt_cells.argtypes = [vp, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.rfv_partition_run.restype = C.c_long
+        L.rfv_partition_run.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]
+        L.rfv_partition_get.restype = C.c_long
+        L.rfv_partition_get.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int)]
         L.rfv_fs_close.argtypes = [vp]
         L.rfv_fs_step.restype = C.c_long
         L.rfv_fs_step.argtypes = [vp, C.c_double]
@@ -286,3 +290,21 @@ class Multiphase(FracStep):
         self.h = _check(lib().rfv_fsm_create(case.h, grid.h))
         s = grid.array("sizes")
         self.N, self.F = int(s[1]), int(s[2])
+
+
+def partition(case, part, n_ranks, n_indices=2):
+    """FiniteVolumeGrid2D::partition (UG/FiniteVolumeGrid2D.cpp:276-392) + initCommBuffers (:459-511) + IndexMap
+    (UE/IndexMap.cpp:5-40) of the reference, run on `n_ranks` MPI ranks (threads of this process) for the rectilinear
+    grid of `case` with the given cell-partition vector.  Returns one dict of int arrays per rank."""
+    part = np.ascontiguousarray(part, np.int32)
+    _check(lib().rfv_partition_run(case.h, n_ranks, part.ctypes.data_as(C.POINTER(C.c_int)), len(part), n_indices))
+    out = []
+    for r in range(n_ranks):
+        d = {}
+        for k in ("globalId", "owner", "bufPtr", "bufCell", "sendPtr", "sendCell", "local", "global", "faceL", "faceR"):
+            n = _check(lib().rfv_partition_get(r, k.encode(), None))
+            a = np.zeros(max(n, 1), np.int32)
+            _check(lib().rfv_partition_get(r, k.encode(), a.ctypes.data_as(C.POINTER(C.c_int))))
+            d[k] = a[:n]
+        out.append(d)
+    return out

@@ -45,6 +45,18 @@ CgnsFile::Solution CgnsFile::readLastFlowSolution(int, int) const {
   throw Exception("CgnsFile", "readLastFlowSolution", "not available in the oracle build");
 }
 
+// ---- METIS hook: the partition vector is an input (oracle/ref_stub/metis.h)
+#include <metis.h>
+namespace { std::vector<int> g_part; }
+void phase_metis_set_partition(const int *part, int n) { g_part.assign(part, part + n); }
+int METIS_PartMeshDual(idx_t *ne, idx_t *, idx_t *, idx_t *, idx_t *, idx_t *, idx_t *, idx_t *, real_t *, idx_t *, idx_t *objval,
+                       idx_t *epart, idx_t *) {
+  if ((int)g_part.size() != *ne) return 0;
+  std::copy(g_part.begin(), g_part.end(), epart);
+  if (objval) *objval = 0;
+  return METIS_OK;
+}
+
 // ---- the recording backend
 typedef int (*rfv_solve_cb)(int n, const int *rowPtr, const int *colInd, const double *vals, const double *b, double *x,
                             void *user);
@@ -362,6 +374,74 @@ long rfv_fs_field(void *fsHandle, const char *name, double *buf, int set) {
       return (long)g.nFaces();
     }
     throw Exception("rfv_fs_field", "name", "unknown field \"" + nm + "\"");
+  });
+}
+
+// ---- FiniteVolumeGrid2D::partition + initCommBuffers + IndexMap on nRanks "MPI ranks" (threads, oracle/ref_mpi_threads.cpp)
+// with the given partition vector: per rank the local grid's globalIds_, cellOwnership_, buffer / send cell groups
+// (local cell ids, group order) and the IndexMap's local / global indices for nIndices sets.
+namespace {
+struct RankResult {
+  std::vector<int> globalId, owner, bufPtr, bufCell, sendPtr, sendCell, local, global, faceL, faceR;
+  std::string err;
+};
+struct PartJob {
+  const RefCase *cs;
+  int nIndices;
+  std::vector<RankResult> res;
+};
+void part_worker(int rank, void *user) {
+  PartJob &J = *static_cast<PartJob *>(user);
+  RankResult &R = J.res[rank];
+  try {
+    StructuredRectilinearGrid g(J.cs->input);
+    g.partition(J.cs->input);
+    const int P = g.comm().nProcs();
+    for (const Cell &c : g.cells()) { R.globalId.push_back((int)g.globalIds()[c.id()]); R.owner.push_back((int)g.cellOwnership()[c.id()]); }
+    R.bufPtr.push_back(0); R.sendPtr.push_back(0);
+    for (int q = 0; q < P; ++q) {
+      for (const Cell &c : g.bufferGroups()[q]) R.bufCell.push_back((int)c.id());
+      R.bufPtr.push_back((int)R.bufCell.size());
+      for (const Cell &c : g.sendGroups()[q]) R.sendCell.push_back((int)c.id());
+      R.sendPtr.push_back((int)R.sendCell.size());
+    }
+    for (const Face &f : g.faces()) { R.faceL.push_back((int)f.lCell().id()); R.faceR.push_back(f.isInterior() ? (int)f.rCell().id() : -1); }
+    IndexMap im(g, J.nIndices);
+    for (int s = 0; s < J.nIndices; ++s)
+      for (const Cell &c : g.cells()) { R.local.push_back((int)im.local(c, s)); R.global.push_back((int)im.global(c, s)); }
+  } catch (const std::exception &e) {
+    R.err = e.what();
+  }
+}
+PartJob *g_job = nullptr;
+}  // namespace
+
+long rfv_partition_run(void *caseHandle, int nRanks, const int *part, int nCells, int nIndices) {
+  return guarded([&]() -> long {
+    delete g_job;
+    g_job = new PartJob();
+    g_job->cs = static_cast<RefCase *>(caseHandle);
+    g_job->nIndices = nIndices;
+    g_job->res.resize(nRanks);
+    phase_metis_set_partition(part, nCells);
+    phase_mpi_run(nRanks, part_worker, g_job);
+    for (auto &r : g_job->res)
+      if (!r.err.empty()) throw Exception("rfv_partition_run", "rank", r.err);
+    return 0L;
+  });
+}
+// which: globalId owner bufPtr bufCell sendPtr sendCell local global faceL faceR
+long rfv_partition_get(int rank, const char *which, int *out) {
+  return guarded([&]() -> long {
+    if (!g_job || rank < 0 || rank >= (int)g_job->res.size()) throw Exception("rfv_partition_get", "rank", "no such rank");
+    const RankResult &R = g_job->res[rank];
+    const std::string w(which);
+    const std::vector<int> *v = w == "globalId" ? &R.globalId : w == "owner" ? &R.owner : w == "bufPtr" ? &R.bufPtr : w == "bufCell" ? &R.bufCell
+                              : w == "sendPtr" ? &R.sendPtr : w == "sendCell" ? &R.sendCell : w == "local" ? &R.local : w == "global" ? &R.global
+                              : w == "faceL" ? &R.faceL : w == "faceR" ? &R.faceR : nullptr;
+    if (!v) throw Exception("rfv_partition_get", "which", "unknown array");
+    if (out) std::copy(v->begin(), v->end(), out);
+    return (long)v->size();
   });
 }
 

@@ -1012,6 +1012,123 @@ k_amg_peer_halo(AmgPeerView pv, int ch, AmgPeerLevel L, int vec, const T *__rest
   __syncthreads();
 }
 
+// ---- fused small levels: one launch runs levels fuseFrom .. L-1 down, the dense coarsest solve and the way back up.
+// These levels hold 2 % of the cycle's data but, as separate launches of 5-10 us each, 30 % of its time (and all of
+// it when the mesh is split over many GPUs).  The pre-smoothing sweep from a zero guess is folded away: its result
+// x = w.*b is recomputed where it is needed (gather side of the residual, row side of the prolongation), so a level
+// is four phases: residual, restriction | prolongation, post-smoothing.  Phases are separated by a sense-reversing
+// grid barrier; the grid is one CTA per SM, all resident.  A spin that runs far too long raises `bar[2]` and gives up
+// (a hung kernel would take the whole process with it).
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void grid_barrier(unsigned *bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned gen = ld_acquire_gpu(bar + 1);
+    __threadfence();
+    if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+      bar[0] = 0u;
+      __threadfence();
+      st_release_gpu(bar + 1, gen + 1u);
+    } else {
+      long long spins = 0;
+      while (ld_acquire_gpu(bar + 1) == gen)
+        if (++spins > (1ll << 31)) { bar[2] = 1u; break; }
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(1024)
+k_amg_tail(const AmgTailOp *__restrict__ ops, int nOps, unsigned *bar, const KrylovSums *S, int maxIters) {
+  if (S && krylov_done(S, maxIters)) return;   // the same answer in every CTA: nobody waits for a CTA that left
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nThreads = gridDim.x * blockDim.x;
+  for (int o = 0; o < nOps; ++o) {
+    const AmgTailOp op = ops[o];
+    if (op.kind == 2) {   // dense coarsest solve: one warp per row of the fp64 inverse
+      const double *Ainv = static_cast<const double *>(op.vals);
+      const T *b = static_cast<const T *>(op.b);
+      T *x = static_cast<T *>(op.y);
+      const int lane = threadIdx.x & 31;
+      for (int row = tid >> 5; row < op.n; row += nThreads >> 5) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          double acc = 0.;
+          for (int k = lane; k < op.n; k += 32) acc = fma(Ainv[(size_t)row * op.n + k], (double)b[(size_t)c * op.ld + k], acc);
+          acc = warp_sum(acc);
+          if (lane == 0) x[(size_t)c * op.ld + row] = (T)acc;
+        }
+      }
+    } else {
+      const T *vals = static_cast<const T *>(op.vals), *w = static_cast<const T *>(op.w);
+      const T *b = static_cast<const T *>(op.b), *xin = static_cast<const T *>(op.x);
+      T *y = static_cast<T *>(op.y);
+      const int L = op.lanes, g = tid & (L - 1);
+      const int rowsPerPass = nThreads / L;
+      for (int row0 = 0; row0 < op.n; row0 += rowsPerPass) {   // uniform trip count: the shuffles below stay converged
+        const int row = row0 + tid / L;
+        const bool live = row < op.n;
+        T acc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = T(0);
+        if (live) {
+          const int off = op.sliceOff[row >> 5];
+          const int wdt = (op.sliceOff[(row >> 5) + 1] - off) >> 5;
+          const size_t base = (size_t)off + (row & 31);
+          for (int k0 = g; k0 < wdt; k0 += 4 * L) {   // four entries in flight per lane: the phase is latency-bound
+            int col[4];
+            T a[4], wc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k = k0 + j * L;
+              col[j] = k < wdt ? op.col[base + (size_t)k * 32] : -1;
+              a[j] = k < wdt ? vals[base + (size_t)k * 32] : T(0);
+            }
+            if (op.kind == 0) {          // gathered vector = w .* b of this level
+#pragma unroll
+              for (int j = 0; j < 4; ++j) wc[j] = col[j] >= 0 ? w[col[j]] : T(0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (col[j] >= 0) {
+#pragma unroll
+                  for (int c = 0; c < NC; ++c) acc[c] = fma(a[j], wc[j] * b[(size_t)c * op.ldIn + col[j]], acc[c]);
+                }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (col[j] >= 0) {
+#pragma unroll
+                  for (int c = 0; c < NC; ++c) acc[c] = fma(a[j], xin[(size_t)c * op.ldIn + col[j]], acc[c]);
+                }
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          for (int s = L >> 1; s > 0; s >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], s);
+        if (live && g == 0) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const size_t i = (size_t)c * op.ld + row;
+            if (op.kind == 0) y[i] = b[i] - acc[c];
+            else if (op.kind == 1) y[i] = acc[c];
+            else if (op.kind == 3) y[i] = w[row] * b[i] + acc[c];
+            else y[i] = xin[i] + w[row] * (b[i] - acc[c]);
+          }
+        }
+      }
+    }
+    if (o + 1 < nOps) grid_barrier(bar);
+  }
+}
+
 // max relative deviation of `a` from ratio * ref over the slots, ratio = a[first] / ref[first]
 __global__ void __launch_bounds__(kThreads)
 k_amg_changed(long long nSlots, const double *__restrict__ a, const double *__restrict__ ref, int first,
@@ -1083,6 +1200,8 @@ int upload_mat(phb_ctx *c, const HCsr &H, bool diagFirst, AmgMat &M) {
   return PHB_OK;
 }
 
+template <typename T> int build_tail_ops(phb_solver *s);
+
 template <typename T>
 int rebuild_t(phb_solver *s) {
   phb_ctx *c = s->ctx;
@@ -1129,6 +1248,7 @@ int rebuild_t(phb_solver *s) {
     PHB_LAUNCH(c, k_amg_to_float, grid_rows(c, P->nSlots), kThreads, 0, P->nSlots, D.refVals.p, D.refValsF.p);
   }
   PHB_CUDA(cudaStreamSynchronize(c->stream));
+  PHB_CHECK(build_tail_ops<T>(s));
   D.src = P;
   D.nComp = s->nComp;
   D.builtSingle = sizeof(T) == 4;
@@ -1330,6 +1450,7 @@ int rebuild_dist_t(phb_solver *s) {
     PHB_LAUNCH(c, k_amg_to_float, grid_rows(c, P->nSlots), kThreads, 0, P->nSlots, D.refVals.p, D.refValsF.p);
   }
   PHB_CUDA(cudaStreamSynchronize(c->stream));
+  PHB_CHECK(build_tail_ops<T>(s));
   D.src = P;
   D.nComp = s->nComp;
   D.builtSingle = sizeof(T) == 4;
@@ -1349,6 +1470,60 @@ int rebuild_dist_t(phb_solver *s) {
 }
 
 template <typename T> const T *level0_vals(const AmgData &D);
+
+// op list of the fused tail (levels fuseFrom .. L-1); called at the end of every (re)build
+template <typename T>
+int build_tail_ops(phb_solver *s) {
+  AmgData &D = s->amg;
+  phb_ctx *c = s->ctx;
+  const int L = (int)D.lev.size();
+  D.fuseFrom = -1;
+  D.nTailOps = 0;
+  if (D.fuseRows <= 0 || D.nu != 1 || !D.denseCoarse || L < 3) return PHB_OK;
+  int F = -1;
+  for (int l = std::max(1, D.nDist); l <= L - 2; ++l)
+    if (D.lev[l]->n <= D.fuseRows && !D.lev[l]->dist) { F = l; break; }
+  if (F < 0) return PHB_OK;
+  const int nThreads = c->numSMs * 1024;
+  auto lanes_for = [&](int rows) {
+    int l = 1;
+    while (l < 8 && (long long)rows * (2 * l) <= nThreads) l *= 2;
+    return l;
+  };
+  std::vector<AmgTailOp> ops;
+  auto sparse = [&](int kind, const AmgMat &M, int n, int ld, int ldIn, const void *w, const void *b, const void *x, void *y) {
+    AmgTailOp o;
+    o.kind = kind; o.n = n; o.ld = ld; o.ldIn = ldIn; o.lanes = lanes_for(n);
+    o.sliceOff = M.pat.sliceOff.p; o.col = M.pat.col.p; o.vals = M.vals.p;
+    o.w = w; o.b = b; o.x = x; o.y = y;
+    ops.push_back(o);
+  };
+  for (int l = F; l <= L - 2; ++l) {
+    AmgLevel &V = *D.lev[l], &C = *D.lev[l + 1];
+    sparse(0, V.A, V.n, V.ld, V.ld, V.w.p, V.b.p, nullptr, V.r.p);
+    sparse(1, V.R, C.n, C.ld, V.ld, nullptr, nullptr, V.r.p, C.b.p);
+  }
+  {
+    AmgLevel &V = *D.lev[L - 1];
+    AmgTailOp o;
+    o.kind = 2; o.n = V.n; o.ld = V.ld; o.ldIn = V.ld; o.lanes = 32;
+    o.sliceOff = nullptr; o.col = nullptr; o.vals = D.coarseInv.p; o.w = nullptr; o.b = V.b.p; o.x = nullptr; o.y = V.x.p;
+    ops.push_back(o);
+  }
+  for (int l = L - 2; l >= F; --l) {
+    AmgLevel &V = *D.lev[l], &C = *D.lev[l + 1];
+    const void *xc = l + 1 == L - 1 ? C.x.p : C.x2.p;
+    sparse(3, V.P, V.n, V.ld, C.ld, V.w.p, V.b.p, xc, V.x.p);
+    sparse(4, V.A, V.n, V.ld, V.ld, V.w.p, V.b.p, V.x.p, V.x2.p);
+  }
+  PHB_CHECK(D.tailOps.upload(ops, c->stream));
+  PHB_CHECK(D.tailBar.alloc(4));
+  PHB_CHECK(D.tailBar.zero(c->stream));
+  PHB_CUDA(cudaStreamSynchronize(c->stream));
+  D.fuseFrom = F;
+  D.nTailOps = (int)ops.size();
+  return PHB_OK;
+}
 template <> const float *level0_vals<float>(const AmgData &D) { return D.refValsF.p; }
 template <> const double *level0_vals<double>(const AmgData &D) { return D.refVals.p; }
 
@@ -1478,6 +1653,21 @@ template <typename T> struct Cycle {
     if (L == 1) { coarse(0, in, out); return PHB_OK; }
     std::vector<T *> xOf(L);
     xOf[0] = down(0, in);
+    const int F = D.fuseFrom;
+    if (F >= 1 && D.nu == 1) {   // levels F .. L-1 in one launch (k_amg_tail); its result is level F's post-smoothed iterate
+      for (int l = 1; l < F; ++l) xOf[l] = down(l, (const T *)as<T>(D.lev[l]->b));
+      if (nc == 1)
+        PHB_LAUNCH(s->ctx, (k_amg_tail<T, 1>), s->ctx->numSMs, 1024, 0, (const AmgTailOp *)D.tailOps.p, D.nTailOps, D.tailBar.p, S,
+                   s->maxIters);
+      else
+        PHB_LAUNCH(s->ctx, (k_amg_tail<T, 2>), s->ctx->numSMs, 1024, 0, (const AmgTailOp *)D.tailOps.p, D.nTailOps, D.tailBar.p, S,
+                   s->maxIters);
+      xOf[F] = as<T>(D.lev[F]->x2);
+      for (int l = F - 1; l >= 1; --l)
+        xOf[l] = up(l, (const T *)as<T>(D.lev[l]->b), xOf[l], (const T *)xOf[l + 1], nullptr);
+      up(0, in, xOf[0], (const T *)xOf[1], out);
+      return failed ? PHB_ERR_COMM : PHB_OK;
+    }
     for (int l = 1; l + 1 < L; ++l) xOf[l] = down(l, (const T *)as<T>(D.lev[l]->b));
     xOf[L - 1] = coarse(L - 1, (const T *)as<T>(D.lev[L - 1]->b), nullptr);
     for (int l = L - 2; l >= 1; --l)
@@ -1533,6 +1723,21 @@ void amg_record_iters(phb_solver *s, int iters) {
   if (s->amg.built && s->amg.itersAfterSetup < 0) s->amg.itersAfterSetup = iters;
 }
 
+// PHB_ERR_STATE when a grid barrier of the fused tail gave up (co-residency of the CTAs lost: should not happen
+// with one CTA per SM on a stream of our own)
+int amg_check(phb_solver *s) {
+  AmgData &D = s->amg;
+  if (D.fuseFrom < 1 || !D.tailBar.p) return PHB_OK;
+  unsigned flag = 0;
+  PHB_CUDA(cudaMemcpyAsync(&flag, D.tailBar.p + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, s->ctx->stream));
+  PHB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  if (flag) {
+    set_error("amg: a grid barrier of the fused small-level kernel timed out");
+    return PHB_ERR_STATE;
+  }
+  return PHB_OK;
+}
+
 int amg_launches_per_apply(const phb_solver *s) {
   const AmgData &D = s->amg;
   const int L = (int)D.lev.size();
@@ -1541,6 +1746,7 @@ int amg_launches_per_apply(const phb_solver *s) {
   int packs = 0;                                       // one pack kernel per ghost refresh of a distributed level
   for (int l = 0; l < D.nDist; ++l)
     if (D.lev[l]->nSend) packs += 2 * D.nu + (l > 0 ? 1 : 0);
+  if (D.fuseFrom >= 1 && D.nu == 1) return D.fuseFrom * perLevel + 1 + packs;
   return (L - 1) * perLevel + (D.denseCoarse ? 1 : 1 + kCoarseSweeps) + packs;
 }
 

@@ -625,7 +625,7 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
   s->runSendDev = nullptr;
   s->lastIters = totalIters;
   s->lastRelres = rel;
-  if (s->precond == PHB_PC_AMG) amg_record_iters(s, totalIters);
+  if (s->precond == PHB_PC_AMG) { amg_record_iters(s, totalIters); PHB_CHECK(amg_check(s)); }
   if (iters) *iters = totalIters;
   if (relres) *relres = rel;
   return launch_status(c);
@@ -702,6 +702,9 @@ int phb_solver_setup(phb_solver *s, const char *key, const char *value) {
   } else if (k == "amgScope") {
     PHB_REQUIRE(lv == "global" || lv == "local", "amgScope must be \"global\" or \"local\"");
     s->amg.global = lv == "global"; s->amg.built = false;
+  } else if (k == "amgFuseRows") {
+    s->amg.fuseRows = std::stoll(v); s->amg.built = false;
+    PHB_REQUIRE(s->amg.fuseRows >= 0, "amgFuseRows must not be negative");
   } else if (k == "amgTailRows") {
     s->amg.tailRows = std::stoll(v); s->amg.built = false;
     PHB_REQUIRE(s->amg.tailRows >= 1, "amgTailRows must be positive");

@@ -109,6 +109,18 @@ struct AmgPeer {
   }
 };
 
+// One phase of the fused small-level kernel (amg.cu: k_amg_tail): every level from `fuseFrom` down to the dense
+// coarsest solve and back up runs in ONE launch, the phases separated by grid barriers instead of kernel boundaries.
+struct AmgTailOp {
+  int kind;                 // 0 r = b - A (w.*b) | 1 y = R r | 2 x = Ainv b (dense) | 3 x = w.*b + P xc | 4 y = x + w.*(b - A x)
+  int n, ld, ldIn;          // rows; leading dimension of the row-wise vectors; of the gathered vector
+  int lanes;                // lanes per row (power of two <= 32)
+  const int *sliceOff, *col;
+  const void *vals;         // matrix values (cycle precision), or the fp64 dense inverse (kind 2)
+  const void *w, *b, *x;    // smoother weights; right-hand side; gathered vector (x, r or xc)
+  void *y;                  // result
+};
+
 struct AmgData {
   std::vector<std::unique_ptr<AmgLevel>> lev;
   phb::DevBuf<double> coarseInv, refVals, chk;
@@ -119,6 +131,11 @@ struct AmgData {
   long long tailRows = 200000;
   std::vector<int> tailOff, tailCnt, tailSendOff, tailSendCnt;
   std::unique_ptr<AmgPeer> peer;            // set when the context has peer memory enabled (else NCCL send/recv)
+  // fused tail: levels fuseFrom .. L-1 in one launch (fuseFrom < 0: off)
+  long long fuseRows = 200000;              // `amgFuseRows`: levels with at most this many rows are fused (0: never)
+  int fuseFrom = -1, nTailOps = 0;
+  phb::DevBuf<AmgTailOp> tailOps;
+  phb::DevBuf<unsigned> tailBar;
   const SellPattern *src = nullptr;
   bool built = false, denseCoarse = false, stale = false, rebuildAlways = false;
   int nComp = 1, nCoarse = 0, nu = 1, coarsest = 1000, setups = 0, itersAfterSetup = -1;
@@ -194,6 +211,7 @@ int amg_prepare(phb_solver *s);
 int amg_apply(phb_solver *s, const double *in, double *out, bool inLoop);
 int amg_launches_per_apply(const phb_solver *s);
 void amg_record_iters(phb_solver *s, int iters);
+int amg_check(phb_solver *s);
 double amg_cycle_bytes(const phb_solver *s);
 int amg_time(phb_solver *s, int reps, double out[8]);
 }  // namespace phb

@@ -31,3 +31,14 @@ def test_two_rank_parity(args):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(" OK") == 2
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("args", [["--peer"], ["--peer", "--fuse-rows", "3000"], ["--fuse-rows", "3000", "--precision", "single"]])
+def test_two_rank_cycle_equals_transcription(args):
+    """the distributed device V-cycle (peer-memory or NCCL ghost refreshes, fused replicated tail) = the scipy
+    transcription of the same distributed hierarchy"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29537", os.path.join(ROOT, "tools", "mgpu_cycle_check.py")] + args
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and " OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

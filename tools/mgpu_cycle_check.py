@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--coarsest", type=int, default=100)
     ap.add_argument("--peer", action="store_true")
     ap.add_argument("--precision", default="double")
+    ap.add_argument("--fuse-rows", type=int, default=200000, help="amgFuseRows: levels up to this size run in the fused kernel")
     a = ap.parse_args()
     import scipy.sparse as sp
     import torch
@@ -61,13 +62,14 @@ def main():
     if a.peer and world > 1:
         comm.enable_peer_memory(g, all_gather)
     keys = dict(tolerance=1e-10, maxIters=500, preconditioner="amg", amgCoarsest=a.coarsest, amgTailRows=a.tail_rows,
-                amgPrecision=a.precision)
+                amgPrecision=a.precision, amgFuseRows=a.fuse_rows)
     fs = lid_driven_cavity(g, 1.0, 0.1, solver=keys)
     dt = 0.5 / a.nx
     fs.solve(dt)
     fs.p.fill(0.0)
     fs.pEqn.solve(warmStart=False)
     its_dev = fs.pEqn.solver.nIters()
+    fs_info = fs.pEqn.solver.amgInfo()
     owner, gid, lrow = g.i32("owner"), g.i32("globalId"), g.i32("localRow")
     mine = np.flatnonzero(owner == rank)
     order = mine[np.argsort(lrow[mine])]           # owned cells in local row order
@@ -119,6 +121,7 @@ def main():
         its_ref = bicgstab_iters(A, M, r, tol=1e-10)[0]
         tol = 1e-10 if a.precision == "double" else 2e-4
         ok = err < tol
+        info += ", %d launches per cycle" % int(fs_info["launchesPerCycle"])
         print("cycle check: %s, %d rank(s), rel. difference of one cycle %.3e (tolerance %.0e); BiCGStab iterations: device %d "
               "(pEqn_ rhs), transcription %d (random rhs)  %s" % (info, world, err, tol, its_dev, its_ref, "OK" if ok else "FAIL"),
               flush=True)
