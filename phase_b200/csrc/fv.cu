@@ -344,7 +344,7 @@ __global__ void k_lap_bnd(MeshView M, const int *__restrict__ faceType, double *
                           double *__restrict__ rhs, int ldr, double gammaConst, const double *__restrict__ gamF,
                           const double *__restrict__ gam0F, const double *__restrict__ phiF,
                           const double *__restrict__ phi0F, const double *__restrict__ phi0, int ldc,
-                          double theta, double sign) {
+                          double theta, double sign, double *__restrict__ tens) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M.nBCells) return;
   const bool steady = theta < 0.;
@@ -357,6 +357,24 @@ __global__ void k_lap_bnd(MeshView M, const int *__restrict__ faceType, double *
   for (int c = 0; c < NC; ++c) r[c] = 0.;
   for (int j = M.bcPtr[i]; j < M.bcPtr[i + 1]; ++j) {
     const int f = M.bcFace[j];
+    if (NC == 2 && !steady && tens && faceType[f] == PHB_SYMMETRY) {
+      // tangential slip (UD/Laplacian.cpp:33-41, 95-101): -theta c on the shared diagonal, + theta c tw (x) tw on the
+      // (cell, cell) block, source (1 - theta) c0 ((phi0 . tw) tw - phi0); tw = unit tangent of the face
+      const double g = M.fG[f];
+      const double coeff = (gamF ? gamF[f] : gammaConst) * g, coeff0 = (gam0F ? gam0F[f] : gammaConst) * g;
+      const double sm = sqrt(M.fSx[f] * M.fSx[f] + M.fSy[f] * M.fSy[f]);
+      const double tx = -M.fSy[f] / sm, ty = M.fSx[f] / sm;
+      diag -= th * coeff;
+      const size_t nL = (size_t)ldr;
+      tens[row] += sign * th * coeff * tx * tx;
+      tens[nL + row] += sign * th * coeff * tx * ty;
+      tens[2 * nL + row] += sign * th * coeff * ty * tx;
+      tens[3 * nL + row] += sign * th * coeff * ty * ty;
+      const double p0x = phi0[row], p0y = phi0[(size_t)ldc + row], d = p0x * tx + p0y * ty;
+      r[0] += (1. - theta) * coeff0 * (d * tx - p0x);
+      r[NC - 1] += (1. - theta) * coeff0 * (d * ty - p0y);
+      continue;
+    }
     if (faceType[f] != PHB_FIXED) continue;
     const double g = M.fG[f];
     const double coeff = (gamF ? gamF[f] : gammaConst) * g;
@@ -470,6 +488,9 @@ __global__ void k_scale_rows(MeshView M, double *__restrict__ vals, double *__re
 #pragma unroll
     for (int c = 0; c < NC; ++c) rhs[(size_t)c * ldr + row] *= s;
   END_FOR_EACH_ROW
+}
+__global__ void k_scale_tens(int n, const double *__restrict__ rho, double *__restrict__ tens) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * n; i += gridDim.x * blockDim.x) tens[i] *= rho[i % n];
 }
 // relax(omega): a_PP /= omega ; rhs_P -= (1-omega) a_PP phi_P
 template <int NC>
@@ -823,6 +844,8 @@ int phb_eqn_destroy(phb_eqn *e) { delete e; return PHB_OK; }
 int phb_eqn_zero(phb_eqn *e) {
   PHB_REQUIRE(e, "phb_eqn_zero: NULL argument");
   PHB_CHECK(e->vals.zero(e->m->ctx->stream));
+  if (e->tens.p) PHB_CHECK(e->tens.zero(e->m->ctx->stream));
+  e->hasTens = false;
   return e->rhs.zero(e->m->ctx->stream);
 }
 
@@ -914,16 +937,17 @@ int phb_assemble_laplacian(phb_eqn *e, double gammaConst, const phb_field *gam, 
   PHB_REQUIRE(!gam || (gam->nComp == 1 && gam->m == e->m), "phb_assemble_laplacian: gamma must be a scalar field");
   PHB_REQUIRE(theta < 0. || cphi->hasOld, "phb_assemble_laplacian: theta form needs a previous time step");
   phb_field *phi = const_cast<phb_field *>(cphi);
-  if (phi->nComp == 2)
-    for (const BcEntry &b : phi->bc)
-      if (b.type == PHB_SYMMETRY) {
-        phb::set_error("phb_assemble_laplacian: SYMMETRY on a vector field couples the components (tensor term, "
-                       "UD/Laplacian.cpp:33-41); not supported by the shared-coefficient equation");
-        return PHB_ERR_UNSUPPORTED;
-      }
-  PHB_CHECK(phb::field_face_types(phi));
   phb_mesh *m = e->m;
   phb_ctx *c = m->ctx;
+  double *tens = nullptr;
+  if (phi->nComp == 2 && theta >= 0.)     // the steady overloads are the primary templates: SYMMETRY adds nothing (UD/Laplacian.h:35-37)
+    for (const BcEntry &b : phi->bc)
+      if (b.type == PHB_SYMMETRY) {
+        if (!e->tens.p) { PHB_CHECK(e->tens.alloc(4 * (size_t)m->nLocal)); PHB_CHECK(e->tens.zero(c->stream)); }
+        e->hasTens = true;
+        tens = e->tens.p;
+      }
+  PHB_CHECK(phb::field_face_types(phi));
   const MeshView M = view(m);
   const double *gF = gam ? gam->faces.p : nullptr;
   const double *g0F = gam ? (gam->hasOld ? gam->faces0.p : gam->faces.p) : nullptr;
@@ -933,13 +957,13 @@ int phb_assemble_laplacian(phb_eqn *e, double gammaConst, const phb_field *gam, 
                m->nDev, theta, sign);
     if (m->nBCells)
       PHB_LAUNCH(c, k_lap_bnd<1>, gb, 256, 0, M, phi->dFaceType.p, e->vals.p, e->rhs.p, m->nLocal, gammaConst, gF,
-                 g0F, phi->faces.p, phi->faces0.p, phi->cells0.p, m->nDev, theta, sign);
+                 g0F, phi->faces.p, phi->faces0.p, phi->cells0.p, m->nDev, theta, sign, (double *)nullptr);
   } else {
     PHB_LAUNCH(c, k_lap<2>, grid, kThreads, 0, M, e->vals.p, e->rhs.p, m->nLocal, gammaConst, gF, g0F, phi->cells0.p,
                m->nDev, theta, sign);
     if (m->nBCells)
       PHB_LAUNCH(c, k_lap_bnd<2>, gb, 256, 0, M, phi->dFaceType.p, e->vals.p, e->rhs.p, m->nLocal, gammaConst, gF,
-                 g0F, phi->faces.p, phi->faces0.p, phi->cells0.p, m->nDev, theta, sign);
+                 g0F, phi->faces.p, phi->faces0.p, phi->cells0.p, m->nDev, theta, sign, tens);
   }
   return PHB_OK;
 }
@@ -1008,6 +1032,8 @@ int phb_eqn_scale_rows(phb_eqn *e, const phb_field *rho) {
     PHB_LAUNCH(m->ctx, k_scale_rows<1>, row_grid(m->ctx, m), kThreads, 0, M, e->vals.p, e->rhs.p, m->nLocal, rho->cells.p);
   else
     PHB_LAUNCH(m->ctx, k_scale_rows<2>, row_grid(m->ctx, m), kThreads, 0, M, e->vals.p, e->rhs.p, m->nLocal, rho->cells.p);
+  if (e->hasTens)
+    PHB_LAUNCH(m->ctx, k_scale_tens, flat_grid(m->ctx, 4ll * m->nLocal), kThreads, 0, m->nLocal, rho->cells.p, e->tens.p);
   return PHB_OK;
 }
 
@@ -1030,7 +1056,11 @@ long long phb_eqn_export_csr(const phb_eqn *e, int layout, int *rowPtr, int *col
   const SellPattern &S = m->sell;
   const int nL = m->nLocal, nc = e->nComp;
   PHB_REQUIRE(layout == 0 || nc == 1, "phb_eqn_export_csr: padded layouts are scalar-only");
-  std::vector<double> hv((size_t)S.nSlots), hr((size_t)nc * nL);
+  std::vector<double> hv((size_t)S.nSlots), hr((size_t)nc * nL), ht;
+  if (e->hasTens) {
+    ht.resize(4 * (size_t)nL);
+    PHB_CUDA(cudaMemcpyAsync(ht.data(), e->tens.p, ht.size() * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+  }
   PHB_CUDA(cudaMemcpyAsync(hv.data(), e->vals.p, hv.size() * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
   PHB_CUDA(cudaMemcpyAsync(hr.data(), e->rhs.p, hr.size() * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
   PHB_CUDA(cudaStreamSynchronize(m->ctx->stream));
@@ -1049,9 +1079,14 @@ long long phb_eqn_export_csr(const phb_eqn *e, int layout, int *rowPtr, int *col
       auto col = [&](int k) { return m->colInd[base + k] + comp * nL; };
       if (layout == 0) {
         for (int k = 0; k < len; ++k) {
-          const double v = hv[slot(d, k)];
+          double v = hv[slot(d, k)];
+          if (k == 0 && !ht.empty()) v += ht[(comp == 0 ? 0 : 3) * (size_t)nL + d];   // xx / yy join the diagonal
           if (k > 0 && v == 0.) continue;  // exact zeros are dropped by operator+= (M/CrsEquation.cpp:196-206)
           ci.push_back(col(k)); va.push_back(v);
+        }
+        if (!ht.empty()) {   // xy / yx: a new column (the cell's other component), appended by the merge, only when non-zero
+          const double x = ht[(comp == 0 ? 1 : 2) * (size_t)nL + d];
+          if (x != 0.) { ci.push_back(m->colInd[base] + (1 - comp) * nL); va.push_back(x); }
         }
       } else {
         // ELL-5: fv::laplacian(Scalar,phi) inserts nb0 first, then P (layout 1); the Field overload P first (layout 2)
@@ -1080,6 +1115,7 @@ int phb_eqn_solve(phb_eqn *e, phb_solver *s, phb_field *phi, int warmStart, int 
   phb_ctx *c = m->ctx;
   PHB_REQUIRE(s->ctx == c, "phb_eqn_solve: solver belongs to another context");
   PHB_CHECK(phb::solver_bind(s, &m->sell, e->vals.p, e->nComp, c->nProcs > 1 ? m : nullptr));
+  s->tens = e->hasTens ? e->tens.p : nullptr;
   const int n = m->nLocal, nc = e->nComp, ld = s->ld;
   PHB_LAUNCH(c, k_neg_copy, flat_grid(c, (long long)n * nc), kThreads, 0, n, nc, n, ld, e->rhs.p, s->b.p);
   if (warmStart)

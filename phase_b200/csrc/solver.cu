@@ -38,7 +38,7 @@ template <int NC, int EPI>
 __global__ void __launch_bounds__(kThreads)
 k_spmv(SellView A, const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
        int ld, const double *__restrict__ w, double *w2, KrylovSums *S, int maxIters,
-       double *partials, unsigned *ticket, int cur, int localFinish, PeerFuse F) {
+       double *partials, unsigned *ticket, int cur, int localFinish, PeerFuse F, TensorTerm TT) {
   if (EPI == 1 || EPI == 2) {
     if (krylov_done(S, maxIters)) return;
     if (F.on && F.waitHalo) halo_wait_block(F);  // the peers' ghost values of x have landed
@@ -57,6 +57,13 @@ k_spmv(SellView A, const double *__restrict__ vals, const double *__restrict__ x
     for (int i = 0; i < NC; ++i) acc[i] = 0.;
     slice_dot_any<NC>(A.col, vals, (size_t)off + lane, wdt, x, ld, acc);
     if (row < A.nRows) {
+      if (NC == 2 && TT.t) {   // (cell, cell) tensor block of SYMMETRY patches
+        const int o = TT.perm ? TT.perm[row] : row;
+        const double sc = TT.scale ? TT.scale[row] : 1.;
+        const double x0 = sc * x[row], x1 = sc * x[(size_t)ld + row];
+        acc[0] += TT.t[o] * x0 + TT.t[(size_t)TT.n + o] * x1;
+        acc[NC - 1] += TT.t[2 * (size_t)TT.n + o] * x0 + TT.t[3 * (size_t)TT.n + o] * x1;
+      }
 #pragma unroll
       for (int i = 0; i < NC; ++i) {
         const size_t idx = (size_t)i * ld + row;
@@ -270,12 +277,18 @@ void launch_spmv(phb_solver *s, const double *vals, const double *x, double *y, 
   const SellPattern *P = s->runPat ? s->runPat : s->pat;
   const SellView A = view_of(P);
   const int grid = spmv_grid(s->ctx, P);
+  TensorTerm TT;
+  if (s->tens && s->nComp == 2) {
+    TT.t = s->tens; TT.n = s->pat->nRows;
+    TT.scale = s->precond == PHB_PC_JACOBI && vals == s->scaled.p ? s->dinv.p : nullptr;
+    TT.perm = s->runPat == &s->ilu.pat ? s->ilu.new2old.p : nullptr;
+  }
   if (s->nComp == 1)
     PHB_LAUNCH(s->ctx, (k_spmv<1, EPI>), grid, kThreads, 0, A, vals, x, y, s->ld, w, w2, s->sums.p, s->maxIters,
-               s->partials.p, s->ticket.p, cur, localFinish, F);
+               s->partials.p, s->ticket.p, cur, localFinish, F, TT);
   else
     PHB_LAUNCH(s->ctx, (k_spmv<2, EPI>), grid, kThreads, 0, A, vals, x, y, s->ld, w, w2, s->sums.p, s->maxIters,
-               s->partials.p, s->ticket.p, cur, localFinish, F);
+               s->partials.p, s->ticket.p, cur, localFinish, F, TT);
 }
 
 // ghost refresh of a gathered vector before an SpMV (grid_->sendMessages analogue
@@ -439,6 +452,7 @@ int solver_bind(phb_solver *s, const SellPattern *pat, const double *dVals, int 
   const bool resized = (s->pat != pat) || s->nComp != nComp || s->ld != pat->nCols;
   s->pat = pat;
   s->dVals = dVals;
+  s->tens = nullptr;   // set by the equation after binding when it carries a tensor block
   s->nComp = nComp;
   s->ld = pat->nCols;
   s->halo = halo;
@@ -544,7 +558,8 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
     const int K = amg ? 2 : std::max(2, s->itersPerGraph & ~1);
     bool graphOk = s->useGraph;
     const void *key[4] = {s->runPat, Aw,
-                          (const void *)(intptr_t)(s->nComp * 1000003 + s->maxIters + 7919 * s->precond), s->halo};
+                          (const void *)(intptr_t)(s->nComp * 1000003 + s->maxIters + 7919 * s->precond + (s->tens ? 104729 : 0)),
+                          s->halo};
     if (graphOk && (!s->graphExec || memcmp(key, s->graphKey, sizeof(key)) != 0)) {
       if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }
       cudaGraph_t g = nullptr;

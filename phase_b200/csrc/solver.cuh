@@ -40,6 +40,14 @@ __device__ __forceinline__ bool krylov_done(const KrylovSums *S, int maxIters) {
   return !(S->rr > S->thresh) || S->iters >= (double)maxIters;
 }
 
+// tensor term of the operator as the SpMV kernels see it
+struct TensorTerm {
+  const double *t = nullptr;      // [4][n]
+  const double *scale = nullptr;  // Jacobi fold: the iterate is D x, the term acts on dinv .* iterate
+  const int *perm = nullptr;      // ILU: run row -> original row
+  int n = 0;
+};
+
 inline phb::SellView view_of(const SellPattern *P) {
   phb::SellView v;
   v.sliceOff = P->sliceOff.p;
@@ -168,6 +176,9 @@ struct phb_solver {
   int nComp = 1;
   int ld = 0;  // vector leading dimension (= pat->nCols)
   const phb_mesh *halo = nullptr;  // halo lists (nProcs > 1)
+  // 2 x 2 tensor on the (row, row) block of a two-component system ([xx | xy | yx | yy][nRows], SYMMETRY patches): part
+  // of the operator in every SpMV, left out of the preconditioners (they see the shared coefficients only)
+  const double *tens = nullptr;
   phb::DevBuf<double> scaled, dinv;
   IluData ilu;
   int iluOrdering = 0;             // 0 multicolour, 1 wavefront levels of the given ordering

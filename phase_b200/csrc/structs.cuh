@@ -93,6 +93,11 @@ struct phb_eqn {
   int nComp = 1;
   phb::DevBuf<double> vals;   // SELL slots (coefficients shared by components)
   phb::DevBuf<double> rhs;    // [comp][nLocal]
+  // vector equations with SYMMETRY patches: the 2 x 2 tensor the reference adds to the (cell, cell) block
+  // (add(cell, cell, Tensor2D), UE/VectorFiniteVolumeEquation.cpp:48-66) on top of the shared coefficients:
+  // [xx | xy | yx | yy][nLocal]; allocated on first use, hasTens = some entry may be non-zero
+  phb::DevBuf<double> tens;
+  bool hasTens = false;
 };
 
 struct phb_fracstep;

@@ -88,9 +88,53 @@ def make_bubble(name, nx, ny, w, h, K, dt):
     print(name, "written")
 
 
+def sheared_mesh(nx, ny, shear):
+    """nodes / cells / patch node pairs of an nx x ny quad lattice on the unit square sheared by x' = x + shear * y:
+    the x-/x+ boundaries are not axis-aligned, so a SYMMETRY patch there couples the velocity components"""
+    om = O.Mesh.rectilinear(nx, ny, 1.0, 1.0)
+    xy = np.stack([om.array("nodeX") + shear * om.array("nodeY"), om.array("nodeY")], axis=1)
+    fp, n1, n2 = om.array("facePatch"), om.array("faceN1"), om.array("faceN2")
+    patches = {}
+    for name in ("x-", "x+", "y-", "y+"):
+        sel = np.flatnonzero(fp == om.patch_id(name))
+        patches[name] = np.stack([n1[sel], n2[sel]], axis=1).reshape(-1)
+    return xy, om.array("cptr"), om.array("cind"), patches
+
+
+SYM_BCS = {"u": {"*": ("fixed", "(0,0)"), "y+": ("fixed", "(1,0)"), "x-": ("symmetry", "(0,0)"), "x+": ("symmetry", "(0,0)")},
+           "p": {"*": ("normal_gradient", "0")}}
+
+
+def make_symmetry(name, nx, ny, shear, K):
+    """FractionalStep with SYMMETRY velocity patches on slanted boundaries: the tensor terms of the vector Laplacian
+    (UD/Laplacian.cpp:33-41) and add(cell, cell, Tensor2D) (UE/VectorFiniteVolumeEquation.cpp:48-66)."""
+    xy, cptr, cind, patches = sheared_mesh(nx, ny, shear)
+    case = R.Case(nx, ny, 1.0, 1.0, 1.0, 0.1, bcs=SYM_BCS)
+    g = R.Grid.create(xy, cptr, cind)
+    for pn, nodes in patches.items():
+        g.patch_by_nodes(pn, nodes)
+    R.use_direct_solver()
+    fs = R.FracStep(case, g)
+    dt = 0.5 / nx
+    out = {"nx": nx, "ny": ny, "shear": shear, "K": K, "dt": dt, "xy": xy, "cptr": cptr, "cind": cind}
+    for pn, nodes in patches.items():
+        out["patch_" + pn] = nodes
+    for _ in range(K):
+        fs.step(dt)
+    for k in ("ux", "uy", "ufx", "ufy", "p", "gpx", "gpy"):
+        out["field_" + k] = fs.view(k)
+    for which in ("uEqn", "pEqn"):
+        rp, ci, va, b = fs.handoff(which)
+        out[which + "_rowPtr"], out[which + "_colInd"], out[which + "_vals"], out[which + "_b"] = rp, ci, va, b
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    fs.close(); g.close(); case.close()
+    print(name, "written")
+
+
 if __name__ == "__main__":
     if not R.available():
         sys.exit("the reference FV library is not available (needs /root/reference)")
     for c in CASES:
         make(*c)
     make_bubble("ref_bubble_24x48", 24, 48, 1.0, 2.0, 4, 1e-3)
+    make_symmetry("ref_symmetry_sheared_10x8", 10, 8, 0.25, 5)
