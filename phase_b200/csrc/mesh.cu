@@ -526,8 +526,8 @@ int phb_mesh_destroy(phb_mesh *m) {
 
 int phb_mesh_sizes(const phb_mesh *m, long long out[11]) {
   PHB_REQUIRE(m && out, "phb_mesh_sizes: NULL argument");
-  long long nb = 0;
-  for (int f = 0; f < m->nFaces; ++f) nb += m->fR[f] < 0;
+  long long nb = m->nBFaces;   // counted once by finalize
+  if (!m->finalized) { nb = 0; for (int f = 0; f < m->nFaces; ++f) nb += m->fR[f] < 0; }
   out[0] = m->nNodes; out[1] = m->nCells; out[2] = m->nFaces; out[3] = (long long)m->patchNames.size();
   out[4] = m->rank; out[5] = m->nProcs; out[6] = m->nLocal; out[7] = m->rowOffset;
   out[8] = m->nFaces - nb; out[9] = nb; out[10] = m->finalized ? (long long)m->rowPtr.back() : -1;
