@@ -52,3 +52,37 @@ def test_piso_cavity_steady_state(comm):
     ux = u2[0].reshape(n, n)
     assert ux[n - 2, n // 2] > 0.3 and ux[n // 4, n // 2] < 0.0
     ps.close(); fs.close(); g.close()
+
+
+@pytest.mark.parametrize("kind,nx,ny,inner,corr", [("rect", 24, 20, 1, 2), ("tri", 10, 9, 2, 1)])
+def test_piso_against_the_cpu_restatement(comm, kind, nx, ny, inner, corr):
+    """K PISO steps of the device module against oracle/piso.py, an independent numpy / scipy transcription of the
+    same equations (exact LU solves): u, p (minus mean), d, the mass imbalance."""
+    import oracle as O
+    from oracle.piso import Piso as OPiso
+    from phase_b200.api import FiniteVolumeGrid2D as G, Piso, FIXED, NORMAL_GRADIENT
+    om = (O.Mesh.rectilinear if kind == "rect" else O.Mesh.triangulated)(nx, ny, 1.0, 1.0)
+    g = (G.rectilinear if kind == "rect" else G.triangulated)(comm, nx, ny, 1.0, 1.0)
+    keys = dict(numInnerIterations=inner, numPressureCorrections=corr, momentumRelaxation=0.7, pressureCorrectionRelaxation=0.4)
+    ps = Piso(g, 1.2, 0.05, **keys)
+    ubc = {"x-": (FIXED, (0.0, 0.0)), "x+": (FIXED, (0.0, 0.0)), "y-": (FIXED, (0.0, 0.0)), "y+": (FIXED, (1.0, 0.0))}
+    pbc = {pt: (NORMAL_GRADIENT, 0.0) for pt in ("x-", "x+", "y-", "y+")}
+    for pt, (t, v) in ubc.items():
+        ps.u.setBoundary(pt, t, v)
+    for pt, (t, v) in pbc.items():
+        ps.p.setBoundary(pt, t, v)
+    cfg = dict(maxIters=20000, tolerance=1e-13, preconditioner="ilu0")
+    ps.uSolver.setup(cfg); ps.pCorrSolver.setup(cfg)
+    ps.initialize()
+    op = OPiso(om, 1.2, 0.05, ubc, pbc, inner, corr, 0.7, 0.4)
+    dt = 0.1
+    for _ in range(6):
+        st = ps.solve(dt)
+        mi = op.step(dt)
+    u, p = ps.u.get("cells"), ps.p.get("cells")
+    assert rel_l2(u[0], op.u[0]) < 1e-6 and rel_l2(u[1], op.u[1]) < 1e-6
+    assert rel_l2(p - p.mean(), op.p - op.p.mean()) < 1e-6
+    assert rel_l2(ps.d.get("cells"), op.d) < 1e-9
+    assert rel_l2(ps.u.get("faces"), op.uf) < 1e-6
+    assert abs(st["maxMassImbalance"] - mi) < 1e-8
+    ps.close(); g.close()
