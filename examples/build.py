@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 OUT = os.path.join(HERE, "_build")
-TARGETS = ["lid_driven_cavity", "seam1_solver", "phase_piso"]
+TARGETS = ["lid_driven_cavity", "seam1_solver", "phase_piso", "equation_ops"]
 
 
 def build(force=False):

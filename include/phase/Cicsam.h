@@ -27,7 +27,7 @@ inline void computeMomentumFlux(Scalar rho1, Scalar rho2, const VectorFiniteVolu
 inline FiniteVolumeEquation<Scalar> div(const VectorFiniteVolumeField &u, ScalarFiniteVolumeField &gamma,
                                         const ScalarFiniteVolumeField &beta, Scalar theta) {
   FiniteVolumeEquation<Scalar> eqn(gamma);
-  eqn.terms().push_back({phase::Term::CICSAM_DIV, 1., gamma.handle(), u.handle(), beta.handle(), 0., 0., theta, nullptr});
+  eqn.terms().push_back({phase::Term::CICSAM_DIV, 1., gamma.handle(), u.handle(), beta.handle(), 0., 0., theta, nullptr, {}});
   return eqn;
 }
 }  // namespace cicsam

@@ -22,22 +22,32 @@
 #include <algorithm>
 #include <cctype>
 
+#include <valarray>
+
 #include "CrsEquation.h"
 #include "FiniteVolumeField.h"
 #include "SparseMatrixSolverFactory.h"
+#include "Tensor2D.h"
 
 namespace phase {
 struct Term {
-  enum Kind { DDT, DIV, DIVE, LAPLACIAN, SRC, SRC_DIV, CICSAM_DIV } kind;
+  enum Kind { DDT, DIV, DIVE, LAPLACIAN, SRC, SRC_DIV, CICSAM_DIV, SRC_LAPLACIAN, DDT_CELLS, SRC_DIV_CELLS } kind;
   double sign;
   phb_field *phi, *u, *aux;  // phi: transported/solved field, u: advecting field, aux: rho / gamma field
   double c0, c1, c2;         // rho or gamma constant, dt, theta
   phb_field *rowScale;       // rho * (sub-expression)
+  std::vector<int> cells;    // cell-group overloads: ids of the group's cells
 };
 // right-hand-side vectors of src:: (evaluated on the device when they meet an equation)
 struct Source {
-  Term term;
+  std::vector<Term> terms;
 };
+inline Source operator+(Source l, const Source &r) { l.terms.insert(l.terms.end(), r.terms.begin(), r.terms.end()); return l; }
+inline Source operator-(Source l, const Source &r) {
+  for (Term t : r.terms) { t.sign = -t.sign; l.terms.push_back(t); }
+  return l;
+}
+inline Source operator-(Source s) { for (Term &t : s.terms) t.sign = -t.sign; return s; }
 }  // namespace phase
 
 template <class T> class FiniteVolumeEquation : public CrsEquation {
@@ -92,6 +102,34 @@ public:
   template <typename cell_iterator, typename coeff_iterator>
   void add(const Cell &cell, cell_iterator begin, cell_iterator end, coeff_iterator coeffs) {
     for (cell_iterator itr = begin; itr != end; ++itr, ++coeffs) add(cell, *itr, *coeffs);
+  }
+  // container overloads (UE/FiniteVolumeEquation.h:52-63)
+  void add(const Cell &cell, const std::vector<Ref<const Cell>> &nbs, const std::vector<Scalar> &vals) {
+    for (size_t i = 0; i < nbs.size(); ++i) add(cell, nbs[i].get(), vals[i]);
+  }
+  void add(const Cell &cell, const std::vector<Ref<const Cell>> &nbs, const std::valarray<Scalar> &vals) {
+    for (size_t i = 0; i < nbs.size(); ++i) add(cell, nbs[i].get(), vals[i]);
+  }
+  // component-wise and tensor coefficients of a vector equation (UE/VectorFiniteVolumeEquation.cpp:38-66): the
+  // off-diagonal tensor entries are only created when non-zero, "to avoid coupling whenever possible"
+  void add(const Cell &cell, const Cell &nb, const Vector2D &val) {
+    requireVector("add");
+    ensureHost();
+    addCoeff(row(cell, 0), col(nb, 0), val.x);
+    addCoeff(row(cell, 1), col(nb, 1), val.y);
+  }
+  void add(const Cell &cell, const Cell &nb, const Tensor2D &val) {
+    requireVector("add");
+    ensureHost();
+    addCoeff(row(cell, 0), col(nb, 0), val.xx);
+    if (val.xy != 0.) addCoeff(row(cell, 0), col(nb, 1), val.xy);
+    if (val.yx != 0.) addCoeff(row(cell, 1), col(nb, 0), val.yx);
+    addCoeff(row(cell, 1), col(nb, 1), val.yy);
+  }
+  // get(cell, nb): the coefficient(s) of nb in the row(s) of cell (UE/VectorFiniteVolumeEquation.cpp:68-76)
+  T get(const Cell &cell, const Cell &nb) {
+    ensureHost();
+    return getImpl(cell, nb, static_cast<T *>(nullptr));
   }
 
   // LinearAlgebra.<name>.lib selects the backend (FiniteVolumeEquation.tpp:47-62)
@@ -171,6 +209,14 @@ public:
   bool hostUsed() const { return hostUsed_; }
 
 protected:
+  void requireVector(const char *method) const {
+    if (FieldTraits<T>::nComp != 2)
+      throw Exception("FiniteVolumeEquation<T>", method, "Vector2D / Tensor2D coefficients need a vector equation.");
+  }
+  Scalar getImpl(const Cell &cell, const Cell &nb, Scalar *) { return coeff(row(cell, 0), col(nb, 0)); }
+  Vector2D getImpl(const Cell &cell, const Cell &nb, Vector2D *) {
+    return Vector2D(coeff(row(cell, 0), col(nb, 0)), coeff(row(cell, 1), col(nb, 1)));
+  }
   int nComp() const { return FieldTraits<T>::nComp; }
   static Scalar component(const Scalar &v, int) { return v; }
   static Scalar component(const Vector2D &v, int k) { return k == 0 ? v.x : v.y; }
@@ -230,6 +276,13 @@ protected:
         case phase::Term::SRC: rc = phb_assemble_src(e_, t.phi, t.sign); break;
         case phase::Term::SRC_DIV: rc = phb_assemble_src_div(e_, t.u, t.sign); break;
         case phase::Term::CICSAM_DIV: rc = phb_assemble_cicsam_div(e_, t.u, t.phi, t.aux, t.c2, t.sign); break;
+        case phase::Term::SRC_LAPLACIAN: rc = phb_assemble_src_laplacian(e_, t.c0, t.aux, t.phi, t.sign); break;
+        case phase::Term::DDT_CELLS:
+          rc = phb_assemble_ddt_cells(e_, t.phi, t.c1, t.sign, (int)t.cells.size(), t.cells.data());
+          break;
+        case phase::Term::SRC_DIV_CELLS:
+          rc = phb_assemble_src_div_cells(e_, t.u, t.sign, (int)t.cells.size(), t.cells.data());
+          break;
         }
         phase::check(rc, "FiniteVolumeEquation<T>", "operator=");
       }
@@ -260,9 +313,7 @@ template <class T> void append(FiniteVolumeEquation<T> &l, const FiniteVolumeEqu
 }
 template <class T> void append(FiniteVolumeEquation<T> &l, const Source &s, double sign) {
   if (l.hostUsed()) throw Exception("FiniteVolumeEquation<T>", "operator", "src:: terms need a device equation.");
-  Term t = s.term;
-  t.sign *= sign;
-  l.terms().push_back(t);
+  for (Term t : s.terms) { t.sign *= sign; l.terms().push_back(t); }
 }
 }  // namespace phase
 
@@ -288,33 +339,41 @@ template <class T> FiniteVolumeEquation<T> operator*(const ScalarFiniteVolumeFie
 namespace fv {
 template <typename T> FiniteVolumeEquation<T> ddt(Scalar rho, FiniteVolumeField<T> &field, Scalar timeStep) {
   FiniteVolumeEquation<T> eqn(field);
-  eqn.terms().push_back({phase::Term::DDT, 1., field.handle(), nullptr, nullptr, rho, timeStep, 0., nullptr});
+  eqn.terms().push_back({phase::Term::DDT, 1., field.handle(), nullptr, nullptr, rho, timeStep, 0., nullptr, {}});
   return eqn;
 }
 template <typename T>
 FiniteVolumeEquation<T> ddt(const ScalarFiniteVolumeField &rho, FiniteVolumeField<T> &field, Scalar timeStep) {
   FiniteVolumeEquation<T> eqn(field);
-  eqn.terms().push_back({phase::Term::DDT, 1., field.handle(), nullptr, rho.handle(), 1., timeStep, 0., nullptr});
+  eqn.terms().push_back({phase::Term::DDT, 1., field.handle(), nullptr, rho.handle(), 1., timeStep, 0., nullptr, {}});
   return eqn;
 }
 template <typename T> FiniteVolumeEquation<T> ddt(FiniteVolumeField<T> &field, Scalar timeStep) {
   return ddt(1., field, timeStep);
 }
+// the cells of a group only (UD/TimeDerivative.h:50-62; the immersed-boundary modules use it)
+template <typename T> FiniteVolumeEquation<T> ddt(FiniteVolumeField<T> &field, Scalar timeStep, const CellGroup &cells) {
+  FiniteVolumeEquation<T> eqn(field);
+  phase::Term t = {phase::Term::DDT_CELLS, 1., field.handle(), nullptr, nullptr, 1., timeStep, 0., nullptr, {}};
+  for (const Cell &c : cells) t.cells.push_back((int)c.id());
+  eqn.terms().push_back(t);
+  return eqn;
+}
 template <typename T>
 FiniteVolumeEquation<T> div(const VectorFiniteVolumeField &u, FiniteVolumeField<T> &phi, Scalar theta = 1.) {
   FiniteVolumeEquation<T> eqn(phi);
-  eqn.terms().push_back({phase::Term::DIV, 1., phi.handle(), u.handle(), nullptr, 0., 0., theta, nullptr});
+  eqn.terms().push_back({phase::Term::DIV, 1., phi.handle(), u.handle(), nullptr, 0., 0., theta, nullptr, {}});
   return eqn;
 }
 template <typename T>
 FiniteVolumeEquation<T> dive(const VectorFiniteVolumeField &u, FiniteVolumeField<T> &phi, Scalar theta) {
   FiniteVolumeEquation<T> eqn(phi);
-  eqn.terms().push_back({phase::Term::DIVE, 1., phi.handle(), u.handle(), nullptr, 0., 0., theta, nullptr});
+  eqn.terms().push_back({phase::Term::DIVE, 1., phi.handle(), u.handle(), nullptr, 0., 0., theta, nullptr, {}});
   return eqn;
 }
 template <class T> FiniteVolumeEquation<T> laplacian(Scalar gamma, FiniteVolumeField<T> &phi, Scalar theta) {
   FiniteVolumeEquation<T> eqn(phi);
-  eqn.terms().push_back({phase::Term::LAPLACIAN, 1., phi.handle(), nullptr, nullptr, gamma, 0., theta, nullptr});
+  eqn.terms().push_back({phase::Term::LAPLACIAN, 1., phi.handle(), nullptr, nullptr, gamma, 0., theta, nullptr, {}});
   return eqn;
 }
 template <class T> FiniteVolumeEquation<T> laplacian(Scalar gamma, FiniteVolumeField<T> &phi) {
@@ -323,7 +382,7 @@ template <class T> FiniteVolumeEquation<T> laplacian(Scalar gamma, FiniteVolumeF
 template <class T>
 FiniteVolumeEquation<T> laplacian(const ScalarFiniteVolumeField &gamma, FiniteVolumeField<T> &phi, Scalar theta) {
   FiniteVolumeEquation<T> eqn(phi);
-  eqn.terms().push_back({phase::Term::LAPLACIAN, 1., phi.handle(), nullptr, gamma.handle(), 0., 0., theta, nullptr});
+  eqn.terms().push_back({phase::Term::LAPLACIAN, 1., phi.handle(), nullptr, gamma.handle(), 0., 0., theta, nullptr, {}});
   return eqn;
 }
 template <class T> FiniteVolumeEquation<T> laplacian(const ScalarFiniteVolumeField &gamma, FiniteVolumeField<T> &phi) {
@@ -333,13 +392,28 @@ template <class T> FiniteVolumeEquation<T> laplacian(const ScalarFiniteVolumeFie
 
 namespace src {
 inline phase::Source div(const VectorFiniteVolumeField &field) {
-  return {{phase::Term::SRC_DIV, 1., nullptr, field.handle(), nullptr, 0., 0., 0., nullptr}};
+  return {{{phase::Term::SRC_DIV, 1., nullptr, field.handle(), nullptr, 0., 0., 0., nullptr, {}}}};
+}
+// src::div(field, cells) (UD/Source.cpp:5-21)
+inline phase::Source div(const VectorFiniteVolumeField &field, const CellGroup &cells) {
+  phase::Source s = {{{phase::Term::SRC_DIV_CELLS, 1., nullptr, field.handle(), nullptr, 0., 0., 0., nullptr, {}}}};
+  for (const Cell &c : cells) s.terms[0].cells.push_back((int)c.id());
+  return s;
+}
+// src::laplacian (UD/Source.cpp:27-75): sum over the links of gamma g_f (phi_nb - phi_P).  The reference's field
+// overload (:50-75) indexes a one-component index map out of bounds; its evident intent (the same scalar sum with
+// gamma taken at the faces) is what exists here.
+inline phase::Source laplacian(Scalar gamma, const ScalarFiniteVolumeField &phi) {
+  return {{{phase::Term::SRC_LAPLACIAN, 1., phi.handle(), nullptr, nullptr, gamma, 0., 0., nullptr, {}}}};
+}
+inline phase::Source laplacian(const ScalarFiniteVolumeField &gamma, const ScalarFiniteVolumeField &phi) {
+  return {{{phase::Term::SRC_LAPLACIAN, 1., phi.handle(), nullptr, gamma.handle(), 0., 0., 0., nullptr, {}}}};
 }
 inline phase::Source src(const ScalarFiniteVolumeField &field) {
-  return {{phase::Term::SRC, 1., field.handle(), nullptr, nullptr, 0., 0., 0., nullptr}};
+  return {{{phase::Term::SRC, 1., field.handle(), nullptr, nullptr, 0., 0., 0., nullptr, {}}}};
 }
 inline phase::Source src(const VectorFiniteVolumeField &field) {
-  return {{phase::Term::SRC, 1., field.handle(), nullptr, nullptr, 0., 0., 0., nullptr}};
+  return {{{phase::Term::SRC, 1., field.handle(), nullptr, nullptr, 0., 0., 0., nullptr, {}}}};
 }
 }  // namespace src
 
