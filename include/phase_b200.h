@@ -213,6 +213,21 @@ int phb_solver_bytes(const phb_solver *s, double out[2]);
  * info = [levels, operator complexity, host setup ms, setups so far, coarsest rows, kernel launches
  *         per cycle, iterations of the first solve after the last setup, hierarchy stale (0/1)] */
 int phb_solver_amg_info(const phb_solver *s, double info[8]);
+/* Numeric re-setup on the device (key `amgRefresh off | auto | always`, default auto; single-rank hierarchies): when the
+ * coefficients change on the same pattern -- pEqn_ = laplacian(dt / rho, p) of FractionalStepMultiphase
+ * (US/FractionalStepMultiphase.cpp:129-148), every uEqn_ -- the aggregates, strength flags and the patterns of
+ * P, R, A P, R A P of the last host setup are kept and the VALUES of every level (smoothed prolongators, Galerkin
+ * products, smoother weights, dense coarsest inverse) are recomputed by kernels from the resident matrix.  `auto`
+ * does so once the iteration count has drifted 20 % above the count after the setup; a refresh that does not bring it
+ * back triggers the host setup again.  phb_solver_amg_refresh forces one now.
+ * info = [refreshes since the last host setup, device ms of the last one, iterations of the first solve after it,
+ *         symbolic data resident (0/1), its bytes, 0, 0, 0] */
+int phb_solver_amg_refresh(phb_solver *s);
+int phb_solver_amg_refresh_info(const phb_solver *s, double info[8]);
+/* Values of one matrix of the hierarchy as the cycle streams them (sliced-ELL slot order, as double): which = 0
+ * operator (levels >= 1), 1 prolongator, 2 restriction, 3 smoother weights, 4 dense coarsest inverse.  Returns the
+ * count (out == NULL: only the count) or a negative error.  Test hook of the numeric re-setup. */
+long long phb_solver_amg_values(const phb_solver *s, int level, int which, double *out, long long cap);
 /* live timing (CUDA events, resident data) of the cycle's level-0 kernels and of one whole cycle:
  * out = ms per launch of [residual, restriction, prolongation, Jacobi sweep], ms per cycle, algorithmic bytes of
  * the Jacobi launch, of the cycle, launches per cycle (bench.py roofline leg; single rank) */

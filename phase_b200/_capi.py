@@ -68,6 +68,9 @@ SIGNATURES = {
     "phb_solver_apply_preconditioner": (ci, [vp, pd, pd, ci]),
     "phb_solver_bytes": (ci, [vp, pd]),
     "phb_solver_amg_info": (ci, [vp, pd]),
+    "phb_solver_amg_refresh": (ci, [vp]),
+    "phb_solver_amg_refresh_info": (ci, [vp, pd]),
+    "phb_solver_amg_values": (cll, [vp, ci, ci, pd, cll]),
     "phb_solver_time_amg": (ci, [vp, ci, pd]),
     "phb_amg_host_build": (ci, [ci, pi, pi, pd, cd, ci, pvp]),
     "phb_amg_host_levels": (ci, [vp, pi, pi, pi]),

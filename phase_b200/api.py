@@ -323,6 +323,23 @@ class SparseMatrixSolver:
                 "itersAfterSetup", "stale")
         return dict(zip(keys, (float(v) for v in out)))
 
+    def amgRefresh(self):
+        """numeric re-setup of the hierarchy on the device from the resident matrix values"""
+        check(self.L.phb_solver_amg_refresh(self.h))
+
+    def amgRefreshInfo(self):
+        out = (C.c_double * 8)()
+        check(self.L.phb_solver_amg_refresh_info(self.h, out))
+        keys = ("refreshes", "refreshMs", "itersAfterRefresh", "resident", "bytes")
+        return dict(zip(keys, (float(v) for v in out)))
+
+    def amgValues(self, level, which):
+        """values of A (0), P (1), R (2), smoother weights (3) of a level or the dense coarsest inverse (4)"""
+        n = check(self.L.phb_solver_amg_values(self.h, level, which, None, 0))
+        out = np.zeros(max(int(n), 1), np.float64)
+        check(self.L.phb_solver_amg_values(self.h, level, which, _dp(out), len(out)))
+        return out[:int(n)]
+
     def timeAmg(self, reps=20):
         out = (C.c_double * 8)()
         check(self.L.phb_solver_time_amg(self.h, reps, out))

@@ -215,6 +215,9 @@ struct HostLevel {
   HCsr A, P, R;
   std::vector<double> diag;  // of the (filtered) operator the smoother uses
   double rho = 2.;           // Gershgorin bound of rho(D^-1 A)
+  // kept for the numeric re-setup on the device (build_hierarchy(..., keepSymbolic)): aggregates, strength flags, pattern of A P
+  std::vector<int> agg, apRp, apCi;
+  std::vector<char> strong;
 };
 
 struct HostHierarchy {
@@ -363,6 +366,8 @@ int make_prolongator(const HCsr &A, double theta, double omegaP, int level, Host
     }
   });
   stitch(P, pci, pv, chunkBegin);
+  L.agg.swap(agg);
+  L.strong.swap(strong);
   return 0;
 }
 
@@ -379,7 +384,7 @@ bool rows_sum_to_zero(const HCsr &A) {
   return maxRow <= 1e-10 * maxDiag;
 }
 
-int build_hierarchy(HCsr A0, double theta, int coarsest, double omegaP, HostHierarchy &H) {
+int build_hierarchy(HCsr A0, double theta, int coarsest, double omegaP, HostHierarchy &H, bool keepSymbolic = false) {
   const auto t0 = std::chrono::steady_clock::now();
   H.lev.clear();
   if (A0.nnz() > 1200000000LL) {  // row pointers of the products are 32-bit
@@ -427,6 +432,8 @@ int build_hierarchy(HCsr A0, double theta, int coarsest, double omegaP, HostHier
       fprintf(stderr, "amg setup level %d (%d rows): prolongator %.0f ms, transpose %.0f, A*P %.0f, R*(AP) %.0f\n", level, n,
               ms(tL, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
     }
+    if (keepSymbolic) { L.apRp.swap(AP.rp); L.apCi.swap(AP.ci); }
+    else { std::vector<int>().swap(L.agg); std::vector<char>().swap(L.strong); }
     L.P = std::move(P);
     L.A = std::move(A);
     H.lev.push_back(std::move(L));
@@ -767,7 +774,8 @@ struct ThreadExchanger : Exchanger {
 };
 
 // sliced-ELL image of a host CSR matrix (diagonal moved to entry 0 when square)
-void sell_from_csr(const HCsr &A, bool diagFirst, SellPattern &S, std::vector<double> &slotVals) {
+void sell_from_csr(const HCsr &A, bool diagFirst, SellPattern &S, std::vector<double> &slotVals,
+                   std::vector<int> *slotSrc = nullptr) {
   S.nRows = A.n; S.nCols = A.m;
   S.nSlices = (A.n + 31) / 32;
   S.hRowLen.assign(A.n, 0);
@@ -782,6 +790,7 @@ void sell_from_csr(const HCsr &A, bool diagFirst, SellPattern &S, std::vector<do
   S.nSlots = S.hSliceOff[S.nSlices];
   S.hCol.assign(S.nSlots, 0);
   slotVals.assign(S.nSlots, 0.);
+  if (slotSrc) slotSrc->assign(S.nSlots, -1);   // CSR entry each slot holds (numeric re-setup)
   for (int sl = 0; sl < S.nSlices; ++sl) {
     const int w = (S.hSliceOff[sl + 1] - S.hSliceOff[sl]) / 32;
     for (int lane = 0; lane < 32; ++lane) {
@@ -794,12 +803,14 @@ void sell_from_csr(const HCsr &A, bool diagFirst, SellPattern &S, std::vector<do
             if (A.ci[j] == r) {
               const size_t slot = (size_t)S.hSliceOff[sl] + lane;
               S.hCol[slot] = r; slotVals[slot] = A.v[j]; k = 1;
+              if (slotSrc) (*slotSrc)[slot] = j;
               break;
             }
         for (int j = A.rp[r]; j < A.rp[r + 1]; ++j) {
           if (diagFirst && A.ci[j] == r) continue;
           const size_t slot = (size_t)S.hSliceOff[sl] + (size_t)k * 32 + lane;
           S.hCol[slot] = A.ci[j]; slotVals[slot] = A.v[j];
+          if (slotSrc) (*slotSrc)[slot] = j;
           ++k;
         }
       }
@@ -1206,13 +1217,165 @@ template <typename T> int upload_as(phb::DevBuf<double> &b, const std::vector<do
 }
 
 template <typename T>
-int upload_mat(phb_ctx *c, const HCsr &H, bool diagFirst, AmgMat &M) {
+int upload_mat(phb_ctx *c, const HCsr &H, bool diagFirst, AmgMat &M, phb::DevBuf<int> *slotSrc = nullptr) {
   std::vector<double> slotVals;
-  sell_from_csr(H, diagFirst, M.pat, slotVals);
+  std::vector<int> src;
+  sell_from_csr(H, diagFirst, M.pat, slotVals, slotSrc ? &src : nullptr);
+  if (slotSrc) PHB_CHECK(slotSrc->upload(src, c->stream));
   PHB_CHECK(M.pat.sliceOff.upload(M.pat.hSliceOff, c->stream));
   PHB_CHECK(M.pat.rowLen.upload(M.pat.hRowLen, c->stream));
   PHB_CHECK(M.pat.col.upload(M.pat.hCol, c->stream));
   PHB_CHECK(upload_as<T>(M.vals, slotVals, c->stream));
+  return PHB_OK;
+}
+
+
+// ===================================================================== numeric re-setup on the device
+#include "amg_refresh.cuh"
+
+// level-0 CSR entry -> sliced-ELL slot of the Krylov matrix; false when two slots of a row share a column (the host
+// setup sums them, the gather kernel cannot)
+bool csr_slot_sources(const SellPattern &S, const HCsr &A, std::vector<int> &src) {
+  src.assign(A.ci.size(), -1);
+  for (int r = 0; r < A.n; ++r) {
+    const int sl = r >> 5, lane = r & 31;
+    for (int k = 0; k < S.hRowLen[r]; ++k) {
+      const size_t slot = (size_t)S.hSliceOff[sl] + (size_t)k * 32 + lane;
+      const int c = S.hCol[slot];
+      if (c >= A.m) continue;
+      const auto b = A.ci.begin() + A.rp[r], e = A.ci.begin() + A.rp[r + 1];
+      const auto it = std::lower_bound(b, e, c);
+      if (it == e || *it != c) return false;
+      int &dst = src[it - A.ci.begin()];
+      if (dst >= 0) return false;
+      dst = (int)slot;
+    }
+  }
+  for (int v : src)
+    if (v < 0) return false;
+  return true;
+}
+
+// uploads the symbolic data of level l (h = its host level; `last`: no coarsening below it)
+int capture_level(phb_solver *s, const HostLevel &h, int l, bool last, AmgRefreshLevel &R, double &bytes) {
+  cudaStream_t st = s->ctx->stream;
+  R.n = h.A.n;
+  R.nnzA = h.A.nnz();
+  PHB_CHECK(R.aRp.upload(h.A.rp, st)); PHB_CHECK(R.aCi.upload(h.A.ci, st));
+  PHB_CHECK(R.aV.alloc((size_t)R.nnzA)); PHB_CHECK(R.diag.alloc((size_t)R.n));
+  bytes += 4. * (R.n + 1) + 12. * R.nnzA + 8. * R.n;
+  std::vector<int> src, rsrc;
+  std::vector<unsigned char> strong;
+  if (l == 0) {
+    if (!csr_slot_sources(*s->pat, h.A, src)) return 1;
+    PHB_CHECK(R.aSrc.upload(src, st));
+    bytes += 4. * R.nnzA;
+  }
+  if (!last) {
+    R.nc = h.P.m;
+    R.nnzP = h.P.nnz();
+    R.nnzAP = (long long)h.apCi.size();
+    strong.assign(h.strong.begin(), h.strong.end());
+    PHB_CHECK(R.strong.upload(strong, st)); PHB_CHECK(R.agg.upload(h.agg, st)); PHB_CHECK(R.df.alloc((size_t)R.n));
+    PHB_CHECK(R.pRp.upload(h.P.rp, st)); PHB_CHECK(R.pCi.upload(h.P.ci, st)); PHB_CHECK(R.pV.alloc((size_t)R.nnzP));
+    // R = P^T holds the entries of P in the order transpose() emits them
+    rsrc.resize((size_t)R.nnzP);
+    std::vector<int> fill(h.R.rp.begin(), h.R.rp.end() - 1);
+    for (int i = 0; i < h.P.n; ++i)
+      for (int k = h.P.rp[i]; k < h.P.rp[i + 1]; ++k) rsrc[fill[h.P.ci[k]]++] = k;
+    PHB_CHECK(R.rRp.upload(h.R.rp, st)); PHB_CHECK(R.rCi.upload(h.R.ci, st)); PHB_CHECK(R.rSrc.upload(rsrc, st));
+    PHB_CHECK(R.rV.alloc((size_t)R.nnzP));
+    PHB_CHECK(R.apRp.upload(h.apRp, st)); PHB_CHECK(R.apCi.upload(h.apCi, st)); PHB_CHECK(R.apV.alloc((size_t)R.nnzAP));
+    bytes += 1. * R.nnzA + 12. * R.n + 8. * (R.n + 1) + 4. * (R.nc + 1) + 32. * R.nnzP + 12. * R.nnzAP;
+  }
+  PHB_CUDA(cudaStreamSynchronize(st));   // the staging vectors go out of scope
+  return PHB_OK;
+}
+
+inline RfCsr rf_view(const phb::DevBuf<int> &rp, const phb::DevBuf<int> &ci, const phb::DevBuf<double> &v) {
+  return RfCsr{rp.p, ci.p, v.p};
+}
+
+// values of every level from the current level-0 matrix (s->dVals); the patterns, the cycle's buffers and the captured
+// graphs stay as they are
+template <typename T>
+int refresh_numeric(phb_solver *s) {
+  phb_ctx *c = s->ctx;
+  AmgData &D = s->amg;
+  AmgRefresh &F = *D.refresh;
+  const int nLev = (int)D.lev.size();
+  const double omegaP = 4. / 3.;
+  cudaEvent_t e0, e1;
+  PHB_CUDA(cudaEventCreate(&e0)); PHB_CUDA(cudaEventCreate(&e1));
+  PHB_CUDA(cudaEventRecord(e0, c->stream));
+  PHB_CHECK(F.scal.zero(c->stream));
+  PHB_CHECK(F.flag.zero(c->stream));
+  {
+    AmgRefreshLevel &R0 = *F.lev[0];
+    PHB_LAUNCH(c, k_rf_gather, grid_rows(c, R0.nnzA), kThreads, 0, R0.nnzA, R0.aSrc.p, s->dVals, R0.aV.p);
+  }
+  for (int l = 0; l < nLev; ++l) {
+    AmgRefreshLevel &R = *F.lev[l];
+    AmgLevel &L = *D.lev[l];
+    const bool last = l + 1 == nLev;
+    double *scal = F.scal.p + 4 * l;
+    const RfCsr A = rf_view(R.aRp, R.aCi, R.aV);
+    PHB_LAUNCH(c, k_rf_diag, grid_rows(c, R.n), kThreads, 0, R.n, A, last ? (const unsigned char *)nullptr : R.strong.p,
+               R.diag.p, last ? (double *)nullptr : R.df.p, scal);
+    PHB_LAUNCH(c, k_rf_weights<T>, grid_rows(c, R.n), kThreads, 0, R.n, R.diag.p, scal, D.omegaS, as<T>(L.w));
+    if (l > 0)
+      PHB_LAUNCH(c, k_rf_fill<T>, grid_rows(c, L.A.pat.nSlots), kThreads, 0, (long long)L.A.pat.nSlots, R.aSell.p, R.aV.p,
+                 as<T>(L.A.vals));
+    if (last) break;
+    AmgRefreshLevel &N = *F.lev[l + 1];
+    PHB_LAUNCH(c, k_rf_prolong<8>, grid_rows(c, 8LL * R.n), kThreads, 0, R.n, A, R.strong.p, R.agg.p, R.df.p, scal, omegaP,
+               R.pRp.p, R.pCi.p, R.pV.p);
+    PHB_LAUNCH(c, k_rf_permute, grid_rows(c, R.nnzP), kThreads, 0, R.nnzP, R.rSrc.p, R.pV.p, R.rV.p);
+    PHB_LAUNCH(c, k_rf_product<16>, grid_rows(c, 16LL * R.n), kThreads, 0, R.n, A, rf_view(R.pRp, R.pCi, R.pV), R.apRp.p,
+               R.apCi.p, R.apV.p);
+    PHB_LAUNCH(c, k_rf_product<16>, grid_rows(c, 16LL * R.nc), kThreads, 0, R.nc, rf_view(R.rRp, R.rCi, R.rV),
+               rf_view(R.apRp, R.apCi, R.apV), N.aRp.p, N.aCi.p, N.aV.p);
+    PHB_LAUNCH(c, k_rf_fill<T>, grid_rows(c, L.P.pat.nSlots), kThreads, 0, (long long)L.P.pat.nSlots, R.pSell.p, R.pV.p,
+               as<T>(L.P.vals));
+    PHB_LAUNCH(c, k_rf_fill<T>, grid_rows(c, L.R.pat.nSlots), kThreads, 0, (long long)L.R.pat.nSlots, R.rSell.p, R.rV.p,
+               as<T>(L.R.vals));
+  }
+  if (D.denseCoarse) {
+    AmgRefreshLevel &R = *F.lev[nLev - 1];
+    const int n = R.n;
+    double *scal = F.scal.p + 4 * (nLev - 1);
+    PHB_LAUNCH(c, k_rf_diag_mean, 1, 1024, 0, n, R.diag.p, scal);
+    PHB_LAUNCH(c, k_rf_dense_fill, grid_rows(c, (long long)n * n), kThreads, 0, n, scal, F.singular ? 1 : 0, F.dense[0].p);
+    PHB_LAUNCH(c, k_rf_dense_scatter, grid_rows(c, n), kThreads, 0, n, rf_view(R.aRp, R.aCi, R.aV), F.dense[0].p);
+    const int tiles = (n + kGjTile - 1) / kGjTile;
+    int cur = 0;
+    for (int k0 = 0; k0 < n; k0 += kGjBlock, cur ^= 1)
+      PHB_LAUNCH(c, k_rf_gj_step, dim3(tiles, tiles), 256, 0, n, k0, F.dense[cur].p, F.dense[cur ^ 1].p, F.flag.p);
+    PHB_CUDA(cudaMemcpyAsync(D.coarseInv.p, F.dense[cur].p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice,
+                             c->stream));
+  }
+  // level 0 of the cycle = the current matrix
+  PHB_CUDA(cudaMemcpyAsync(D.refVals.p, s->dVals, (size_t)s->pat->nSlots * sizeof(double), cudaMemcpyDeviceToDevice,
+                           c->stream));
+  if (sizeof(T) == 4)
+    PHB_LAUNCH(c, k_amg_to_float, grid_rows(c, s->pat->nSlots), kThreads, 0, s->pat->nSlots, D.refVals.p, D.refValsF.p);
+  PHB_CUDA(cudaEventRecord(e1, c->stream));
+  // zero diagonal on some level / vanishing pivot in the dense inverse: the host setup decides what to do
+  int flag = 0;
+  std::vector<double> scalH((size_t)4 * nLev);
+  PHB_CUDA(cudaMemcpyAsync(&flag, F.flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  PHB_CUDA(cudaMemcpyAsync(scalH.data(), F.scal.p, scalH.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PHB_CUDA(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  for (int l = 0; l < nLev; ++l)
+    if (scalH[4 * l + 3] != 0.) flag = 1;
+  if (flag) return 1;
+  D.refreshMs = ms;
+  D.refreshes++;
+  D.itersAfterRefresh = -1;
+  D.stale = false;
   return PHB_OK;
 }
 
@@ -1228,18 +1391,28 @@ int rebuild_t(phb_solver *s) {
                            c->stream));
   PHB_CUDA(cudaStreamSynchronize(c->stream));
   HostHierarchy H;
-  PHB_CHECK(build_hierarchy(csr_from_sell(*P, slotVals), D.theta, D.coarsest, 4. / 3., H));
+  const bool keep = D.refreshMode != 0;
+  PHB_CHECK(build_hierarchy(csr_from_sell(*P, slotVals), D.theta, D.coarsest, 4. / 3., H, keep));
   D.lev.clear();
   D.nDist = 0;
+  D.refresh.reset();
+  std::unique_ptr<AmgRefresh> F(keep ? new AmgRefresh() : nullptr);
   const int nLev = (int)H.lev.size();
   for (int l = 0; l < nLev; ++l) {
     std::unique_ptr<AmgLevel> L(new AmgLevel());
     HostLevel &h = H.lev[l];
     L->n = h.A.n;
-    if (l > 0) PHB_CHECK(upload_mat<T>(c, h.A, true, L->A));
+    AmgRefreshLevel *RL = nullptr;
+    if (F) { F->lev.emplace_back(new AmgRefreshLevel()); RL = F->lev.back().get(); }
+    if (l > 0) PHB_CHECK(upload_mat<T>(c, h.A, true, L->A, RL ? &RL->aSell : nullptr));
     if (l + 1 < nLev) {
-      PHB_CHECK(upload_mat<T>(c, h.P, false, L->P));
-      PHB_CHECK(upload_mat<T>(c, h.R, false, L->R));
+      PHB_CHECK(upload_mat<T>(c, h.P, false, L->P, RL ? &RL->pSell : nullptr));
+      PHB_CHECK(upload_mat<T>(c, h.R, false, L->R, RL ? &RL->rSell : nullptr));
+    }
+    if (F) {
+      const int rc = capture_level(s, h, l, l + 1 == nLev, *RL, F->bytes);
+      if (rc < 0) return rc;
+      if (rc > 0) F.reset();   // pattern the gather cannot follow: host setups only
     }
     std::vector<double> w(L->n);
     for (int i = 0; i < L->n; ++i) w[i] = (D.omegaS / h.rho) / h.diag[i];
@@ -1254,6 +1427,16 @@ int rebuild_t(phb_solver *s) {
   D.nCoarse = H.lev.back().A.n;
   D.denseCoarse = !H.coarseInv.empty();
   if (D.denseCoarse) PHB_CHECK(D.coarseInv.upload(H.coarseInv, c->stream));
+  if (F) {
+    F->singular = H.singular;
+    PHB_CHECK(F->scal.alloc((size_t)4 * nLev));
+    PHB_CHECK(F->flag.alloc(1));
+    if (D.denseCoarse)
+      for (int k = 0; k < 2; ++k) PHB_CHECK(F->dense[k].alloc((size_t)D.nCoarse * D.nCoarse));
+    D.refresh = std::move(F);
+  }
+  D.refreshes = 0;
+  D.itersAfterRefresh = -1;
   // level 0 operator of the cycle = the matrix the hierarchy was built from (kept in fp64 for the
   // change test, plus the float image the single-precision cycle streams)
   PHB_CHECK(D.refVals.alloc((size_t)P->nSlots));
@@ -1714,8 +1897,26 @@ int amg_prepare(phb_solver *s) {
     PHB_CUDA(cudaStreamSynchronize(c->stream));
     const double dev = c->pinned[0];
     D.stale = !(dev <= 1e-9);
-    if (D.stale && D.itersAfterSetup >= 0 && s->lastIters > std::max(2 * D.itersAfterSetup, D.itersAfterSetup + 10))
-      need = true;
+    if (D.stale) {
+      // coefficients changed on the same pattern.  Cheap answer: recompute the values of every level on the device with
+      // the aggregates and patterns as they are (once the iteration count has drifted 20 % from the count after the
+      // setup, or every time with `amgRefresh always`); a refresh that does not bring the count back means the
+      // aggregates no longer fit the coefficients, and the host setup runs again.
+      const int base = D.itersAfterSetup;
+      const bool doubled = base >= 0 && s->lastIters > std::max(2 * base, base + 10);
+      if (D.refresh && D.refreshMode != 0 && c->nProcs == 1) {
+        const bool inVain = D.refreshes > 0 && base >= 0 && D.itersAfterRefresh > std::max(2 * base, base + 10);
+        if (inVain) {
+          need = true;
+        } else if (D.refreshMode == 2 || (base >= 0 && s->lastIters > std::max((6 * base + 4) / 5, base + 2))) {
+          const int rc = D.single ? refresh_numeric<float>(s) : refresh_numeric<double>(s);
+          if (rc < 0) return rc;
+          if (rc > 0) need = true;
+        }
+      } else if (doubled) {
+        need = true;
+      }
+    }
     if (D.rebuildAlways && D.stale) need = true;
   }
   const bool dist = c->nProcs > 1 && s->halo && D.global;
@@ -1737,6 +1938,23 @@ int amg_prepare(phb_solver *s) {
 
 void amg_record_iters(phb_solver *s, int iters) {
   if (s->amg.built && s->amg.itersAfterSetup < 0) s->amg.itersAfterSetup = iters;
+  if (s->amg.built && s->amg.refreshes > 0 && s->amg.itersAfterRefresh == -1) s->amg.itersAfterRefresh = iters;
+}
+
+// `amgRefresh auto`, inside a solve: the hierarchy belongs to other coefficients and this solve has already used twice
+// the iterations the hierarchy needed when it was new
+bool amg_wants_refresh(const phb_solver *s, int itersSoFar) {
+  const AmgData &D = s->amg;
+  if (!D.stale || !D.refresh || D.refreshMode != 1 || s->ctx->nProcs != 1 || D.itersAfterSetup < 0) return false;
+  return itersSoFar >= std::max(2 * D.itersAfterSetup, D.itersAfterSetup + 10);
+}
+int amg_refresh_midsolve(phb_solver *s) {
+  AmgData &D = s->amg;
+  const int rc = D.single ? refresh_numeric<float>(s) : refresh_numeric<double>(s);
+  if (rc < 0) return rc;
+  D.stale = false;               // rc > 0 (vanishing pivot): keep the old values, do not try again in this solve
+  D.itersAfterRefresh = -2;      // the count of this solve includes the iterations spent before the refresh: not a measure
+  return PHB_OK;
 }
 
 // PHB_ERR_STATE when a grid barrier of the fused tail gave up (co-residency of the CTAs lost: should not happen
@@ -1753,6 +1971,9 @@ int amg_check(phb_solver *s) {
   }
   return PHB_OK;
 }
+
+int refresh_numeric_f(phb_solver *s) { return refresh_numeric<float>(s); }
+int refresh_numeric_d(phb_solver *s) { return refresh_numeric<double>(s); }
 
 int amg_launches_per_apply(const phb_solver *s) {
   const AmgData &D = s->amg;
@@ -2150,6 +2371,66 @@ int phb_solver_time_amg(phb_solver *s, int reps, double out[8]) {
 
 // [levels, operator complexity, setup ms (host), setups so far, coarsest rows, kernel launches per cycle,
 //  iterations of the first solve after the last setup, hierarchy currently stale (0/1)]
+// out: [0] refreshes since the last host setup, [1] ms of the last one (device time), [2] iterations of the first solve
+// after it, [3] 1 when the symbolic data for the numeric re-setup is resident, [4] its bytes
+int phb_solver_amg_refresh_info(const phb_solver *s, double out[8]) {
+  PHB_REQUIRE(s && out, "phb_solver_amg_refresh_info: NULL argument");
+  const AmgData &D = s->amg;
+  for (int k = 0; k < 8; ++k) out[k] = 0.;
+  out[0] = D.refreshes; out[1] = D.refreshMs; out[2] = D.itersAfterRefresh; out[3] = D.refresh ? 1. : 0.;
+  out[4] = D.refresh ? D.refresh->bytes : 0.;
+  return PHB_OK;
+}
+
+// Numeric re-setup now, from the matrix values resident in the solver (what `amgRefresh` does on its own when the
+// iteration count drifts).  PHB_ERR_STATE when there is no hierarchy or no symbolic data to refresh.
+int phb_solver_amg_refresh(phb_solver *s) {
+  PHB_REQUIRE(s, "phb_solver_amg_refresh: NULL solver");
+  AmgData &D = s->amg;
+  if (!D.built || !D.refresh || s->ctx->nProcs != 1 || !s->dVals) {
+    set_error("phb_solver_amg_refresh: no single-rank hierarchy with symbolic data (solve once with preconditioner amg, amgRefresh auto|always)");
+    return PHB_ERR_STATE;
+  }
+  const int rc = D.single ? phb::refresh_numeric_f(s) : phb::refresh_numeric_d(s);
+  if (rc > 0) {
+    set_error("phb_solver_amg_refresh: zero diagonal or vanishing pivot on a coarse level");
+    return PHB_ERR_BREAKDOWN;
+  }
+  return rc;
+}
+
+// Values of one matrix of the hierarchy as the cycle streams them (sliced-ELL slots, converted to double):
+// which = 0 operator (levels >= 1), 1 prolongator, 2 restriction, 3 smoother weights, 4 dense coarse inverse (level ignored).
+// Returns the number of values; with out == NULL only the count.
+long long phb_solver_amg_values(const phb_solver *s, int level, int which, double *out, long long cap) {
+  if (!s || !s->amg.built) { set_error("phb_solver_amg_values: no hierarchy"); return PHB_ERR_STATE; }
+  const AmgData &D = s->amg;
+  if (level < 0 || level >= (int)D.lev.size()) { set_error("phb_solver_amg_values: bad level"); return PHB_ERR_ARG; }
+  const AmgLevel &L = *D.lev[level];
+  const void *p = nullptr;
+  long long n = 0;
+  bool cyc = true;
+  if (which == 0 && level > 0) { p = L.A.vals.p; n = L.A.pat.nSlots; }
+  else if (which == 1 && level + 1 < (int)D.lev.size()) { p = L.P.vals.p; n = L.P.pat.nSlots; }
+  else if (which == 2 && level + 1 < (int)D.lev.size()) { p = L.R.vals.p; n = L.R.pat.nSlots; }
+  else if (which == 3) { p = L.w.p; n = L.n; }
+  else if (which == 4 && D.denseCoarse) { p = D.coarseInv.p; n = (long long)D.nCoarse * D.nCoarse; cyc = false; }
+  else { set_error("phb_solver_amg_values: level %d has no matrix %d", level, which); return PHB_ERR_ARG; }
+  if (!out) return n;
+  if (cap < n) { set_error("phb_solver_amg_values: buffer too small"); return PHB_ERR_ARG; }
+  cudaStream_t st = s->ctx->stream;
+  if (cyc && D.builtSingle) {
+    std::vector<float> t((size_t)n);
+    PHB_CUDA(cudaMemcpyAsync(t.data(), p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PHB_CUDA(cudaStreamSynchronize(st));
+    for (long long k = 0; k < n; ++k) out[k] = t[k];
+  } else {
+    PHB_CUDA(cudaMemcpyAsync(out, p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PHB_CUDA(cudaStreamSynchronize(st));
+  }
+  return n;
+}
+
 int phb_solver_amg_info(const phb_solver *s, double out[8]) {
   PHB_REQUIRE(s && out, "phb_solver_amg_info: NULL argument");
   const AmgData &D = s->amg;

@@ -506,6 +506,8 @@ int phb_mesh_finalize(phb_mesh *m) {
       if (m->fL[f] == c) m->slotL[f] = k; else m->slotR[f] = k;
     }
   }
+  m->nBFaces = 0;   // also on host-only contexts, where upload() has nothing to do
+  for (int f = 0; f < m->nFaces; ++f) m->nBFaces += m->fR[f] < 0;
   PHB_CHECK(upload(m));
   m->finalized = true;
   return PHB_OK;

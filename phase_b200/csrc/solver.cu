@@ -582,7 +582,7 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
                                 (s->precond == PHB_PC_ILU0 ? 2 * ilu_launches_per_apply(s) : 0) +
                                 (amg ? 2 * amg_launches_per_apply(s) : 0);
     int launched = 0, burst = 1;
-    bool done = false;
+    bool done = false, midRefresh = false;
     while (!done && launched < budget) {
       for (int g = 0; g < burst && launched < budget; ++g) {
         if (graphOk) {
@@ -597,6 +597,9 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
       PHB_CUDA(cudaStreamSynchronize(c->stream));
       done = !(hs->rr > hs->thresh) || hs->iters >= (double)budget;
       burst = amg ? 1 : std::min(burst * 2, 8);
+      // a hierarchy built for other coefficients that has already cost twice its usual iterations: stop here, recompute
+      // its values on the device and restart from the current x (`amgRefresh auto`)
+      if (!done && amg && amg_wants_refresh(s, totalIters + (int)hs->iters)) { midRefresh = true; break; }
     }
     // the x-update of the last completed iteration is still pending (it rides in the NEXT fused update)
     {
@@ -624,6 +627,7 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
       return PHB_ERR_BREAKDOWN;
     }
     if (rel <= s->tol * 1.0000001 || totalIters >= s->maxIters) break;
+    if (midRefresh) { PHB_CHECK(amg_refresh_midsolve(s)); --attempt; }
   }
   if (s->precond == PHB_PC_JACOBI) {
     if (s->nComp == 1)
@@ -726,6 +730,10 @@ int phb_solver_setup(phb_solver *s, const char *key, const char *value) {
   } else if (k == "amgRebuild") {
     PHB_REQUIRE(lv == "auto" || lv == "always", "amgRebuild must be \"auto\" or \"always\"");
     s->amg.rebuildAlways = lv == "always";
+  } else if (k == "amgRefresh") {  // numeric re-setup on the device when the coefficients change on a fixed pattern
+    PHB_REQUIRE(lv == "off" || lv == "auto" || lv == "always", "amgRefresh must be \"off\", \"auto\" or \"always\"");
+    s->amg.refreshMode = lv == "off" ? 0 : lv == "auto" ? 1 : 2;
+    s->amg.built = false;
   } else if (k == "peerFusion") {
     s->peerFused = std::stoi(v) != 0;
     if (s->graphExec) { cudaGraphExecDestroy(s->graphExec); s->graphExec = nullptr; }

@@ -129,8 +129,30 @@ struct AmgTailOp {
   void *y;                  // result
 };
 
+// Symbolic part of a setup kept on the device for the numeric re-setup (amg_refresh.cuh): per level the CSR pattern
+// of the operator, the strength flags and aggregates, the patterns of P, R = P^T and A P, and for every sliced-ELL
+// matrix of the cycle the CSR entry each slot holds.
+struct AmgRefreshLevel {
+  int n = 0, nc = 0;
+  long long nnzA = 0, nnzP = 0, nnzAP = 0;
+  phb::DevBuf<int> aRp, aCi, aSrc, agg, pRp, pCi, rRp, rCi, rSrc, apRp, apCi, aSell, pSell, rSell;
+  phb::DevBuf<unsigned char> strong;
+  phb::DevBuf<double> aV, diag, df, pV, rV, apV;
+};
+struct AmgRefresh {
+  std::vector<std::unique_ptr<AmgRefreshLevel>> lev;
+  phb::DevBuf<double> scal, dense[2];   // 4 scalars per level: rho, rhoP, mean diagonal, zero-diagonal flag
+  phb::DevBuf<int> flag;
+  bool singular = false;
+  double bytes = 0.;                    // device memory the symbolic data takes
+};
+
 struct AmgData {
   std::vector<std::unique_ptr<AmgLevel>> lev;
+  std::unique_ptr<AmgRefresh> refresh;      // single-rank hierarchies (`amgRefresh` != off)
+  int refreshMode = 1;                      // `amgRefresh`: 0 off | 1 auto (when the iteration count drifts) | 2 always
+  int refreshes = 0, itersAfterRefresh = -1;
+  double refreshMs = 0.;
   phb::DevBuf<double> coarseInv, refVals, chk;
   phb::DevBuf<float> refValsF;
   bool single = true, builtSingle = true;   // cycle precision (`amgPrecision single|double`)
@@ -222,6 +244,8 @@ int amg_prepare(phb_solver *s);
 int amg_apply(phb_solver *s, const double *in, double *out, bool inLoop);
 int amg_launches_per_apply(const phb_solver *s);
 void amg_record_iters(phb_solver *s, int iters);
+bool amg_wants_refresh(const phb_solver *s, int itersSoFar);
+int amg_refresh_midsolve(phb_solver *s);
 int amg_check(phb_solver *s);
 double amg_cycle_bytes(const phb_solver *s);
 int amg_time(phb_solver *s, int reps, double out[8]);

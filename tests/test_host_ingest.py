@@ -82,3 +82,22 @@ def test_uniform_refinement():
     assert ((fp2 >= 0) == (r.i32("faceR") < 0)).all()
     q = G.rectilinear(host(), 2, 2).refined(1)
     assert q.sizes()["nCells"] == 16 and np.allclose(q.f64("vol"), 1.0 / 16)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CGNS), reason="/root/reference absent")
+def test_cylinder_fixture_is_the_shipped_mesh():
+    """tests/golden/ref_cylinder_mesh.npz (what tools/cylinder_case.py runs config 3 from on the GPU box) rebuilds the mesh
+    the reader makes of the shipped CGNS file: same faces, patches and link order."""
+    from phase_b200.api import FiniteVolumeGrid2D as G
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cylinder_mesh.npz"))
+    c = host()
+    ref = G.from_cgns(c, REF_CGNS)
+    g = G.from_cells(c, d["xy"], np.arange(0, 3 * len(d["tris"]) + 1, 3), d["tris"].ravel())
+    for name in d["patch_order"]:
+        g.createPatchByNodes(str(name), d["patch_" + str(name)].ravel())
+    g.finalize()
+    assert g.patch_names() == ref.patch_names() == ["Cylinder", "TopBottom", "Inlet", "Outlet"]
+    for k in ("faceL", "faceR", "facePatch", "faceN1", "faceN2", "ilPtr", "ilCell", "ilFace", "blPtr", "blFace"):
+        assert np.array_equal(ref.i32(k), g.i32(k)), k
+    for k in ("vol", "faceSx", "faceSy"):
+        assert np.array_equal(ref.f64(k), g.f64(k)), k

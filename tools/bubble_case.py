@@ -28,6 +28,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--precond", default="amg", choices=["amg", "ilu0"])
+    ap.add_argument("--amg-refresh", default="auto", choices=["off", "auto", "always"],
+                    help="numeric re-setup of the multigrid hierarchy on the device when the coefficients change")
+    ap.add_argument("--dt-scale", type=float, default=1.0, help="multiplies the case's time step")
     a = ap.parse_args()
     import torch
     from phase_b200.api import FIXED, NORMAL_GRADIENT, Communicator, FiniteVolumeGrid2D as G, FractionalStepMultiphase
@@ -47,13 +50,15 @@ def main():
     mp.gamma.set("cells", np.clip(0.5 - d / h, 0.0, 1.0))
     mp.gamma.interpolateFaces()
     base = dict(solver="BICGSTAB", maxIters=5000, tolerance=a.tol)
+    if a.precond == "amg":
+        base["amgRefresh"] = a.amg_refresh
     mp.gammaEqn.solver.setup(dict(base, preconditioner="jacobi"))
     mp.uEqn.solver.setup(dict(base, preconditioner=a.precond))
     mp.pEqn.solver.setup(dict(base, preconditioner=a.precond))
     t0 = time.perf_counter()
     mp.initialize()
     t_init = time.perf_counter() - t0
-    dt = 2.5e-5 * (h / 0.01)
+    dt = 2.5e-5 * (h / 0.01) * a.dt_scale
     stream = torch.cuda.ExternalStream(comm.stream())
     stats = [mp.solve(dt) for _ in range(a.warmup)]
     torch.cuda.synchronize()
@@ -80,6 +85,7 @@ def main():
     if a.precond == "amg":
         line["amg_pEqn"] = mp.pEqn.solver.amgInfo()
         line["amg_uEqn"] = mp.uEqn.solver.amgInfo()
+        line["amg_refresh"] = {"mode": a.amg_refresh, "pEqn": mp.pEqn.solver.amgRefreshInfo(), "uEqn": mp.uEqn.solver.amgRefreshInfo()}
     print(json.dumps(line), flush=True)
     mp.close(); g.close(); comm.close()
 
