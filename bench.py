@@ -389,6 +389,7 @@ def parity_record(job, args):
 
 
 def refresh_record(args):
+    import numpy as np
     """Variable-density pressure operator (config 4's pEqn_) at the headline size with a bubble that moves every step:
     the multigrid values are recomputed on the device (amg_refresh.cuh), against a host setup from scratch per matrix."""
     from phase_b200.api import Communicator, SparseMatrixSolver

@@ -80,7 +80,7 @@ def test_equation_ops_cell_groups_and_tensor_entries(exes, tmp_path):
     nx, ny, w, h = 12, 9, 1.2, 0.9
     assert n == nx * ny
     om = O.Mesh.rectilinear(nx, ny, w, h)
-    cx, cy = om.array("cx"), om.array("cy")
+    cx, cy = om.array("cellCx"), om.array("cellCy")
     comm = Communicator(0)
     try:
         g = G.rectilinear(comm, nx, ny, w, h)
