@@ -98,7 +98,10 @@ def test_cavity_with_amg_pressure_solve(comm, kind, nx, ny, upc):
     assert info["setups"] == 1 and info["levels"] >= 3, info
     if upc == "amg":
         iu = gfs.uEqn.solver.amgInfo()
-        assert iu["setups"] == 1 and iu["stale"] == 1 and iu["levels"] >= 3, iu
+        # the convection term changes every step: the hierarchy either stays (stale) or had its values recomputed on
+        # the device (`amgRefresh auto`) -- never a second host setup
+        assert iu["setups"] == 1 and iu["levels"] >= 3, iu
+        assert iu["stale"] == 1 or gfs.uEqn.solver.amgRefreshInfo()["refreshes"] >= 1, iu
     u, p, po = gfs.u.get("cells"), gfs.p.get("cells"), ofs.view("p").copy()
     assert rel_l2(u[0], ofs.view("ux")) < TOL and rel_l2(u[1], ofs.view("uy")) < TOL
     assert rel_l2(p - p.mean(), po - po.mean()) < TOL
