@@ -243,6 +243,8 @@ int phb_amg_host_level_size(const phb_amg_host *h, int level, int which, int *nR
                             long long *nnz, double *rho);
 int phb_amg_host_level_csr(const phb_amg_host *h, int level, int which, int *rowPtr, int *colInd,
                            double *vals);
+/* smoother weights of a level = wScale / a_ii (Gershgorin rule on level 0, power-iteration rule on Galerkin levels) */
+int phb_amg_host_level_weight(const phb_amg_host *h, int level, double *wScale);
 int phb_amg_host_coarse_inverse(const phb_amg_host *h, double *inv);
 int phb_amg_host_destroy(phb_amg_host *h);
 /* The distributed setup used when nProcs > 1 (`amgScope global`): aggregates are rank-local, the prolongator

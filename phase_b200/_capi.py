@@ -76,6 +76,7 @@ SIGNATURES = {
     "phb_amg_host_levels": (ci, [vp, pi, pi, pi]),
     "phb_amg_host_level_size": (ci, [vp, ci, ci, pi, pi, C.POINTER(cll), pd]),
     "phb_amg_host_level_csr": (ci, [vp, ci, ci, pi, pi, pd]),
+    "phb_amg_host_level_weight": (ci, [vp, ci, pd]),
     "phb_amg_host_coarse_inverse": (ci, [vp, pd]),
     "phb_amg_host_destroy": (ci, [vp]),
     "phb_amg_dist_build": (ci, [ci, ci, pi, pi, pd, pi, cd, ci, cll, pvp]),

@@ -152,11 +152,32 @@ std::vector<double> diagonal(const HCsr &A) {
   return d;
 }
 
+// `amgTheta` (strength of connection, also filters the operator the prolongator is smoothed with) and `amgAggTheta`
+// (membership graph of the aggregates only).
+// Smoother rule: damped Jacobi with weight omegaS / rho_Gershgorin on the levels before `firstCoarse`, and
+// omegaC / lambda on the others, lambda a power-iteration estimate of the largest eigenvalue of D^-1 A (omegaC = 0:
+// the Gershgorin rule everywhere).  On Galerkin levels the Gershgorin bound (2 for every zero-row-sum M-matrix)
+// overestimates lambda (1.35-1.5) by a third and the sweep is correspondingly weak.
+struct Strength {
+  double theta, agg;
+  double omegaS = 1.8, omegaC = phb::kAmgCoarseWeight;
+  int firstCoarse = 1;
+  Strength(double t = 0., double a = phb::kAmgAggTheta) : theta(t), agg(a) {}
+};
+
+Strength strength_of(const AmgData &D) {
+  Strength st(D.theta, D.thetaAgg);
+  st.omegaS = D.omegaS;
+  st.omegaC = D.omegaC;
+  return st;
+}
+
 // Greedy aggregation on the strength graph |a_ij|^2 >= theta^2 |a_ii a_jj| (three passes: roots whose
 // strong neighbourhood is free, leftovers join a neighbouring aggregate, the rest seed new aggregates).
-int aggregate(const HCsr &A, const std::vector<double> &d, double theta, std::vector<int> &agg,
+int aggregate(const HCsr &A, const std::vector<double> &d, Strength st, std::vector<int> &agg,
               std::vector<char> &strong) {
   const int n = A.n;
+  const double theta = st.theta;
   strong.assign(A.ci.size(), 0);
   for (int i = 0; i < n; ++i)
     for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) {
@@ -165,6 +186,24 @@ int aggregate(const HCsr &A, const std::vector<double> &d, double theta, std::ve
       // columns >= n are ghosts (rows of another rank): aggregates and prolongator smoothing stay rank-local
       strong[k] = (j != i && j < n && a != 0. && a * a >= theta * theta * std::fabs(d[i] * d[j])) ? 1 : 0;
     }
+  // Membership graph of the aggregates: strong couplings that reach thetaAgg x the largest strong coupling of the row.
+  // The Galerkin operators of a smoothed prolongator carry many small long-range entries; with every one of them a
+  // member-maker, a root of a 17-entry row founds a 17-cell aggregate where 9 is typical, and a smooth error mode
+  // localised there survives the coarse correction (uniform Poisson, 4000 x 2000 cells: 21 iterations, 4001 x 2000: 10;
+  // with the filter 11 and 10).  The prolongator is still smoothed with the unfiltered strength graph, so this is not
+  // `amgTheta`: that one makes the variable-density and the momentum hierarchies worse (31 vs 21, stalled coarsening).
+  std::vector<char> sa(strong);
+  {
+    const double thetaAgg = st.agg;
+    if (thetaAgg > 0.)
+      for (int i = 0; i < n; ++i) {
+        double mx = 0.;
+        for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
+          if (strong[k]) mx = std::max(mx, std::fabs(A.v[k]));
+        for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
+          if (strong[k] && std::fabs(A.v[k]) < thetaAgg * mx) sa[k] = 0;
+      }
+  }
   agg.assign(n, -1);
   int nc = 0;
   // roots in natural order: on mesh-derived matrices this tiles the graph regularly; a scrambled order was tried and
@@ -173,11 +212,11 @@ int aggregate(const HCsr &A, const std::vector<double> &d, double theta, std::ve
     if (agg[i] >= 0) continue;
     bool free_ = true;
     for (int k = A.rp[i]; k < A.rp[i + 1] && free_; ++k)
-      if (strong[k] && agg[A.ci[k]] >= 0) free_ = false;
+      if (sa[k] && agg[A.ci[k]] >= 0) free_ = false;
     if (!free_) continue;
     agg[i] = nc;
     for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
-      if (strong[k]) agg[A.ci[k]] = nc;
+      if (sa[k]) agg[A.ci[k]] = nc;
     ++nc;
   }
   // leftovers join the neighbouring root aggregate they are coupled to most strongly (sum of |a_ij| over its
@@ -191,11 +230,11 @@ int aggregate(const HCsr &A, const std::vector<double> &d, double theta, std::ve
     int best = -1;
     double bestW = 0.;
     for (int k = A.rp[i]; k < A.rp[i + 1]; ++k) {
-      if (!strong[k] || agg[A.ci[k]] < 0) continue;
+      if (!sa[k] || agg[A.ci[k]] < 0) continue;
       const int a = agg[A.ci[k]];
       double w = 0.;
       for (int q = A.rp[i]; q < A.rp[i + 1]; ++q)
-        if (strong[q] && agg[A.ci[q]] == a) w += std::fabs(A.v[q]);
+        if (sa[q] && agg[A.ci[q]] == a) w += std::fabs(A.v[q]);
       if (best < 0 || w > bestW * (1. + 1e-12) || (w >= bestW * (1. - 1e-12) && size[a] < size[best])) { best = a; bestW = w; }
     }
     if (best >= 0) { pass2[i] = best; size[best]++; }
@@ -205,7 +244,7 @@ int aggregate(const HCsr &A, const std::vector<double> &d, double theta, std::ve
     if (agg[i] >= 0) continue;
     agg[i] = nc;
     for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
-      if (strong[k] && agg[A.ci[k]] < 0) agg[A.ci[k]] = nc;
+      if (sa[k] && agg[A.ci[k]] < 0) agg[A.ci[k]] = nc;
     ++nc;
   }
   return nc;
@@ -215,6 +254,7 @@ struct HostLevel {
   HCsr A, P, R;
   std::vector<double> diag;  // of the (filtered) operator the smoother uses
   double rho = 2.;           // Gershgorin bound of rho(D^-1 A)
+  double wScale = 0.9;       // smoother weights = wScale / a_ii (omegaS / rho, or omegaC / lambda on Galerkin levels)
   // kept for the numeric re-setup on the device (build_hierarchy(..., keepSymbolic)): aggregates, strength flags, pattern of A P
   std::vector<int> agg, apRp, apCi;
   std::vector<char> strong;
@@ -304,11 +344,56 @@ double gershgorin(const HCsr &A, const std::vector<double> &d) {
   return rho;
 }
 
+// largest eigenvalue of D^-1 A by power iteration from a fixed pseudo-random vector (row-parallel, independent of the
+// thread count up to the rounding of the norms)
+double power_lambda(const HCsr &A, const std::vector<double> &d, int iters = 20) {
+  const int n = A.n;
+  std::vector<double> x(n), y(n);
+  for (int i = 0; i < n; ++i) {
+    unsigned h = (unsigned)i * 2654435761u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    x[i] = ((h & 1u) ? 1. : -1.) * (0.5 + (double)((h >> 8) & 0xffffu) / 65536.);
+  }
+  double lam = 0.;
+  for (int it = 0; it < iters; ++it) {
+    const int T = chunk_count(n);
+    std::vector<double> nx(T, 0.), ny(T, 0.);
+    parallel_chunks(n, [&](int begin, int end, int t) {
+      double sx = 0., sy = 0.;
+      for (int i = begin; i < end; ++i) {
+        double acc = 0.;
+        for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
+          if (A.ci[k] < n) acc += A.v[k] * x[A.ci[k]];
+        y[i] = acc / d[i];
+        sx += x[i] * x[i]; sy += y[i] * y[i];
+      }
+      nx[t] = sx; ny[t] = sy;
+    });
+    double sx = 0., sy = 0.;
+    for (int t = 0; t < T; ++t) { sx += nx[t]; sy += ny[t]; }
+    if (!(sx > 0.) || !(sy > 0.)) return 0.;
+    lam = std::sqrt(sy / sx);
+    const double inv = 1. / std::sqrt(sy);
+    for (int i = 0; i < n; ++i) x[i] = y[i] * inv;
+  }
+  return lam;
+}
+
+// smoother weight scale of a level (HostLevel::wScale); L.diag and L.rho are set
+void smoother_rule(const HCsr &A, const Strength &st, int level, HostLevel &L) {
+  L.wScale = st.omegaS / L.rho;
+  if (st.omegaC > 0. && level >= st.firstCoarse) {
+    const double lam = power_lambda(A, L.diag);
+    // the iteration approaches lambda from below: 5 % on top, never beyond the bound, never below half of it
+    if (lam > 0.) L.wScale = st.omegaC / std::min(L.rho, std::max(0.5 * L.rho, 1.05 * lam));
+  }
+}
+
 // One coarsening step on the rows of A (A.n owned rows; columns >= A.n are ghosts): fills the smoother data of
 // L and the prolongator P = (I - (omegaP / rho) Df^-1 Af) T with T(i, agg[i]) = 1 and Af the operator with weak
 // and ghost couplings lumped onto the diagonal (so that P reproduces the constant whenever A does).
 // Returns 1 when the level cannot be coarsened any further, 0 on success, < 0 on error.
-int make_prolongator(const HCsr &A, double theta, double omegaP, int level, HostLevel &L, HCsr &P, int &nc,
+int make_prolongator(const HCsr &A, Strength theta, double omegaP, int level, HostLevel &L, HCsr &P, int &nc,
                      bool allowStall = false) {
   const int n = A.n;
   std::vector<double> d = diagonal(A);
@@ -384,7 +469,7 @@ bool rows_sum_to_zero(const HCsr &A) {
   return maxRow <= 1e-10 * maxDiag;
 }
 
-int build_hierarchy(HCsr A0, double theta, int coarsest, double omegaP, HostHierarchy &H, bool keepSymbolic = false) {
+int build_hierarchy(HCsr A0, Strength theta, int coarsest, double omegaP, HostHierarchy &H, bool keepSymbolic = false) {
   const auto t0 = std::chrono::steady_clock::now();
   H.lev.clear();
   if (A0.nnz() > 1200000000LL) {  // row pointers of the products are 32-bit
@@ -413,6 +498,7 @@ int build_hierarchy(HCsr A0, double theta, int coarsest, double omegaP, HostHier
       rc = make_prolongator(A, theta, omegaP, level, L, P, nc);
       if (rc < 0) return rc;
     }
+    smoother_rule(A, theta, level, L);
     if (rc == 1) {  // coarsest level (or coarsening stalled)
       L.A = std::move(A);
       H.lev.push_back(std::move(L));
@@ -503,7 +589,7 @@ template <typename T> T take(const char *&p) {
   return v;
 }
 
-int build_dist_hierarchy(Exchanger &ex, HCsr A, Halo halo, std::vector<int> gid, double theta, int coarsest,
+int build_dist_hierarchy(Exchanger &ex, HCsr A, Halo halo, std::vector<int> gid, Strength theta, int coarsest,
                          long long tailRows, double omegaP, DistHierarchy &H) {
   const auto t0 = std::chrono::steady_clock::now();
   const int NP = ex.nProcs, me = ex.rank;
@@ -529,6 +615,7 @@ int build_dist_hierarchy(Exchanger &ex, HCsr A, Halo halo, std::vector<int> gid,
     if (!bad) {
       D.L.diag = d;
       D.L.rho = gershgorin(A, d);
+      D.L.wScale = theta.omegaS / D.L.rho;   // distributed levels: Gershgorin rule (no distributed power iteration)
       nc = aggregate(A, d, theta, agg, strong);
     }
     // ---- exchange 0: coarse sizes + the aggregate of every cell a neighbour holds as a ghost
@@ -741,7 +828,9 @@ int build_dist_hierarchy(Exchanger &ex, HCsr A, Halo halo, std::vector<int> gid,
       G.rp.push_back((int)G.ci.size());
     }
   }
-  PHB_CHECK(build_hierarchy(std::move(G), theta, coarsest, omegaP, H.tail.H));
+  Strength tailRule = theta;
+  tailRule.firstCoarse = 0;   // the gathered level is a Galerkin level of the global hierarchy
+  PHB_CHECK(build_hierarchy(std::move(G), tailRule, coarsest, omegaP, H.tail.H));
   H.setupMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return PHB_OK;
 }
@@ -1322,7 +1411,7 @@ int refresh_numeric(phb_solver *s) {
     const RfCsr A = rf_view(R.aRp, R.aCi, R.aV);
     PHB_LAUNCH(c, k_rf_diag, grid_rows(c, R.n), kThreads, 0, R.n, A, last ? (const unsigned char *)nullptr : R.strong.p,
                R.diag.p, last ? (double *)nullptr : R.df.p, scal);
-    PHB_LAUNCH(c, k_rf_weights<T>, grid_rows(c, R.n), kThreads, 0, R.n, R.diag.p, scal, D.omegaS, as<T>(L.w));
+    PHB_LAUNCH(c, k_rf_weights<T>, grid_rows(c, R.n), kThreads, 0, R.n, R.diag.p, scal, L.omegaEff, as<T>(L.w));
     if (l > 0)
       PHB_LAUNCH(c, k_rf_fill<T>, grid_rows(c, L.A.pat.nSlots), kThreads, 0, (long long)L.A.pat.nSlots, R.aSell.p, R.aV.p,
                  as<T>(L.A.vals));
@@ -1392,7 +1481,7 @@ int rebuild_t(phb_solver *s) {
   PHB_CUDA(cudaStreamSynchronize(c->stream));
   HostHierarchy H;
   const bool keep = D.refreshMode != 0;
-  PHB_CHECK(build_hierarchy(csr_from_sell(*P, slotVals), D.theta, D.coarsest, 4. / 3., H, keep));
+  PHB_CHECK(build_hierarchy(csr_from_sell(*P, slotVals), strength_of(D), D.coarsest, 4. / 3., H, keep));
   D.lev.clear();
   D.nDist = 0;
   D.refresh.reset();
@@ -1415,7 +1504,8 @@ int rebuild_t(phb_solver *s) {
       if (rc > 0) F.reset();   // pattern the gather cannot follow: host setups only
     }
     std::vector<double> w(L->n);
-    for (int i = 0; i < L->n; ++i) w[i] = (D.omegaS / h.rho) / h.diag[i];
+    for (int i = 0; i < L->n; ++i) w[i] = h.wScale / h.diag[i];
+    L->omegaEff = h.wScale * h.rho;
     PHB_CHECK(upload_as<T>(L->w, w, c->stream));
     L->ld = l == 0 ? P->nCols : L->n;                      // level 0 vectors carry (zero) ghost entries
     const size_t len = (size_t)L->ld * s->nComp;
@@ -1479,7 +1569,8 @@ int finish_level(phb_solver *s, AmgLevel &L, const HostLevel &h, int ld, bool ha
     PHB_CHECK(upload_mat<T>(c, h.R, false, L.R));
   }
   std::vector<double> w(L.n);
-  for (int i = 0; i < L.n; ++i) w[i] = (D.omegaS / h.rho) / h.diag[i];
+  for (int i = 0; i < L.n; ++i) w[i] = h.wScale / h.diag[i];
+  L.omegaEff = h.wScale * h.rho;
   PHB_CHECK(upload_as<T>(L.w, w, c->stream));
   L.ld = ld;
   const size_t len = (size_t)ld * s->nComp;
@@ -1602,7 +1693,7 @@ int rebuild_dist_t(phb_solver *s) {
   ex.rank = me; ex.nProcs = NP; ex.c = c;
   g_hostRanks = NP;   // the ranks of one node share its cores
   DistHierarchy H;
-  PHB_CHECK(build_dist_hierarchy(ex, std::move(A0), std::move(h0), std::move(gid), D.theta, D.coarsest, D.tailRows,
+  PHB_CHECK(build_dist_hierarchy(ex, std::move(A0), std::move(h0), std::move(gid), strength_of(D), D.coarsest, D.tailRows,
                                  4. / 3., H));
   D.lev.clear();
   D.peer.reset();
@@ -2334,6 +2425,12 @@ int phb_amg_host_level_size(const phb_amg_host *h, int level, int which, int *nR
   PHB_REQUIRE(M, "phb_amg_host_level_size: no matrix %d on level %d", which, level);
   *nRows = M->n; *nCols = M->m; *nnz = M->nnz();
   if (rho) *rho = h->H.lev[level].rho;
+  return PHB_OK;
+}
+
+int phb_amg_host_level_weight(const phb_amg_host *h, int level, double *wScale) {
+  PHB_REQUIRE(h && wScale && level >= 0 && level < (int)h->H.lev.size(), "phb_amg_host_level_weight: bad argument");
+  *wScale = h->H.lev[level].wScale;
   return PHB_OK;
 }
 

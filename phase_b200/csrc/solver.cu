@@ -705,6 +705,9 @@ int phb_solver_setup(phb_solver *s, const char *key, const char *value) {
   } else if (k == "amgTheta") {
     s->amg.theta = std::stod(v); s->amg.built = false;
     PHB_REQUIRE(s->amg.theta >= 0. && s->amg.theta < 1., "amgTheta must lie in [0, 1)");
+  } else if (k == "amgAggTheta") {
+    s->amg.thetaAgg = std::stod(v); s->amg.built = false;
+    PHB_REQUIRE(s->amg.thetaAgg >= 0. && s->amg.thetaAgg <= 1., "amgAggTheta must lie in [0, 1]");
   } else if (k == "amgCoarsest") {
     s->amg.coarsest = std::stoi(v); s->amg.built = false;
     PHB_REQUIRE(s->amg.coarsest >= 1 && s->amg.coarsest <= 1024, "amgCoarsest must lie in 1..1024 (dense coarsest solve)");
@@ -715,6 +718,9 @@ int phb_solver_setup(phb_solver *s, const char *key, const char *value) {
   } else if (k == "amgSmootherWeight") {
     s->amg.omegaS = std::stod(v); s->amg.built = false;
     PHB_REQUIRE(s->amg.omegaS > 0. && s->amg.omegaS < 2., "amgSmootherWeight must lie in (0, 2)");
+  } else if (k == "amgCoarseSmootherWeight") {
+    s->amg.omegaC = std::stod(v); s->amg.built = false;
+    PHB_REQUIRE(s->amg.omegaC >= 0. && s->amg.omegaC < 2., "amgCoarseSmootherWeight must lie in [0, 2)");
   } else if (k == "amgPrecision") {
     PHB_REQUIRE(lv == "single" || lv == "double" || lv == "float", "amgPrecision must be \"single\" or \"double\"");
     s->amg.single = lv != "double";

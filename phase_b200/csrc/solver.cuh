@@ -76,10 +76,19 @@ struct AmgMat {
   SellPattern pat;
   phb::DevBuf<double> vals;        // bytes: float or double values per `amgPrecision`
 };
+namespace phb {
+// `amgAggTheta` default: a coupling makes its neighbour a member of the row's aggregate when it reaches this fraction
+// of the row's largest coupling (amg.cu: aggregate)
+constexpr double kAmgAggTheta = 0.1;
+// `amgCoarseSmootherWeight` default: Jacobi weight omegaC / lambda_max(D^-1 A) on the Galerkin levels (0: Gershgorin rule)
+constexpr double kAmgCoarseWeight = 1.6;
+}  // namespace phb
+
 struct AmgLevel {
   int n = 0, ld = 0;               // rows, leading dimension of the level vectors
   AmgMat A, P, R;                  // level operator (levels >= 1), prolongator n x n_c, restriction n_c x n
   phb::DevBuf<double> w;           // smoother weight omega / a_ii
+  double omegaEff = 1.8;           // w = omegaEff / rho_Gershgorin / a_ii: what the numeric re-setup rescales
   phb::DevBuf<double> x, x2, b, r;
   // distributed levels (nProcs > 1, `amgScope global`): the operator has ghost columns, refreshed by a
   // neighbour exchange before every residual / smoothing sweep
@@ -172,7 +181,7 @@ struct AmgData {
   // smoother weight omegaS / rho(D^-1 A): 1.8 instead of the textbook 4/3 -- inside a Krylov method the stronger damping of
   // the mid-range modes wins (scipy transcription, 1M cells: 10-12 instead of 13-15 iterations; 11-13 % fewer on the
   // variable-density and 7-point operators); |1 - 1.8 lambda / rho| <= 0.8 for every mode, so the sweep stays a contraction
-  double theta = 0., omegaS = 1.8, setupMs = 0., opComplexity = 1.;
+  double theta = 0., thetaAgg = phb::kAmgAggTheta, omegaS = 1.8, omegaC = phb::kAmgCoarseWeight, setupMs = 0., opComplexity = 1.;
 };
 
 struct phb_solver {

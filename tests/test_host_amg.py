@@ -64,12 +64,17 @@ class HostAmg:
         assert self.L.phb_amg_host_coarse_inverse(self.h, inv.ctypes.data_as(_capi.pd)) == 0
         return inv
 
-    def cycle(self, nu=1, omega_s=1.8):
+    def weight_scale(self, level):
+        f = C.c_double()
+        assert self.L.phb_amg_host_level_weight(self.h, level, C.byref(f)) == 0
+        return f.value
+
+    def cycle(self, nu=1):
         """scipy transcription of amg_apply() (amg.cu)"""
         lv = []
         for l in range(self.nLevels):
             A, rho = self.mat(l, 0)
-            e = dict(A=A, w=(omega_s / rho) / A.diagonal())
+            e = dict(A=A, w=self.weight_scale(l) / A.diagonal())
             if l + 1 < self.nLevels:
                 e["P"] = self.mat(l, 1)[0]
                 e["R"] = self.mat(l, 2)[0]

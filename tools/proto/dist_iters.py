@@ -13,7 +13,7 @@ def dist_cycle(A, part, coarsest, tail_rows, omega=1.8):
         P = H.global_matrix(l, 1, (Al.shape[0], nc)); R = H.global_matrix(l, 2, (nc, Al.shape[0]))
         An = H.global_matrix(l + 1, 0, (nc, nc)) if l + 1 < H.nDist else H.tail(0).mat(0, 0)[0]
         levels.append((Al, P, R)); Al = An
-    tail = H.tail(0).cycle(omega_s=omega)
+    tail = H.tail(0).cycle()
     def cyc(l, b):
         if l == H.nDist: return tail(b)
         A_, P_, R_ = levels[l]
