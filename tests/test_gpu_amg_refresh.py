@@ -96,7 +96,10 @@ def test_refresh_follows_moving_interface(comm, mode):
     if mode == "always":
         assert all(a <= 1.2 * b + 2 for a, b in zip(iters, fresh)), (iters, fresh)
     else:
-        assert max(iters) <= 2 * max(fresh) + 10
+        # worst case of `auto`: a stale hierarchy is given up inside a solve after max(2 f, f + 10) iterations, the solve
+        # restarts from the current iterate with the refreshed one (<= 1.2 f + 2, the bound of `always`)
+        f = max(fresh)
+        assert max(iters) <= max(2 * f, f + 10) + 1.2 * f + 2, (iters, fresh)
     s.close()
 
 
