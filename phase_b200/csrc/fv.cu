@@ -392,6 +392,46 @@ __global__ void k_lap_bnd(MeshView M, const int *__restrict__ faceType, double *
   for (int c = 0; c < NC; ++c) rhs[(size_t)c * ldr + row] += sign * r[c];
 }
 
+// The momentum predictor of FractionalStep in ONE pass over the rows (US/FractionalStep.cpp:82-83):
+//   fv::ddt(u, dt) + fv::div(u, u, 0) == fv::laplacian(gamma, u, 0.5) - src::src(gradP)
+// i.e. k_ddt + k_div<NC,0>(theta 0) + k_lap(theta 0.5, sign -1) + k_src on a zeroed equation, term sums kept apart
+// and added in that order.  Every slot and rhs entry of a live row is WRITTEN (no zero-fill, no read-modify-write):
+// 4 launches and 3 extra sweeps over `vals` less.  Boundary links follow in k_div_bnd / k_lap_bnd as before.
+template <int NC>
+__global__ void k_momentum_fused(MeshView M, double *__restrict__ vals, double *__restrict__ rhs, int ldr,
+                                 const double *__restrict__ u0F, const double *__restrict__ phi0, int ldc,
+                                 const double *__restrict__ gradP, double gamma, double dt) {
+  FOR_EACH_ROW(M)
+    const double V = M.vol[row];
+    double p0[NC], rDiv[NC], rLap[NC], diagLap = 0.;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { p0[c] = phi0[(size_t)c * ldc + row]; rDiv[c] = 0.; rLap[c] = 0.; }
+    for (int k = 1; k < wdt; ++k) {
+      const size_t slot = slot0 + (size_t)k * 32;
+      const int lf = M.linkFace[slot];
+      if (lf < 0) { vals[slot] = 0.; continue; }
+      const int f = lf >> 1, nb = M.A.col[slot];
+      const double sg = (lf & 1) ? -1. : 1.;
+      const double flux0 = sg * (u0F[f] * M.fSx[f] + u0F[(size_t)M.nFaces + f] * M.fSy[f]);
+      const double a = fmax(flux0, 0.), b = fmin(flux0, 0.);
+      const double coeff = gamma * M.fG[f];
+      vals[slot] = -(0.5 * coeff);
+      diagLap -= 0.5 * coeff;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const double pn = phi0[(size_t)c * ldc + nb];
+        rDiv[c] += a * p0[c];
+        rDiv[c] += b * pn;
+        rLap[c] += (0.5 * coeff) * (pn - p0[c]);
+      }
+    }
+    vals[slot0] = V / dt - diagLap;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      rhs[(size_t)c * ldr + row] = ((-V * p0[c] / dt + rDiv[c]) - rLap[c]) + gradP[(size_t)c * ldc + row] * V;
+  END_FOR_EACH_ROW
+}
+
 // src::laplacian: rhs[row] += sign * sum c (phi_nb - phi_P)
 __global__ void k_src_lap(MeshView M, double *__restrict__ rhs, double gammaConst, const double *__restrict__ gamF,
                           const double *__restrict__ phi, double sign) {
@@ -968,6 +1008,40 @@ int phb_assemble_laplacian(phb_eqn *e, double gammaConst, const phb_field *gam, 
   return PHB_OK;
 }
 
+}  // extern "C"
+
+namespace phb {
+// uEqn_ of FractionalStep in one pass (k_momentum_fused) + the two boundary launches.  Returns 1 when the fused
+// form does not apply (SYMMETRY patches carry a tensor block): the caller then assembles term by term.
+int assemble_momentum_predictor(phb_eqn *e, phb_field *u, const phb_field *gradP, double gamma, double dt) {
+  PHB_CHECK(check_pair(e, u, "assemble_momentum_predictor"));
+  PHB_CHECK(check_pair(e, gradP, "assemble_momentum_predictor"));
+  PHB_REQUIRE(e->nComp == 2 && u->nComp == 2 && gradP->nComp == 2, "assemble_momentum_predictor: vector equation expected");
+  PHB_REQUIRE(u->hasOld, "assemble_momentum_predictor: u has no previous time step (savePreviousTimeStep)");
+  PHB_REQUIRE(dt > 0., "assemble_momentum_predictor: dt must be positive");
+  for (const BcEntry &b : u->bc)
+    if (b.type == PHB_SYMMETRY) return 1;
+  phb_mesh *m = e->m;
+  phb_ctx *c = m->ctx;
+  PHB_CHECK(phb::field_face_types(u));
+  if (e->tens.p) PHB_CHECK(e->tens.zero(c->stream));
+  e->hasTens = false;
+  const MeshView M = view(m);
+  const int grid = row_grid(c, m), gb = (m->nBCells + 255) / 256;
+  PHB_LAUNCH(c, k_momentum_fused<2>, grid, kThreads, 0, M, e->vals.p, e->rhs.p, m->nLocal, u->faces0.p, u->cells0.p,
+             m->nDev, gradP->cells.p, gamma, dt);
+  if (m->nBCells) {
+    PHB_LAUNCH(c, (k_div_bnd<2, 0>), gb, 256, 0, M, u->dFaceType.p, e->vals.p, e->rhs.p, m->nLocal, u->faces.p,
+               u->faces0.p, u->faces0.p, u->faces.p, u->faces0.p, u->faces0.p, u->cells0.p, m->nDev, 0., +1.);
+    PHB_LAUNCH(c, k_lap_bnd<2>, gb, 256, 0, M, u->dFaceType.p, e->vals.p, e->rhs.p, m->nLocal, gamma,
+               (const double *)nullptr, (const double *)nullptr, u->faces.p, u->faces0.p, u->cells0.p, m->nDev, 0.5,
+               -1., (double *)nullptr);
+  }
+  return PHB_OK;
+}
+}  // namespace phb
+
+extern "C" {
 int phb_assemble_src(phb_eqn *e, const phb_field *f, double sign) {
   PHB_CHECK(check_pair(e, f, "phb_assemble_src"));
   PHB_REQUIRE(f->nComp == e->nComp, "phb_assemble_src: component mismatch");

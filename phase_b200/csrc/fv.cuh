@@ -11,6 +11,8 @@ int field_axpy_cells(phb_field *y, double a, const phb_field *x);  // owned cell
 int field_axpy_faces(phb_field *y, double a, const phb_field *x);  // all faces
 int field_send_messages(phb_field *f);
 int field_all_neumann(phb_field *f, bool *out);
+// FractionalStep's uEqn_ (ddt + div == laplacian(gamma, theta 0.5) - src(gradP)) in one pass; 1 = not applicable
+int assemble_momentum_predictor(phb_eqn *e, phb_field *u, const phb_field *gradP, double gamma, double dt);
 // device max over owned cells of |sum_f u_f.S_f| (mode 0) or the Courant number (mode 1)
 int field_flux_max(const phb_field *u, int mode, double dt, DevBuf<double> &scratch, DevBuf<double> &partials,
                    DevBuf<unsigned> &ticket, double *devOut);

@@ -44,6 +44,24 @@ def test_ueqn_peqn_reference_layout(comm, kind, nx, ny):
     gfs.close(); g.close()
 
 
+@pytest.mark.parametrize("kind,nx,ny", [("rect", 33, 31), ("tri", 14, 12)])
+def test_fused_momentum_assembly_equals_term_by_term(comm, kind, nx, ny):
+    """phb_fs_assemble_u in one pass (k_momentum_fused) against the same equation assembled one operator at a time
+    (fusedAssembly 0): identical pattern, coefficients and right-hand side to rounding."""
+    om, ofs = oracle_cavity(kind, nx, ny, 1.0, 0.8)
+    g, gfs = gpu_cavity(comm, kind, nx, ny, 1.0, 0.8)
+    set_random_state(ofs, gfs, seed=11)
+    dt = 0.007
+    fused = gfs.assembleU(dt).export(0)
+    gfs.setup(fusedAssembly=0)
+    terms = gfs.assembleU(dt).export(0)
+    gfs.setup(fusedAssembly=1)
+    assert_eqn_equal(fused, terms, rtol=1e-14)
+    assert np.abs(fused[3]).max() > 0
+    assert_eqn_equal(fused, ofs.assemble_u(dt).export())
+    gfs.close(); g.close()
+
+
 def test_normal_gradient_and_fixed_pressure(comm):
     """outflow-type setup: u normal_gradient on x+, p fixed there (Channel-like)."""
     from phase_b200.api import FiniteVolumeGrid2D as G, FractionalStep, FIXED, NORMAL_GRADIENT
