@@ -76,7 +76,8 @@ public:
                                  "ordering", "nullSpace", "itersPerGraph",
                                  // preconditioner amg (the reference's `lib muelu` role)
                                  "amgTheta", "amgCoarsest", "amgSweeps", "amgSmootherWeight", "amgPrecision",
-                                 "amgRebuild", "amgScope", "amgTailRows"};
+                                 "amgRebuild", "amgScope", "amgTailRows", "amgFuseRows", "amgRefresh", "amgAggTheta",
+                                 "amgCoarseSmootherWeight"};
     for (const char *k : keys) {
       const boost::property_tree::ptree *c = p.get_child_optional(k);
       if (c) phase::check(phb_solver_setup(s_, k, c->data().c_str()), "B200SparseMatrixSolver", "setup");

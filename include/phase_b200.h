@@ -208,7 +208,9 @@ int phb_solver_bytes(const phb_solver *s, double out[2]);
  * Math/TrilinosMueluSparseMatrixSolver.cpp:27-32).  Extra setup keys: amgTheta (strength threshold, 0),
  * amgCoarsest (rows of the densely inverted coarsest level, at most 1000 = default), amgSweeps (Jacobi sweeps before and
  * after the coarse correction, 1), amgSmootherWeight (1.8, divided by the Gershgorin bound of
- * rho(D^-1 A)), amgRebuild (auto | always).  The hierarchy is built on the host once per matrix and
+ * rho(D^-1 A); level 0), amgCoarseSmootherWeight (1.6, divided by a power-iteration estimate of lambda_max(D^-1 A);
+ * Galerkin levels; 0 = Gershgorin rule everywhere), amgAggTheta (0.1: couplings below this fraction of the row's largest
+ * do not make a neighbour a member of the row's aggregate), amgRebuild (auto | always).  The hierarchy is built on the host once per matrix and
  * reused while the matrix stays a scalar multiple of it or the iteration count does not degrade.
  * info = [levels, operator complexity, host setup ms, setups so far, coarsest rows, kernel launches
  *         per cycle, iterations of the first solve after the last setup, hierarchy stale (0/1)] */

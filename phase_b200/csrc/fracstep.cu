@@ -25,7 +25,7 @@ struct phb_fracstep {
   int guessOrder = 1;
   phb::DevBuf<double> pPrev;  // p^(n-1), owned cells
   int nStepsDone = 0;
-  bool fusedAssembly = true;     // uEqn_ in one pass over the rows ("fusedAssembly" 0: one kernel per operator)
+  bool fusedAssembly = true;     // uEqn_ and pEqn_ each in one pass over the rows ("fusedAssembly" 0: one kernel per operator)
 };
 
 namespace {
@@ -119,6 +119,7 @@ int phb_fs_assemble_u(phb_fracstep *fs, double dt) {
 // pEqn_ = (fv::laplacian(dt, p) == src::div(u))  (US/FractionalStep.cpp:97)
 int phb_fs_assemble_p(phb_fracstep *fs, double dt) {
   PHB_REQUIRE(fs && dt > 0., "phb_fs_assemble_p: bad argument");
+  if (fs->fusedAssembly) return phb::assemble_pressure_poisson(fs->pEqn, fs->p, fs->u, dt);
   PHB_CHECK(phb_eqn_zero(fs->pEqn));
   PHB_CHECK(phb_assemble_laplacian(fs->pEqn, dt, nullptr, fs->p, -1., +1.));
   PHB_CHECK(phb_assemble_src_div(fs->pEqn, fs->u, -1.));

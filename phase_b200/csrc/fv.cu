@@ -432,6 +432,27 @@ __global__ void k_momentum_fused(MeshView M, double *__restrict__ vals, double *
   END_FOR_EACH_ROW
 }
 
+// pEqn_ of FractionalStep in one pass (US/FractionalStep.cpp:97):  fv::laplacian(dt, p) == src::div(u), i.e. the steady
+// k_lap<1> (sign +1) + k_flux_sum<0> (sign -1) on a zeroed equation; every slot and rhs entry of a live row is written.
+__global__ void k_pressure_fused(MeshView M, double *__restrict__ vals, double *__restrict__ rhs,
+                                 const double *__restrict__ uF, double gamma) {
+  FOR_EACH_ROW(M)
+    double diag = 0., d = 0.;
+    for (int k = 1; k < wdt; ++k) {
+      const size_t slot = slot0 + (size_t)k * 32;
+      const int lf = M.linkFace[slot];
+      if (lf < 0) { vals[slot] = 0.; continue; }
+      const int f = lf >> 1;
+      const double coeff = gamma * M.fG[f];
+      vals[slot] = coeff;
+      diag -= coeff;
+      d += ((lf & 1) ? -1. : 1.) * (uF[f] * M.fSx[f] + uF[(size_t)M.nFaces + f] * M.fSy[f]);
+    }
+    vals[slot0] = diag;
+    rhs[row] = -d;
+  END_FOR_EACH_ROW
+}
+
 // src::laplacian: rhs[row] += sign * sum c (phi_nb - phi_P)
 __global__ void k_src_lap(MeshView M, double *__restrict__ rhs, double gammaConst, const double *__restrict__ gamF,
                           const double *__restrict__ phi, double sign) {
@@ -1036,6 +1057,27 @@ int assemble_momentum_predictor(phb_eqn *e, phb_field *u, const phb_field *gradP
     PHB_LAUNCH(c, k_lap_bnd<2>, gb, 256, 0, M, u->dFaceType.p, e->vals.p, e->rhs.p, m->nLocal, gamma,
                (const double *)nullptr, (const double *)nullptr, u->faces.p, u->faces0.p, u->cells0.p, m->nDev, 0.5,
                -1., (double *)nullptr);
+  }
+  return PHB_OK;
+}
+// pEqn_ of FractionalStep in one pass (k_pressure_fused) + the two boundary launches
+int assemble_pressure_poisson(phb_eqn *e, phb_field *p, const phb_field *u, double gamma) {
+  PHB_CHECK(check_pair(e, p, "assemble_pressure_poisson"));
+  PHB_CHECK(check_pair(e, u, "assemble_pressure_poisson"));
+  PHB_REQUIRE(e->nComp == 1 && p->nComp == 1 && u->nComp == 2, "assemble_pressure_poisson: scalar equation, vector flux field");
+  phb_mesh *m = e->m;
+  phb_ctx *c = m->ctx;
+  PHB_CHECK(phb::field_face_types(p));
+  if (e->tens.p) PHB_CHECK(e->tens.zero(c->stream));
+  e->hasTens = false;
+  const MeshView M = view(m);
+  const int gb = (m->nBCells + 255) / 256;
+  PHB_LAUNCH(c, k_pressure_fused, row_grid(c, m), kThreads, 0, M, e->vals.p, e->rhs.p, u->faces.p, gamma);
+  if (m->nBCells) {
+    PHB_LAUNCH(c, k_lap_bnd<1>, gb, 256, 0, M, p->dFaceType.p, e->vals.p, e->rhs.p, m->nLocal, gamma,
+               (const double *)nullptr, (const double *)nullptr, p->faces.p, p->faces0.p, p->cells0.p, m->nDev, -1., +1.,
+               (double *)nullptr);
+    PHB_LAUNCH(c, k_flux_sum_bnd<0>, gb, 256, 0, M, u->faces.p, e->rhs.p, -1., 0., (const int *)nullptr);
   }
   return PHB_OK;
 }

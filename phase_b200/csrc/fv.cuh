@@ -12,6 +12,8 @@ int field_axpy_faces(phb_field *y, double a, const phb_field *x);  // all faces
 int field_send_messages(phb_field *f);
 int field_all_neumann(phb_field *f, bool *out);
 // FractionalStep's uEqn_ (ddt + div == laplacian(gamma, theta 0.5) - src(gradP)) in one pass; 1 = not applicable
+// FractionalStep's pEqn_ (laplacian(gamma, p) == src::div(u)) in one pass
+int assemble_pressure_poisson(phb_eqn *e, phb_field *p, const phb_field *u, double gamma);
 int assemble_momentum_predictor(phb_eqn *e, phb_field *u, const phb_field *gradP, double gamma, double dt);
 // device max over owned cells of |sum_f u_f.S_f| (mode 0) or the Courant number (mode 1)
 int field_flux_max(const phb_field *u, int mode, double dt, DevBuf<double> &scratch, DevBuf<double> &partials,

@@ -45,7 +45,7 @@ def test_ueqn_peqn_reference_layout(comm, kind, nx, ny):
 
 
 @pytest.mark.parametrize("kind,nx,ny", [("rect", 33, 31), ("tri", 14, 12)])
-def test_fused_momentum_assembly_equals_term_by_term(comm, kind, nx, ny):
+def test_fused_assembly_equals_term_by_term(comm, kind, nx, ny):
     """phb_fs_assemble_u in one pass (k_momentum_fused) against the same equation assembled one operator at a time
     (fusedAssembly 0): identical pattern, coefficients and right-hand side to rounding."""
     om, ofs = oracle_cavity(kind, nx, ny, 1.0, 0.8)
@@ -59,6 +59,13 @@ def test_fused_momentum_assembly_equals_term_by_term(comm, kind, nx, ny):
     assert_eqn_equal(fused, terms, rtol=1e-14)
     assert np.abs(fused[3]).max() > 0
     assert_eqn_equal(fused, ofs.assemble_u(dt).export())
+    fusedP = gfs.assembleP(dt).export(1)
+    gfs.setup(fusedAssembly=0)
+    termsP = gfs.assembleP(dt).export(1)
+    gfs.setup(fusedAssembly=1)
+    assert_eqn_equal(fusedP, termsP, rtol=1e-14)
+    assert np.abs(fusedP[3]).max() > 0
+    assert_eqn_equal(fusedP, ofs.assemble_p(dt).export())
     gfs.close(); g.close()
 
 
