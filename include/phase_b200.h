@@ -240,6 +240,10 @@ int phb_solver_time_amg(phb_solver *s, int reps, double out[8]);
 typedef struct phb_amg_host phb_amg_host;
 int phb_amg_host_build(int n, const int *rowPtr, const int *colInd, const double *vals, double theta,
                        int coarsest, phb_amg_host **out);
+/* the same with the two setup rules of round 2 exposed: aggTheta (`amgAggTheta`) and coarseWeight
+ * (`amgCoarseSmootherWeight`); a negative value selects the default (0.1, 1.6), 0 switches the rule off */
+int phb_amg_host_build_ex(int n, const int *rowPtr, const int *colInd, const double *vals, double theta,
+                          double aggTheta, double coarseWeight, int coarsest, phb_amg_host **out);
 int phb_amg_host_levels(const phb_amg_host *h, int *nLevels, int *singular, int *denseCoarse);
 int phb_amg_host_level_size(const phb_amg_host *h, int level, int which, int *nRows, int *nCols,
                             long long *nnz, double *rho);

@@ -73,6 +73,7 @@ SIGNATURES = {
     "phb_solver_amg_values": (cll, [vp, ci, ci, pd, cll]),
     "phb_solver_time_amg": (ci, [vp, ci, pd]),
     "phb_amg_host_build": (ci, [ci, pi, pi, pd, cd, ci, pvp]),
+    "phb_amg_host_build_ex": (ci, [ci, pi, pi, pd, cd, cd, cd, ci, pvp]),
     "phb_amg_host_levels": (ci, [vp, pi, pi, pi]),
     "phb_amg_host_level_size": (ci, [vp, ci, ci, pi, pi, C.POINTER(cll), pd]),
     "phb_amg_host_level_csr": (ci, [vp, ci, ci, pi, pi, pd]),

@@ -2376,8 +2376,16 @@ int phb_amg_dist_destroy(phb_amg_dist *h) {
 
 int phb_amg_host_build(int n, const int *rowPtr, const int *colInd, const double *vals, double theta,
                        int coarsest, phb_amg_host **out) {
+  return phb_amg_host_build_ex(n, rowPtr, colInd, vals, theta, -1., -1., coarsest, out);
+}
+
+int phb_amg_host_build_ex(int n, const int *rowPtr, const int *colInd, const double *vals, double theta,
+                          double aggTheta, double coarseWeight, int coarsest, phb_amg_host **out) {
   PHB_TRY_BEGIN
   PHB_REQUIRE(n > 0 && rowPtr && colInd && vals && out, "phb_amg_host_build: bad argument");
+  Strength rule(theta);
+  if (aggTheta >= 0.) rule.agg = aggTheta;
+  if (coarseWeight >= 0.) rule.omegaC = coarseWeight;
   HCsr A;
   A.n = A.m = n;
   A.rp.assign(n + 1, 0);
@@ -2396,7 +2404,7 @@ int phb_amg_host_build(int n, const int *rowPtr, const int *colInd, const double
     A.rp[r + 1] = (int)A.ci.size();
   }
   std::unique_ptr<phb_amg_host> h(new phb_amg_host());
-  PHB_CHECK(build_hierarchy(std::move(A), theta, coarsest > 0 ? coarsest : 1000, 4. / 3., h->H));
+  PHB_CHECK(build_hierarchy(std::move(A), rule, coarsest > 0 ? coarsest : 1000, 4. / 3., h->H));
   *out = h.release();
   return PHB_OK;
   PHB_TRY_END

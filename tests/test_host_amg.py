@@ -30,7 +30,8 @@ def neumann_laplacian(nx, ny, fixed_left=False, sign=-1.0):
 
 
 class HostAmg:
-    def __init__(self, A, theta=0.0, coarsest=400):
+    def __init__(self, A, theta=0.0, coarsest=400, agg_theta=-1.0, coarse_weight=-1.0):
+        """agg_theta / coarse_weight: `amgAggTheta` / `amgCoarseSmootherWeight` (negative: library default, 0: rule off)"""
         self.L = _capi.lib()
         A = A.tocsr()
         A.sort_indices()
@@ -38,8 +39,8 @@ class HostAmg:
         ci = A.indices.astype(np.int32)
         v = A.data.astype(np.float64)
         h = C.c_void_p()
-        rc = self.L.phb_amg_host_build(A.shape[0], rp.ctypes.data_as(_capi.pi), ci.ctypes.data_as(_capi.pi),
-                                       v.ctypes.data_as(_capi.pd), theta, coarsest, C.byref(h))
+        rc = self.L.phb_amg_host_build_ex(A.shape[0], rp.ctypes.data_as(_capi.pi), ci.ctypes.data_as(_capi.pi),
+                                          v.ctypes.data_as(_capi.pd), theta, agg_theta, coarse_weight, coarsest, C.byref(h))
         assert rc == 0, self.L.phb_last_error()
         self.h = h
         n, s, d = C.c_int(), C.c_int(), C.c_int()
@@ -147,6 +148,30 @@ def test_cycle_preconditions_bicgstab_mesh_independently():
         counts.append(its)
         H.close()
     assert max(counts) <= 20, counts
+
+
+def test_iterations_do_not_depend_on_the_row_length_of_the_mesh():
+    """Round 1's wide-mesh pathology (a 4000-cell-wide mesh needed twice the iterations of a 3998-cell-wide one): with every
+    small Galerkin entry a member-maker, oversized aggregates formed at the end of the natural order on the coarse
+    levels.  The row-relative membership filter (`amgAggTheta`) and the power-iteration smoother weights on the Galerkin
+    levels (`amgCoarseSmootherWeight`) bring both meshes to the same count; switched off, the old behaviour is back."""
+    rng = np.random.default_rng(0)
+    counts = {}
+    for nx in (4000, 3998):
+        A = neumann_laplacian(nx, 250)
+        b = rng.standard_normal(A.shape[0])
+        b -= b.mean()
+        for tag, kw in (("new", {}), ("old", dict(agg_theta=0.0, coarse_weight=0.0))):
+            H = HostAmg(A, coarsest=1000, **kw)
+            counts[nx, tag] = bicgstab_iters(A, H.cycle(), b)[0]
+            if tag == "new":
+                ws = [H.weight_scale(l) for l in range(H.nLevels)]
+                assert abs(ws[0] - 0.9) < 1e-12 and all(0.95 < w < 1.35 for w in ws[1:]), ws
+            else:
+                assert all(abs(H.weight_scale(l) - 0.9) < 1e-12 for l in range(H.nLevels))
+            H.close()
+    assert counts[4000, "new"] <= 9 and counts[3998, "new"] <= 9, counts
+    assert counts[4000, "old"] >= counts[4000, "new"] + 2, counts
 
 
 def test_variable_coefficient_and_threshold():
