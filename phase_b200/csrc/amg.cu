@@ -967,7 +967,9 @@ __device__ __forceinline__ void amg_epilogue(int row, const T (&acc)[NC], const 
 // MODE 3: y += M x
 // NC components share the coefficients; x has leading dimension ldx, y and b have ldy.
 // Streaming variant: warp <-> slice, lane <-> row (large levels, HBM-bound).
-template <int MODE, int NC, typename T, typename TB, typename TY>
+// WIDE: rows of more than seven entries (slice_dot_wide, kernels.cuh) -- an instantiation of its own, so that its
+// registers do not cost the 5-entry level-0 sweeps their occupancy
+template <int MODE, int NC, typename T, typename TB, typename TY, bool WIDE = false>
 __global__ void __launch_bounds__(kThreads)
 k_amg_spmv(SellView M, const T *__restrict__ vals, const T *__restrict__ x, int ldx, TY *__restrict__ y, int ldy,
            const TB *__restrict__ b, const T *__restrict__ w, const KrylovSums *S, int maxIters) {
@@ -983,7 +985,8 @@ k_amg_spmv(SellView M, const T *__restrict__ vals, const T *__restrict__ x, int 
     T acc[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) acc[i] = T(0);
-    slice_dot_any<NC>(M.col, vals, (size_t)off + lane, wdt, x, ldx, acc);
+    if (WIDE) slice_dot_wide<NC>(M.col, vals, (size_t)off + lane, wdt, x, ldx, acc);
+    else slice_dot_any<NC>(M.col, vals, (size_t)off + lane, wdt, x, ldx, acc);
     if (row < M.nRows) amg_epilogue<MODE, NC, T, TB, TY>(row, acc, x, ldx, y, ldy, b, w);
   }
 }
@@ -1283,6 +1286,17 @@ void launch(phb_solver *s, const SellPattern &P, const T *vals, const T *x, int 
     return;
   }
   const int grid = grid_rows(s->ctx, (long long)P.nSlices * 32);
+  // mean slice width beyond seven entries: Galerkin operators and restrictions
+  const bool wide = P.nSlices > 0 && P.nSlots > (long long)P.nSlices * 32 * 7;
+  if (wide) {
+    if (s->nComp == 1)
+      PHB_LAUNCH(s->ctx, (k_amg_spmv<MODE, 1, T, TB, TY, true>), grid, kThreads, 0, V, vals, x, ldx, y, ldy, b, w, S,
+                 s->maxIters);
+    else
+      PHB_LAUNCH(s->ctx, (k_amg_spmv<MODE, 2, T, TB, TY, true>), grid, kThreads, 0, V, vals, x, ldx, y, ldy, b, w, S,
+                 s->maxIters);
+    return;
+  }
   if (s->nComp == 1)
     PHB_LAUNCH(s->ctx, (k_amg_spmv<MODE, 1, T, TB, TY>), grid, kThreads, 0, V, vals, x, ldx, y, ldy, b, w, S,
                s->maxIters);

@@ -397,8 +397,9 @@ __global__ void k_lap_bnd(MeshView M, const int *__restrict__ faceType, double *
 // i.e. k_ddt + k_div<NC,0>(theta 0) + k_lap(theta 0.5, sign -1) + k_src on a zeroed equation, term sums kept apart
 // and added in that order.  Every slot and rhs entry of a live row is WRITTEN (no zero-fill, no read-modify-write):
 // 4 launches and 3 extra sweeps over `vals` less.  Boundary links follow in k_div_bnd / k_lap_bnd as before.
+constexpr int kFusedBlocksPerSM = 6;   // 40 registers without spills; the grid is sized to be resident in one wave
 template <int NC>
-__global__ void k_momentum_fused(MeshView M, double *__restrict__ vals, double *__restrict__ rhs, int ldr,
+__global__ void __launch_bounds__(kThreads, kFusedBlocksPerSM) k_momentum_fused(MeshView M, double *__restrict__ vals, double *__restrict__ rhs, int ldr,
                                  const double *__restrict__ u0F, const double *__restrict__ phi0, int ldc,
                                  const double *__restrict__ gradP, double gamma, double dt) {
   FOR_EACH_ROW(M)
@@ -1048,7 +1049,7 @@ int assemble_momentum_predictor(phb_eqn *e, phb_field *u, const phb_field *gradP
   if (e->tens.p) PHB_CHECK(e->tens.zero(c->stream));
   e->hasTens = false;
   const MeshView M = view(m);
-  const int grid = row_grid(c, m), gb = (m->nBCells + 255) / 256;
+  const int grid = std::min(row_grid(c, m), c->numSMs * kFusedBlocksPerSM), gb = (m->nBCells + 255) / 256;
   PHB_LAUNCH(c, k_momentum_fused<2>, grid, kThreads, 0, M, e->vals.p, e->rhs.p, m->nLocal, u->faces0.p, u->cells0.p,
              m->nDev, gradP->cells.p, gamma, dt);
   if (m->nBCells) {

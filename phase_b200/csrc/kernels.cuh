@@ -130,4 +130,32 @@ __device__ __forceinline__ void slice_dot_any(const int *__restrict__ col, const
   }
 }
 
+// Wide rows (Galerkin operators: 9-13 entries; restrictions: 20-30): the whole row -- or sixteen entries at a time --
+// is in flight before the first gather, so a slice costs one or two load round trips instead of one per four entries.
+// Levels of 10^5-10^6 rows hand each warp two or three slices: they are bound by that chain, not by bytes.
+template <int NC, typename T>
+__device__ __forceinline__ void slice_dot_wide(const int *__restrict__ col, const T *__restrict__ vals,
+                                               size_t base, int w, const T *__restrict__ x, int ld, T (&acc)[NC]) {
+  int k = 0;
+  for (; k + 16 <= w; k += 16) slice_dot<NC, 16, T>(col, vals, base + (size_t)k * 32, x, ld, acc);
+  switch (w - k) {
+    case 15: slice_dot<NC, 15, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    case 14: slice_dot<NC, 14, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    case 13: slice_dot<NC, 13, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    case 12: slice_dot<NC, 12, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    case 11: slice_dot<NC, 11, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    case 10: slice_dot<NC, 10, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    case 9: slice_dot<NC, 9, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    case 8: slice_dot<NC, 8, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    case 7: slice_dot<NC, 7, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    case 6: slice_dot<NC, 6, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    case 5: slice_dot<NC, 5, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    case 4: slice_dot<NC, 4, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    case 3: slice_dot<NC, 3, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    case 2: slice_dot<NC, 2, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    case 1: slice_dot<NC, 1, T>(col, vals, base + (size_t)k * 32, x, ld, acc); break;
+    default: break;
+  }
+}
+
 }  // namespace phb
