@@ -1169,8 +1169,17 @@ __global__ void __launch_bounds__(1024)
 k_amg_tail(const AmgTailOp *__restrict__ ops, int nOps, unsigned *bar, const KrylovSums *S, int maxIters) {
   if (S && krylov_done(S, maxIters)) return;   // the same answer in every CTA: nobody waits for a CTA that left
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nThreads = gridDim.x * blockDim.x;
+  // the op list once into shared memory: one global round trip per launch instead of one per phase
+  __shared__ AmgTailOp sOps[kMaxTailOps];
+  {
+    const int words = nOps * (int)(sizeof(AmgTailOp) / sizeof(int));
+    const int *src = reinterpret_cast<const int *>(ops);
+    int *dst = reinterpret_cast<int *>(sOps);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
   for (int o = 0; o < nOps; ++o) {
-    const AmgTailOp op = ops[o];
+    const AmgTailOp op = sOps[o];
     if (op.kind == 2) {   // dense coarsest solve: one warp per row of the fp64 inverse
       const double *Ainv = static_cast<const double *>(op.vals);
       const T *b = static_cast<const T *>(op.b);
@@ -1820,6 +1829,7 @@ int build_tail_ops(phb_solver *s) {
     sparse(3, V.P, V.n, V.ld, C.ld, V.w.p, V.b.p, xc, V.x.p);
     sparse(4, V.A, V.n, V.ld, V.ld, V.w.p, V.b.p, V.x.p, V.x2.p);
   }
+  if ((int)ops.size() > kMaxTailOps) return PHB_OK;   // deeper than the kernel's shared op list: separate launches
   PHB_CHECK(D.tailOps.upload(ops, c->stream));
   PHB_CHECK(D.tailBar.alloc(4));
   PHB_CHECK(D.tailBar.zero(c->stream));
@@ -1993,6 +2003,9 @@ int amg_prepare(phb_solver *s) {
   AmgData &D = s->amg;
   bool need = !D.built || D.src != s->pat || D.refVals.n != (size_t)s->pat->nSlots || D.nComp != s->nComp ||
               D.builtSingle != D.single;
+  // the caller vouches that this matrix is the one the hierarchy's values were computed from (same tag on every rank):
+  // nothing to compare, nothing to agree on
+  if (!need && s->valsTag != 0ull && s->valsTag == D.builtTag) return PHB_OK;
   if (!need) {
     PHB_CHECK(D.chk.alloc(2));
     int first = 0;
@@ -2025,19 +2038,25 @@ int amg_prepare(phb_solver *s) {
     if (D.rebuildAlways && D.stale) need = true;
   }
   const bool dist = c->nProcs > 1 && s->halo && D.global;
+  bool staleAnywhere = D.stale;
   if (c->nProcs > 1) {  // the setup talks to the other ranks: everybody rebuilds or nobody does
+    // ... and everybody holds the same opinion on whether the hierarchy still fits (the coefficient tags below must
+    // agree across the ranks, or the next solve would leave some of them alone in this exchange)
     PHB_CHECK(D.chk.alloc(2));
-    const double flag[2] = {need ? 1. : 0., 0.};
+    const double flag[2] = {need ? 1. : 0., D.stale ? 1. : 0.};
     PHB_CUDA(cudaMemcpyAsync(D.chk.p, flag, sizeof(flag), cudaMemcpyHostToDevice, c->stream));
-    PHB_CHECK(comm_allreduce_max(c, D.chk.p, 1));
-    PHB_CUDA(cudaMemcpyAsync(c->pinned, D.chk.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PHB_CHECK(comm_allreduce_max(c, D.chk.p, 2));
+    PHB_CUDA(cudaMemcpyAsync(c->pinned, D.chk.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     PHB_CUDA(cudaStreamSynchronize(c->stream));
     need = c->pinned[0] > 0.5;
+    staleAnywhere = c->pinned[1] > 0.5;
   }
   if (need) {
     if (dist) PHB_CHECK(D.single ? rebuild_dist_t<float>(s) : rebuild_dist_t<double>(s));
     else PHB_CHECK(D.single ? rebuild_t<float>(s) : rebuild_t<double>(s));
   }
+  // values of the hierarchy == current coefficients (fresh setup, refresh, or the comparison found no drift)?
+  D.builtTag = (need || !staleAnywhere) ? s->valsTag : 0ull;
   return PHB_OK;
 }
 

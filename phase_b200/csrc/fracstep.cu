@@ -5,6 +5,7 @@
 // pieces themselves (the C++ mirror in include/phase/ does).
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "comm.cuh"
 #include "fv.cuh"
@@ -25,10 +26,24 @@ struct phb_fracstep {
   int guessOrder = 1;
   phb::DevBuf<double> pPrev;  // p^(n-1), owned cells
   int nStepsDone = 0;
+  unsigned long long uTag = 0, pTag = 0;   // coefficient tags of the last one-pass assembly (0: assembled term by term)
   bool fusedAssembly = true;     // uEqn_ and pEqn_ each in one pass over the rows ("fusedAssembly" 0: one kernel per operator)
 };
 
 namespace {
+// equal tags <=> equal coefficients of a one-pass assembly (never 0)
+unsigned long long matrix_tag(int which, double dt, double gamma, unsigned bcVersion) {
+  unsigned long long a, b;
+  memcpy(&a, &dt, 8);
+  memcpy(&b, &gamma, 8);
+  unsigned long long h = 1469598103934665603ull;
+  for (unsigned long long v : {(unsigned long long)which, a, b, (unsigned long long)bcVersion}) {
+    h ^= v;
+    h *= 1099511628211ull;
+    h ^= h >> 29;
+  }
+  return h ? h : 1ull;
+}
 // x = 2 x - xPrev ; xPrev = old x        (owned cells of a scalar field)
 __global__ void k_extrapolate(int n, double *__restrict__ x, double *__restrict__ xPrev, int apply) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -104,8 +119,11 @@ int phb_fs_initialize(phb_fracstep *fs) {
 // (US/FractionalStep.cpp:82-83); expects u.savePreviousTimeStep to have run.
 int phb_fs_assemble_u(phb_fracstep *fs, double dt) {
   PHB_REQUIRE(fs && dt > 0., "phb_fs_assemble_u: bad argument");
+  fs->uTag = 0ull;
   if (fs->fusedAssembly) {
     const int rc = phb::assemble_momentum_predictor(fs->uEqn, fs->u, fs->gradP, fs->mu / fs->rho, dt);
+    // the coefficients are V/dt and the halved diffusion links: a function of dt, nu and the boundary types alone
+    if (rc == PHB_OK) fs->uTag = matrix_tag(1, dt, fs->mu / fs->rho, fs->u->bcVersion);
     if (rc <= 0) return rc;   // 1: SYMMETRY patches -> term by term
   }
   PHB_CHECK(phb_eqn_zero(fs->uEqn));
@@ -119,7 +137,12 @@ int phb_fs_assemble_u(phb_fracstep *fs, double dt) {
 // pEqn_ = (fv::laplacian(dt, p) == src::div(u))  (US/FractionalStep.cpp:97)
 int phb_fs_assemble_p(phb_fracstep *fs, double dt) {
   PHB_REQUIRE(fs && dt > 0., "phb_fs_assemble_p: bad argument");
-  if (fs->fusedAssembly) return phb::assemble_pressure_poisson(fs->pEqn, fs->p, fs->u, dt);
+  fs->pTag = 0ull;
+  if (fs->fusedAssembly) {
+    PHB_CHECK(phb::assemble_pressure_poisson(fs->pEqn, fs->p, fs->u, dt));
+    fs->pTag = matrix_tag(2, dt, 1., fs->p->bcVersion);   // coefficients dt g_f: dt and the boundary types
+    return PHB_OK;
+  }
   PHB_CHECK(phb_eqn_zero(fs->pEqn));
   PHB_CHECK(phb_assemble_laplacian(fs->pEqn, dt, nullptr, fs->p, -1., +1.));
   PHB_CHECK(phb_assemble_src_div(fs->pEqn, fs->u, -1.));
@@ -134,7 +157,7 @@ int phb_fs_step(phb_fracstep *fs, double dt, double stats[6]) {
   // ---- solveUEqn (US/FractionalStep.cpp:79-94)
   PHB_CHECK(phb_field_save_previous(fs->u));
   PHB_CHECK(phb_fs_assemble_u(fs, dt));
-  PHB_CHECK(phb_eqn_solve(fs->uEqn, fs->uSolver, fs->u, fs->warmStart, &itU, &rrU));
+  PHB_CHECK(phb::eqn_solve_tagged(fs->uEqn, fs->uSolver, fs->u, fs->warmStart, fs->uTag, &itU, &rrU));
   PHB_CHECK(phb::field_axpy_cells(fs->u, dt, fs->gradP));
   PHB_CHECK(phb::field_send_messages(fs->u));
   PHB_CHECK(phb::field_interpolate_faces(fs->u));
@@ -147,7 +170,7 @@ int phb_fs_step(phb_fracstep *fs, double dt, double stats[6]) {
     const int g = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)c->numSMs * 8));
     PHB_LAUNCH(c, k_extrapolate, g, 256, 0, n, fs->p->cells.p, fs->pPrev.p, fs->nStepsDone >= 2 ? 1 : 0);
   }
-  PHB_CHECK(phb_eqn_solve(fs->pEqn, fs->pSolver, fs->p, fs->warmStart, &itP, &rrP));
+  PHB_CHECK(phb::eqn_solve_tagged(fs->pEqn, fs->pSolver, fs->p, fs->warmStart, fs->pTag, &itP, &rrP));
   fs->nStepsDone++;
   PHB_CHECK(phb::field_send_messages(fs->p));
   PHB_CHECK(phb::field_set_boundary_faces(fs->p));
@@ -157,8 +180,7 @@ int phb_fs_step(phb_fracstep *fs, double dt, double stats[6]) {
   PHB_CHECK(phb::field_send_messages(fs->u));
   PHB_CHECK(phb::field_axpy_faces(fs->u, -dt, fs->gradP));
   // ---- diagnostics (:41-43): max divergence error, max CFL
-  PHB_CHECK(phb::field_flux_max(fs->u, 0, dt, fs->scratch, fs->partials, fs->ticket, fs->out.p));
-  PHB_CHECK(phb::field_flux_max(fs->u, 1, dt, fs->scratch, fs->partials, fs->ticket, fs->out.p + 1));
+  PHB_CHECK(phb::field_flux_diagnostics(fs->u, dt, fs->scratch, fs->partials, fs->ticket, fs->out.p));
   PHB_CUDA(cudaMemcpyAsync(c->pinned + 64, fs->out.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   PHB_CUDA(cudaStreamSynchronize(c->stream));
   if (stats) {

@@ -529,6 +529,49 @@ __global__ void k_flux_sum_bnd(MeshView M, const double *__restrict__ uF, double
   if (OUT == 0) out[row] += sign * d;
   else out[row] += d;
 }
+// both per-step diagnostics of FractionalStep::solve (US/FractionalStep.cpp:41-43) in one pass over the links:
+// div[row] = sum_f u_f . S_out, co[row] = sum_f max(u_f . S_out, 0)
+__global__ void k_flux_both(MeshView M, const double *__restrict__ uF, double *__restrict__ div, double *__restrict__ co) {
+  FOR_EACH_ROW(M)
+    double d = 0., p = 0.;
+    for (int k = 1; k < wdt; ++k) {
+      const int lf = M.linkFace[slot0 + (size_t)k * 32];
+      if (lf < 0) continue;
+      const int f = lf >> 1;
+      const double flux = ((lf & 1) ? -1. : 1.) * (uF[f] * M.fSx[f] + uF[(size_t)M.nFaces + f] * M.fSy[f]);
+      d += flux;
+      p += fmax(flux, 0.);
+    }
+    div[row] = d;
+    co[row] = p;
+  END_FOR_EACH_ROW
+}
+__global__ void k_flux_both_bnd(MeshView M, const double *__restrict__ uF, double *__restrict__ div, double *__restrict__ co) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M.nBCells) return;
+  const int row = M.bcCell[i];
+  double d = 0., p = 0.;
+  for (int j = M.bcPtr[i]; j < M.bcPtr[i + 1]; ++j) {
+    const int f = M.bcFace[j];
+    const double flux = uF[f] * M.fSx[f] + uF[(size_t)M.nFaces + f] * M.fSy[f];
+    d += flux;
+    p += fmax(flux, 0.);
+  }
+  div[row] += d;
+  co[row] += p;
+}
+// out[0] = max |div|, out[1] = max co dt / V over owned rows
+__global__ void k_max_reduce2(int n, const double *__restrict__ div, const double *__restrict__ co,
+                              const double *__restrict__ vol, double dt, double *partials, unsigned *ticket, double *out) {
+  double m0 = 0., m1 = 0.;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    m0 = fmax(m0, fabs(div[i]));
+    m1 = fmax(m1, co[i] * dt / vol[i]);
+  }
+  double v[2] = {m0, m1};
+  grid_reduce<2, true>(v, partials, ticket, out);
+}
+
 // max |x| (MODE 0) or max (x dt / V) (MODE 1) over owned rows
 template <int MODE>
 __global__ void k_max_reduce(int n, const double *__restrict__ x, const double *__restrict__ vol, double dt,
@@ -709,7 +752,7 @@ int field_flux_max(const phb_field *u, int mode, double dt, phb::DevBuf<double> 
   phb_mesh *m = u->m;
   phb_ctx *c = m->ctx;
   const MeshView M = view(m);
-  PHB_CHECK(scratch.alloc((size_t)m->nLocal));
+  PHB_CHECK(scratch.alloc(2 * (size_t)m->nLocal));   // same sizes as field_flux_diagnostics: no reallocation between them
   const int grid = row_grid(c, m);
   if (mode == 0) {
     PHB_LAUNCH(c, k_flux_sum<1>, grid, kThreads, 0, M, u->faces.p, scratch.p, 1., dt, (const int *)nullptr);
@@ -719,13 +762,32 @@ int field_flux_max(const phb_field *u, int mode, double dt, phb::DevBuf<double> 
     if (m->nBCells) PHB_LAUNCH(c, k_flux_sum_bnd<2>, (m->nBCells + 255) / 256, 256, 0, M, u->faces.p, scratch.p, 1., dt, (const int *)nullptr);
   }
   const int g2 = flat_grid(c, m->nLocal);
-  PHB_CHECK(partials.alloc((size_t)c->numSMs * 8));
+  PHB_CHECK(partials.alloc((size_t)c->numSMs * 8 * 2));
   if (!ticket.p) { PHB_CHECK(ticket.alloc(1)); PHB_CHECK(ticket.zero(c->stream)); }
   if (mode == 0)
     PHB_LAUNCH(c, k_max_reduce<0>, g2, kThreads, 0, m->nLocal, scratch.p, m->dVol.p, dt, partials.p, ticket.p, devOut);
   else
     PHB_LAUNCH(c, k_max_reduce<1>, g2, kThreads, 0, m->nLocal, scratch.p, m->dVol.p, dt, partials.p, ticket.p, devOut);
   PHB_CHECK(comm_allreduce_max(c, devOut, 1));
+  return PHB_OK;
+}
+
+// devOut[0] = max |sum_f u_f . S_f| (divergence error), devOut[1] = max Courant number; one pass over the links
+int field_flux_diagnostics(const phb_field *u, double dt, phb::DevBuf<double> &scratch, phb::DevBuf<double> &partials,
+                           phb::DevBuf<unsigned> &ticket, double *devOut) {
+  phb_mesh *m = u->m;
+  phb_ctx *c = m->ctx;
+  const MeshView M = view(m);
+  const size_t n = (size_t)m->nLocal;
+  PHB_CHECK(scratch.alloc(2 * n));
+  double *div = scratch.p, *co = scratch.p + n;
+  PHB_LAUNCH(c, k_flux_both, row_grid(c, m), kThreads, 0, M, u->faces.p, div, co);
+  if (m->nBCells) PHB_LAUNCH(c, k_flux_both_bnd, (m->nBCells + 255) / 256, 256, 0, M, u->faces.p, div, co);
+  PHB_CHECK(partials.alloc((size_t)c->numSMs * 8 * 2));
+  if (!ticket.p) { PHB_CHECK(ticket.alloc(1)); PHB_CHECK(ticket.zero(c->stream)); }
+  PHB_LAUNCH(c, k_max_reduce2, flat_grid(c, m->nLocal), kThreads, 0, m->nLocal, (const double *)div, (const double *)co,
+             m->dVol.p, dt, partials.p, ticket.p, devOut);
+  PHB_CHECK(comm_allreduce_max(c, devOut, 2));
   return PHB_OK;
 }
 
@@ -756,6 +818,7 @@ int phb_field_set_bc(phb_field *f, const char *patch, int type, double vx, doubl
   PHB_REQUIRE(type == PHB_FIXED || type == PHB_NORMAL_GRADIENT || type == PHB_SYMMETRY,
               "phb_field_set_bc: unrecognized boundary type %d", type);
   phb_mesh *m = f->m;
+  f->bcVersion++;   // on every rank, whether or not the patch touches it: matrix tags must change everywhere at once
   const int p = phb_mesh_patch_id(m, patch);
   // a partitioned mesh only carries the patches that touch it: boundary input for
   // the others is ignored, as setBoundaryTypes does (UF/FiniteVolumeField.tpp:452-476)
@@ -1225,6 +1288,16 @@ long long phb_eqn_export_csr(const phb_eqn *e, int layout, int *rowPtr, int *col
 }
 
 int phb_eqn_solve(phb_eqn *e, phb_solver *s, phb_field *phi, int warmStart, int *iters, double *relres) {
+  return phb::eqn_solve_tagged(e, s, phi, warmStart, 0ull, iters, relres);
+}
+}  // extern "C"
+
+namespace phb {
+// `tag` != 0: the caller vouches that equal tags mean equal coefficients (the one-pass assembly of FractionalStep: the
+// matrix is a function of dt, the diffusivity and the boundary types only) -- the multigrid preconditioner then skips
+// its per-solve comparison of the coefficients with the ones it was built from (one sweep over both + a host sync)
+int eqn_solve_tagged(phb_eqn *e, phb_solver *s, phb_field *phi, int warmStart, unsigned long long tag, int *iters,
+                     double *relres) {
   PHB_TRY_BEGIN
   PHB_CHECK(check_pair(e, phi, "phb_eqn_solve"));
   PHB_REQUIRE(s && phi->nComp == e->nComp, "phb_eqn_solve: bad argument");
@@ -1240,7 +1313,9 @@ int phb_eqn_solve(phb_eqn *e, phb_solver *s, phb_field *phi, int warmStart, int 
                phi->cells.p, s->x.p);
   else
     PHB_CUDA(cudaMemsetAsync(s->x.p, 0, (size_t)ld * nc * sizeof(double), c->stream));
+  s->valsTag = tag;
   int rc = phb::solver_run(s, iters, relres);
+  s->valsTag = 0ull;
   if (rc != PHB_OK) return rc;
   // mapFromSparseSolver: x -> field cells (UE/ScalarFiniteVolumeEquation.cpp:59-64)
   PHB_LAUNCH(c, k_copy2d, flat_grid(c, (long long)n * nc), kThreads, 0, n, nc, (long long)ld, (long long)m->nDev,
@@ -1248,5 +1323,4 @@ int phb_eqn_solve(phb_eqn *e, phb_solver *s, phb_field *phi, int warmStart, int 
   return PHB_OK;
   PHB_TRY_END
 }
-
-}  // extern "C"
+}  // namespace phb

@@ -128,6 +128,7 @@ struct AmgPeer {
 
 // One phase of the fused small-level kernel (amg.cu: k_amg_tail): every level from `fuseFrom` down to the dense
 // coarsest solve and back up runs in ONE launch, the phases separated by grid barriers instead of kernel boundaries.
+constexpr int kMaxTailOps = 48;   // op list of the fused small-level kernel, staged in shared memory (4 per level + 1)
 struct AmgTailOp {
   int kind;                 // 0 r = b - A (w.*b) | 1 y = R r | 2 x = Ainv b (dense) | 3 x = w.*b + P xc | 4 y = x + w.*(b - A x)
   int n, ld, ldIn;          // rows; leading dimension of the row-wise vectors; of the gathered vector
@@ -176,6 +177,7 @@ struct AmgData {
   phb::DevBuf<AmgTailOp> tailOps;
   phb::DevBuf<unsigned> tailBar;
   const SellPattern *src = nullptr;
+  unsigned long long builtTag = 0;          // coefficient tag of the matrix the hierarchy's values belong to (0: untagged)
   bool built = false, denseCoarse = false, stale = false, rebuildAlways = false;
   int nComp = 1, nCoarse = 0, nu = 1, coarsest = 1000, setups = 0, itersAfterSetup = -1;
   // smoother weight omegaS / rho(D^-1 A): 1.8 instead of the textbook 4/3 -- inside a Krylov method the stronger damping of
@@ -222,6 +224,7 @@ struct phb_solver {
   // Measured on 2 B200s (2M rows per GPU): 0.235 vs 0.223 ms per iteration -- the waits serialise the
   // same way and every CTA pays for them, so the separate kernels stay the default (`peerFusion 1` opts in).
   bool peerFused = false;
+  unsigned long long valsTag = 0;  // coefficient tag of the solve in progress (fv.cu: eqn_solve_tagged), 0 = none
   int peerRegion = -1;             // slot of this solver in the peer arena (-1 unassigned, -2 not usable)
   double *runPh = nullptr, *runSh = nullptr;
   phb::DevBuf<double> b, x, r, rhat, p, v, s, t;

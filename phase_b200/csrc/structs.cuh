@@ -83,6 +83,7 @@ struct phb_field {
   phb::DevBuf<int> dBfType;             // per boundary face (flat list order)
   phb::DevBuf<int> dFaceType;           // per face (interior faces: NORMAL_GRADIENT)
   bool bcDirty = true;
+  unsigned bcVersion = 1;               // bumped by every boundary-condition change (matrix tags of the fused assembly)
   phb::DevBuf<double> cells, faces;     // [comp][nDev], [comp][nFaces]
   phb::DevBuf<double> cells0, faces0;   // old time level
   bool hasOld = false;
