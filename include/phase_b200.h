@@ -367,7 +367,9 @@ phb_field *phb_fs_field(phb_fracstep *fs, const char *name); /* u p gradP */
 phb_eqn *phb_fs_eqn(phb_fracstep *fs, const char *name);      /* uEqn pEqn */
 phb_solver *phb_fs_solver(phb_fracstep *fs, const char *name);
 /* options: "warmStart" (1: solves start from the current field values; the reference
- * passes no guess), "guessOrder" (1: pEqn_ guess = 2 p^n - p^(n-1)) */
+ * passes no guess), "guessOrder" (1: pEqn_ guess = 2 p^n - p^(n-1)), "fusedAssembly" (1, default: uEqn_ and
+ * pEqn_ each assembled in one pass over the rows; 0: one kernel per fv:: / src:: operator, the path the operator
+ * interface phb_assemble_* takes -- same coefficients to rounding) */
 int phb_fs_setup(phb_fracstep *fs, const char *key, double value);
 int phb_fs_initialize(phb_fracstep *fs);
 int phb_fs_assemble_u(phb_fracstep *fs, double dt);

@@ -582,6 +582,10 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
                                 (s->precond == PHB_PC_ILU0 ? 2 * ilu_launches_per_apply(s) : 0) +
                                 (amg ? 2 * amg_launches_per_apply(s) : 0);
     int launched = 0, burst = 1;
+    // With the multigrid preconditioner a solve is a handful of iterations and every poll leaves the GPU idle for a host
+    // round trip plus a graph launch: the first poll waits until one iteration short of what this solver needed last
+    // time (kernels past convergence leave on the device-side test, so overshooting costs empty launches only)
+    if (amg && graphOk && s->lastIters > K) burst = std::max(1, (s->lastIters - 1) / K);
     bool done = false, midRefresh = false;
     while (!done && launched < budget) {
       for (int g = 0; g < burst && launched < budget; ++g) {
