@@ -450,14 +450,16 @@ def weak_record(job, args, peak):
 
 
 def e2e_record(job, comm, fs, dt, steps, sizes, weak):
-    """The same step through the public API with HOST state in pinned memory: per step H2D of the state a time step
-    starts from (u cells + faces, p cells; grad p and the boundary faces of p follow from p on the device), the
-    step, D2H of the same arrays -- a serial chain, since a host-owned state feeds every step with the previous
-    step's output."""
+    """The same step through the public API with HOST state in pinned memory.  The state is what the reference itself
+    persists between runs: the CELL values of u and p (Solver::readLatestCgnsFlowSolution, US/Solver.cpp:544-581, reads
+    cell fields and re-derives the faces).  Per step: H2D of those cells, FractionalStep.rebuildFaces (ghosts, boundary
+    faces, grad p and the face velocities exactly as the previous step left them -- tests/test_gpu_fracstep.py::
+    test_state_from_cells_alone), the step, D2H of the same arrays -- a serial chain, since a host-owned state feeds
+    every step with the previous step's output."""
     torch = job.torch
-    N, F = sizes["nCells"], sizes["nFaces"]
-    host = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k, n in (("uc", 2 * N), ("uf", 2 * F), ("pc", N))}
-    parts = {"uc": (fs.u, "cells"), "uf": (fs.u, "faces"), "pc": (fs.p, "cells")}
+    N = sizes["nCells"]
+    host = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k, n in (("uc", 2 * N), ("pc", N))}
+    parts = {"uc": (fs.u, "cells"), "pc": (fs.p, "cells")}
     for k, (fld, part) in parts.items():
         host[k].numpy()[:] = fld.get(part).reshape(-1)
     nbytes = sum(v.numel() for v in host.values()) * 8
@@ -465,7 +467,7 @@ def e2e_record(job, comm, fs, dt, steps, sizes, weak):
     def one_step():
         for k, (fld, part) in parts.items():
             fld.set(part, host[k].numpy())
-        fs.p.sendMessages(); fs.p.setBoundaryFaces(); fs.computeGradP()
+        fs.rebuildFaces(dt)
         fs.solve(dt)
         for k, (fld, part) in parts.items():
             fld.get(part, out=host[k].numpy())
@@ -480,8 +482,9 @@ def e2e_record(job, comm, fs, dt, steps, sizes, weak):
     s = job.max_over_ranks((time.perf_counter() - t0) / steps)
     return {"value": (job.world if weak else 1) / s, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
             "steps": steps, "warmup": 2, "ms_per_step": 1e3 * s,
-            "what": "pinned host state (u cells + faces, p cells) copied in, grad p rebuilt, FractionalStep.solve, the same "
-                    "arrays copied out, every step; wall clock, max over ranks"}
+            "what": "pinned host state (cells of u and p: what the reference's restart persists) copied in, faces and grad p "
+                    "rebuilt on the device (phb_fs_rebuild_faces), FractionalStep.solve, the same arrays copied out, every step; "
+                    "wall clock, max over ranks"}
 
 
 def seam1_record(comm, fs, dt, args):

@@ -372,6 +372,11 @@ phb_solver *phb_fs_solver(phb_fracstep *fs, const char *name);
  * interface phb_assemble_* takes -- same coefficients to rounding) */
 int phb_fs_setup(phb_fracstep *fs, const char *key, double value);
 int phb_fs_initialize(phb_fracstep *fs);
+/* A step's state from CELL values alone, as the reference's restart does (Solver::readLatestCgnsFlowSolution,
+ * US/Solver.cpp:544-581: cell fields are read, faces re-derived): with the owned cells of u and p on the device and
+ * dtPrev = the time step of the step that produced them, rebuilds ghosts, boundary faces, gradP and the face
+ * velocities as phb_fs_step left them (dtPrev = 0: plain interpolateFaces, the reference's restart). */
+int phb_fs_rebuild_faces(phb_fracstep *fs, double dtPrev);
 int phb_fs_assemble_u(phb_fracstep *fs, double dt);
 int phb_fs_assemble_p(phb_fracstep *fs, double dt);
 /* stats: [itersU, itersP, relresU, relresP, maxDivergence, maxCourant] */

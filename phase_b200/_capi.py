@@ -126,6 +126,7 @@ SIGNATURES = {
     "phb_fs_solver": (vp, [vp, cs]),
     "phb_fs_setup": (ci, [vp, cs, cd]),
     "phb_fs_initialize": (ci, [vp]),
+    "phb_fs_rebuild_faces": (ci, [vp, cd]),
     "phb_fs_assemble_u": (ci, [vp, cd]),
     "phb_fs_assemble_p": (ci, [vp, cd]),
     "phb_fs_step": (ci, [vp, cd, pd]),

@@ -584,6 +584,11 @@ class FractionalStep:
         has been replaced from the host."""
         check(self.L.phb_field_gradient(self.p.h, self.gradP.h))
 
+    def rebuildFaces(self, dtPrev):
+        """State from cell values alone (the reference's restart, US/Solver.cpp:544-581): ghosts, boundary faces, gradP and
+        the face velocities of the step that ended with time step `dtPrev`, from the cells of u and p on the device."""
+        check(self.L.phb_fs_rebuild_faces(self.h, float(dtPrev)))
+
     def computeMaxTimeStep(self, maxCo, prevDt, maxDt):
         out = C.c_double()
         check(self.L.phb_fs_max_time_step(self.h, maxCo, prevDt, maxDt, C.byref(out)))

@@ -25,6 +25,7 @@ struct phb_fracstep {
   // (the predictor sequence carries the lagged pressure gradient and is not smooth in time); p gains 7.7 -> 7.35.
   int guessOrder = 1;
   phb::DevBuf<double> pPrev;  // p^(n-1), owned cells
+  phb::DevBuf<double> uSave;  // cells of u while phb_fs_rebuild_faces borrows them
   int nStepsDone = 0;
   unsigned long long uTag = 0, pTag = 0;   // coefficient tags of the last one-pass assembly (0: assembled term by term)
   bool fusedAssembly = true;     // uEqn_ and pEqn_ each in one pass over the rows ("fusedAssembly" 0: one kernel per operator)
@@ -50,6 +51,14 @@ __global__ void k_extrapolate(int n, double *__restrict__ x, double *__restrict_
     const double cur = x[i], old = xPrev[i];
     xPrev[i] = cur;
     if (apply) x[i] = 2. * cur - old;
+  }
+}
+// y += a x on every face that is not a FIXED boundary face of the field (correctVelocity, US/FractionalStep.cpp:109-117)
+__global__ void k_axpy_faces_nonfixed(long long nF, int nc, const int *__restrict__ faceType, double a,
+                                      const double *__restrict__ x, double *__restrict__ y) {
+  for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < nF; f += (long long)gridDim.x * blockDim.x) {
+    if (faceType[f] == PHB_FIXED) continue;
+    for (int c = 0; c < nc; ++c) y[(size_t)c * nF + f] += a * x[(size_t)c * nF + f];
   }
 }
 }  // namespace
@@ -186,6 +195,37 @@ int phb_fs_step(phb_fracstep *fs, double dt, double stats[6]) {
   if (stats) {
     stats[0] = itU; stats[1] = itP; stats[2] = rrU; stats[3] = rrP;
     stats[4] = c->pinned[64]; stats[5] = c->pinned[65];
+  }
+  return phb::launch_status(c);
+}
+
+// State of a time step from CELL values alone -- what the reference itself persists: Solver::readLatestCgnsFlowSolution
+// (US/Solver.cpp:544-581) reads the cell fields of a restart file and re-derives every face value.  Given the owned
+// cells of u and p on the device and the time step dtPrev of the step that produced them, rebuild p's ghosts and
+// boundary faces, gradP, and the face velocities exactly as phb_fs_step left them:
+//   u* = u + dtPrev grad p (cells) -> interpolateFaces -> faces - dtPrev (grad p)_f    (FIXED boundary faces keep
+// their boundary values), the cells themselves untouched.  dtPrev = 0 (state at rest / unknown): plain interpolation,
+// the reference's own restart.
+int phb_fs_rebuild_faces(phb_fracstep *fs, double dtPrev) {
+  PHB_REQUIRE(fs && dtPrev >= 0., "phb_fs_rebuild_faces: bad argument");
+  phb_ctx *c = fs->m->ctx;
+  PHB_CHECK(phb::field_send_messages(fs->p));
+  PHB_CHECK(phb::field_set_boundary_faces(fs->p));
+  PHB_CHECK(phb::field_gradient(fs->p, fs->gradP));
+  const size_t len = fs->u->cells.n;
+  PHB_CHECK(fs->uSave.alloc(len));
+  PHB_CUDA(cudaMemcpyAsync(fs->uSave.p, fs->u->cells.p, len * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (dtPrev > 0.) PHB_CHECK(phb::field_axpy_cells(fs->u, dtPrev, fs->gradP));
+  PHB_CHECK(phb::field_send_messages(fs->u));
+  PHB_CHECK(phb::field_interpolate_faces(fs->u));
+  PHB_CUDA(cudaMemcpyAsync(fs->u->cells.p, fs->uSave.p, len * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  PHB_CHECK(phb::field_send_messages(fs->u));
+  if (dtPrev > 0.) {
+    PHB_CHECK(phb::field_face_types(fs->u));
+    const long long nF = fs->m->nFaces;
+    const int g = (int)std::max<long long>(1, std::min<long long>((nF + 255) / 256, (long long)c->numSMs * 8));
+    PHB_LAUNCH(c, k_axpy_faces_nonfixed, g, 256, 0, nF, 2, (const int *)fs->u->dFaceType.p, -dtPrev,
+               (const double *)fs->gradP->faces.p, fs->u->faces.p);
   }
   return phb::launch_status(c);
 }

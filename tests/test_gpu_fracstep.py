@@ -108,6 +108,40 @@ def test_cavity_with_amg_pressure_solve(comm, kind, nx, ny, upc):
     gfs.close(); g.close()
 
 
+@pytest.mark.parametrize("kind,nx,ny", [("rect", 40, 32), ("tri", 16, 18)])
+def test_state_from_cells_alone(comm, kind, nx, ny):
+    """phb_fs_rebuild_faces: a time step continued from the CELL values of u and p alone (what the reference's restart
+    persists, US/Solver.cpp:544-581) reproduces the device-resident run: every step of the second solver starts from
+    host copies of the cells, with the interior face velocities, p's faces and gradP overwritten by garbage first."""
+    from phase_b200.api import FiniteVolumeGrid2D as G, lid_driven_cavity
+    g = (G.rectilinear if kind == "rect" else G.triangulated)(comm, nx, ny, 1.0, 1.0)
+    keys = dict(tolerance=1e-12, maxIters=20000, preconditioner="ilu0")
+    a, b = lid_driven_cavity(g, 1.0, 0.1, solver=keys), lid_driven_cavity(g, 1.0, 0.1, solver=keys)
+    interior = g.i32("faceR") >= 0
+    rng = np.random.default_rng(4)
+    dts = [0.5 / nx, 0.5 / nx, 0.35 / nx, 0.45 / nx, 0.45 / nx, 0.5 / nx]
+    prev = 0.0
+    for dt in dts:
+        a.solve(dt)
+        uc, pc = b.u.get("cells").copy(), b.p.get("cells").copy()          # "host-owned" state: cells only
+        uf = b.u.get("faces")
+        uf[:, interior] = rng.standard_normal((2, int(interior.sum())))    # everything else is lost
+        b.u.set("faces", uf.reshape(-1))
+        b.p.set("faces", rng.standard_normal(b.p.get("faces").shape))
+        b.gradP.set("cells", rng.standard_normal(b.gradP.get("cells").shape).reshape(-1))
+        b.gradP.set("faces", rng.standard_normal(b.gradP.get("faces").shape).reshape(-1))
+        b.u.set("cells", uc.reshape(-1)); b.p.set("cells", pc)
+        b.rebuildFaces(prev)
+        b.solve(dt)
+        prev = dt
+    for name in ("cells", "faces"):
+        ua, ub = a.u.get(name), b.u.get(name)
+        assert rel_l2(ub[0], ua[0]) < 1e-7 and rel_l2(ub[1], ua[1]) < 1e-7, name
+    pa, pb = a.p.get("cells"), b.p.get("cells")
+    assert rel_l2(pb - pb.mean(), pa - pa.mean()) < TOL
+    a.close(); b.close(); g.close()
+
+
 def test_cavity_bench_defaults_1m_cells(comm):
     """The configuration bench.py times -- V-cycle on both equations, single-precision cycle, default
     `amgCoarsest` (5 levels with a ~900-row dense tail at this size) -- at 1000x1000 cells for 3 steps against
