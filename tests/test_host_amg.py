@@ -174,6 +174,36 @@ def test_iterations_do_not_depend_on_the_row_length_of_the_mesh():
     assert counts[4000, "old"] >= counts[4000, "new"] + 2, counts
 
 
+def test_smoother_weights_keep_jacobi_a_contraction():
+    """`amgCoarseSmootherWeight` / lambda_est on the Galerkin levels: the power-iteration estimate approaches lambda_max
+    from below, so the weight must stay safely under 2 / lambda_max(D^-1 A) (the Jacobi sweep would amplify the top modes
+    otherwise) and -- the point of the rule -- above the Gershgorin weight it replaces on these levels."""
+    nx, ny = 96, 192
+    x = (np.arange(nx) + .5) / nx
+    y = 2 * (np.arange(ny) + .5) / ny
+    X, Y = np.meshgrid(x, y)
+    rho = np.where((X - .5) ** 2 + (Y - .5) ** 2 < .125 ** 2, 1.0, 1000.).ravel()
+    idx = np.arange(nx * ny).reshape(ny, nx)
+    V = sp.csr_matrix((nx * ny, nx * ny))
+    for a, b in ((idx[:, :-1].ravel(), idx[:, 1:].ravel()), (idx[:-1, :].ravel(), idx[1:, :].ravel())):
+        w = 1. / (0.5 * (rho[a] + rho[b]))
+        V = V + sp.coo_matrix((np.r_[-w, -w, w, w], (np.r_[a, b, a, b], np.r_[b, a, a, b])), shape=V.shape)
+    for A in (neumann_laplacian(150, 120), neumann_laplacian(90, 70, fixed_left=True), V.tocsr()):
+        H = HostAmg(A, coarsest=60)
+        assert H.nLevels >= 3
+        for l in range(1, H.nLevels - 1):
+            M, rho_g = H.mat(l, 0)
+            d = M.diagonal()
+            Dh = sp.diags(1. / np.sqrt(np.abs(d)))
+            S = (Dh @ M @ Dh).tocsc() * np.sign(d[0])          # symmetric, same spectrum as D^-1 A
+            lam = float(spla.eigsh(S, k=1, which="LA", return_eigenvectors=False, tol=1e-8)[0])
+            f = H.weight_scale(l)
+            assert f * lam < 1.9, (l, f, lam)                   # contraction on every mode, with a margin
+            assert f > 1.8 / rho_g, (l, f, rho_g)               # on these Galerkin levels stronger than the rule it replaces
+            assert abs(f - 1.6 / min(rho_g, max(0.5 * rho_g, 1.05 * lam))) < 0.1 * f, (l, f, lam)   # the estimate is close
+        H.close()
+
+
 def test_variable_coefficient_and_threshold():
     """density ratio 815 (config 4's pEqn): both theta = 0 and the classical 0.08 give a usable hierarchy"""
     nx, ny = 96, 192
