@@ -585,7 +585,7 @@ int solver_run(phb_solver *s, int *iters, double *relres) {
     // With the multigrid preconditioner a solve is a handful of iterations and every poll leaves the GPU idle for a host
     // round trip plus a graph launch: the first poll waits until one iteration short of what this solver needed last
     // time (kernels past convergence leave on the device-side test, so overshooting costs empty launches only)
-    if (amg && graphOk && s->lastIters > K) burst = std::max(1, (s->lastIters - 1) / K);
+    if (amg && graphOk && s->lastIters > K) burst = std::min(8, std::max(1, (s->lastIters - 1) / K));   // at most 16 iterations blind
     bool done = false, midRefresh = false;
     while (!done && launched < budget) {
       for (int g = 0; g < burst && launched < budget; ++g) {
